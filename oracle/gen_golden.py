@@ -1,0 +1,135 @@
+"""Generate golden vectors by executing the UNMODIFIED reference module (build container only).
+
+Usage (in the build container, where /root/reference exists):
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference's `forward` hard-codes `.cuda()` (adaptive_stereo/models/stereo_net.py:129,177), so on this
+GPU-less host `Tensor.cuda` / `Module.cuda` are shimmed to identity.  The reference modules are
+loaded by file path; weights and inputs come from the seeded generators in oracle/stereonet_oracle.py so the
+fixtures only need to hold OUTPUTS (plus checksums of the regenerated inputs to detect RNG drift).
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import stereonet_oracle as O  # noqa: E402
+
+REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# name: (B, H, W, k, input_scale, sharpen, with_train)
+CASES = {
+  "k3_small_dgtw":   dict(B=1, H=64, W=128, k=3, s=0, sharpen=1.0, train=False),    # D'=24 > W'=16
+  "k3_b2_sharp":     dict(B=2, H=96, W=256, k=3, s=0, sharpen=40.0, train=True),
+  "k4_sharp":        dict(B=1, H=64, W=256, k=4, s=0, sharpen=40.0, train=False),   # D'=12
+  "k3_ragged":       dict(B=1, H=68, W=120, k=3, s=0, sharpen=40.0, train=True),    # 68->34->17->9 rows
+  "k3_scale1":       dict(B=1, H=48, W=96,  k=3, s=1, sharpen=40.0, train=False),   # D'=12 via input_scale
+}
+
+
+def _load(name, rel):
+  spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  return mod
+
+
+def load_reference():
+  torch.Tensor.cuda = lambda self, *a, **k: self
+  torch.nn.Module.cuda = lambda self, *a, **k: self
+  sn = _load("ref_stereo_net", "adaptive_stereo/models/stereo_net.py")
+  lw = _load("ref_linear_warping", "adaptive_stereo/models/linear_warping.py")
+  # loss_functions imports nothing from the package at module level
+  lf = _load("ref_loss_functions", "adaptive_stereo/utils/loss_functions.py")
+  fc = _load("ref_feature_contrast", "adaptive_stereo/utils/feature_contrast.py")
+  return sn, lw, lf, fc
+
+
+def summarize(t: torch.Tensor):
+  t = t.detach().double().flatten()
+  return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().sqrt().item()], dtype=np.float64)
+
+
+def run_case(name, cfg, sn, lw, lf, fc):
+  B, H, W, k, s = cfg["B"], cfg["H"], cfg["W"], cfg["k"], cfg["s"]
+  fsd = O.make_feature_state(k, seed=11)
+  ssd = O.make_stereo_state(seed=22, sharpen=cfg["sharpen"])
+  left, right, gt = O.make_stereo_pair(B, H, W, seed=1000, max_disp_px=min(60.0, W / 4))
+  out = {"in_left_sum": summarize(left), "in_right_sum": summarize(right),
+         "w_feat_sum": summarize(torch.cat([v.flatten().float() for v in fsd.values()])),
+         "w_stereo_sum": summarize(torch.cat([v.flatten().float() for v in ssd.values()]))}
+
+  fnet = sn.FeatureExtractorNetwork(k)
+  snet = sn.StereoNet(k, 1, s, maxdisp=192)
+  fnet.load_state_dict(fsd, strict=True)
+  snet.load_state_dict(ssd, strict=True)
+
+  # ---- eval / no-grad forward (train.process_batch, train.py:19-22)
+  fnet.eval(); snet.eval()
+  with torch.no_grad():
+    fl, fr = fnet(left), fnet(right)
+    o = snet(left, fl, fr, "l", output_cost_volume=True)
+  out["eval/left_features"] = fl.numpy()
+  out["eval/right_features"] = fr.numpy()
+  for key, v in o.items():
+    out["eval/" + key] = v.numpy()
+  out["eval/fcs"] = fc.feature_contrast_mean(o[f"cost_volume_l/{s + k}"]).mean().numpy()
+  out["eval/epe"] = torch.abs(o[f"pred_disp_l/{s}"] - gt)[gt > 0].mean().numpy()
+
+  if cfg["train"]:
+    # ---- one adaptation step exactly as adapt.py:313-337,381-394 (Adam lr 5e-5, clip on stereo_net only)
+    fnet.train(); snet.train()
+    opt = torch.optim.Adam([{"params": snet.parameters()}, {"params": fnet.parameters()}], lr=5e-5)
+    warper = lw.LinearWarping(H, W, torch.device("cpu"))
+    fl, fr = fnet(left), fnet(right)
+    o = snet(left, fl, fr, "l", output_cost_volume=True)
+    lw_img, mask = warper(right, o[f"pred_disp_l/{s}"], right_to_left=True)
+    loss = lf.monodepth_loss(o[f"pred_disp_l/{s}"], left, lw_img, smoothness_weight=1e-3)[0][mask].mean()
+    opt.zero_grad()
+    loss.backward()
+    out["train/loss"] = loss.detach().numpy()
+    out["train/left_features"] = fl.detach().numpy()
+    for key, v in o.items():
+      out["train/" + key] = v.detach().numpy()
+    for tag, net in (("s", snet), ("f", fnet)):
+      for n, p in net.named_parameters():
+        if p.grad is None:
+          out[f"grad_none/{tag}/{n}"] = np.array(1)
+        else:
+          out[f"grad_sum/{tag}/{n}"] = summarize(p.grad)
+          if p.grad.numel() <= 1024:
+            out[f"grad/{tag}/{n}"] = p.grad.numpy().copy()
+    # a few full-size gradients for direct comparison
+    out["grad/s/filter.0.0.0.weight"] = snet.filter[0][0][0].weight.grad.numpy().copy()
+    out["grad/f/downsample.0.weight"] = fnet.downsample[0].weight.grad.numpy().copy()
+    out["grad/f/conv_alone.weight"] = fnet.conv_alone.weight.grad.numpy().copy()
+    out["train/grad_norm_stereo"] = torch.nn.utils.clip_grad_norm_(snet.parameters(), 1.0).numpy()
+    opt.step()
+    for tag, net in (("s", snet), ("f", fnet)):
+      for n, v in net.state_dict().items():
+        if "running_" in n or "num_batches" in n:
+          out[f"post/{tag}/{n}"] = v.numpy().copy()
+        else:
+          out[f"post_sum/{tag}/{n}"] = summarize(v)
+    out["post/s/conv3d_alone.weight"] = snet.conv3d_alone.weight.detach().numpy().copy()
+    out["post/f/conv_alone.bias"] = fnet.conv_alone.bias.detach().numpy().copy()
+
+  os.makedirs(OUT, exist_ok=True)
+  np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+  c = out[f"eval/cost_volume_l/{s + k}"]
+  print(f"{name}: cost range [{c.min():.2f}, {c.max():.2f}] fcs {out['eval/fcs']:.3f} epe {out['eval/epe']:.3f} "
+        f"disp mean {out[f'eval/pred_disp_l/{s}'].mean():.3f} std {out[f'eval/pred_disp_l/{s}'].std():.3f}"
+        + (f" loss {out['train/loss']:.5f} gnorm {out['train/grad_norm_stereo']:.4f}" if cfg["train"] else ""))
+
+
+if __name__ == "__main__":
+  torch.manual_seed(123)
+  torch.set_num_threads(8)
+  mods = load_reference()
+  for name, cfg in CASES.items():
+    run_case(name, cfg, *mods)
