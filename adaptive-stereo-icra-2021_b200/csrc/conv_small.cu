@@ -1,0 +1,180 @@
+// Small-Cin first-layer convolutions (Cin = 3 or 4 -> 32), direct fp32, NCHW image in, channels-last out.
+//  * snb_conv5x5s2_c3   : FeatureExtractorNetwork.downsample[0], stereo_net.py:64-70,81 (K = 75, too thin for MMA)
+//  * snb_refine_in_conv : EdgeAwareRefinement head, stereo_net.py:105-117: bilinear upsample + scale + concat + 3x3 conv
+// CTA = 256 threads = 8 x 64 output pixels; every thread owns 2 pixels x 32 couts (64 accumulators); the input halo tile
+// sits in smem (column-parity de-interleaved for stride 2 so reads are conflict free), weights are broadcast LDS.128.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TH = 8, TW = 64;
+
+template <int CIN, int KS, int S>
+struct TileDims {
+  static constexpr int IH = (TH - 1) * S + KS;
+  static constexpr int IW = (TW - 1) * S + KS;
+  static constexpr int IWP = (S == 2) ? ((IW + 1) / 2 + 1) : IW + 1;       // per-parity row pitch (+1 pad)
+  static constexpr int ROW = (S == 2) ? 2 * IWP : IWP;
+  static constexpr int IN_FLOATS = CIN * IH * ROW;
+  static constexpr int W_FLOATS = CIN * KS * KS * 32;
+  static constexpr int SMEM_BYTES = (IN_FLOATS + W_FLOATS + 64 * 8) * 4;
+};
+
+template <int S, int IWP>
+__device__ __forceinline__ int col_index(int c) { return (S == 2) ? (c & 1) * IWP + (c >> 1) : c; }
+
+struct ImgLoader {          // plain NCHW image
+  const float* img; int C, H, W;
+  __device__ __forceinline__ float operator()(int b, int ci, int iy, int ix) const {
+    if ((unsigned)iy >= (unsigned)H || (unsigned)ix >= (unsigned)W) return 0.f;
+    return img[(((size_t)b * C + ci) * H + iy) * W + ix];
+  }
+};
+
+struct RefineLoader {       // channel 0 = scale * bilinear(coarse), channels 1..3 = rgb (stereo_net.py:105-117)
+  const float* coarse; const float* rgb; int h, w, H, W; float sh, sw, mul;
+  __device__ __forceinline__ float operator()(int b, int ci, int iy, int ix) const {
+    if ((unsigned)iy >= (unsigned)H || (unsigned)ix >= (unsigned)W) return 0.f;
+    if (ci == 0) return bilinear_sample(coarse + (size_t)b * h * w, h, w, iy, ix, sh, sw) * mul;
+    return rgb[(((size_t)b * 3 + (ci - 1)) * H + iy) * W + ix];
+  }
+};
+
+template <int CIN, int KS, int S, class Loader>
+__global__ void __launch_bounds__(256)
+conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y, float* __restrict__ up_out,
+                  int OH, int OW, int pad, snb_conv_epilogue e) {
+  using T = TileDims<CIN, KS, S>;
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;
+  float* sW = smem + T::IN_FLOATS;             // [k][32], k = (ci*KS + kh)*KS + kw
+  float* sRed = sW + T::W_FLOATS;              // [8 warps][64]
+  const int t = threadIdx.x;
+  const int tiles_x = (OW + TW - 1) / TW, tiles_y = (OH + TH - 1) / TH;
+  const int tile = blockIdx.x;
+  const int b = tile / (tiles_x * tiles_y);
+  const int trem = tile - b * tiles_x * tiles_y;
+  const int oy0 = (trem / tiles_x) * TH, ox0 = (trem % tiles_x) * TW;
+  const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
+
+  for (int i = t; i < CIN * T::IH * T::IW; i += 256) {
+    const int c = i % T::IW;
+    const int r = (i / T::IW) % T::IH;
+    const int ci = i / (T::IW * T::IH);
+    sIn[(ci * T::IH + r) * T::ROW + col_index<S, T::IWP>(c)] = ld(b, ci, iy0 + r, ix0 + c);
+  }
+  for (int i = t; i < T::W_FLOATS; i += 256) {   // w is [32][CIN][KS][KS]
+    const int co = i / (CIN * KS * KS);
+    const int k = i - co * (CIN * KS * KS);
+    sW[k * 32 + co] = w[i];
+  }
+  __syncthreads();
+
+  const int ty = t >> 5, tx = t & 31;
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+  for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+      const float* rowp = sIn + (ci * T::IH + ty * S + kh) * T::ROW;
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) {
+        const float x0 = rowp[col_index<S, T::IWP>(tx * S + kw)];
+        const float x1 = rowp[col_index<S, T::IWP>((tx + 32) * S + kw)];
+        const float4* wp = reinterpret_cast<const float4*>(sW + ((ci * KS + kh) * KS + kw) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wv = wp[j];
+          acc0[4 * j + 0] = fmaf(x0, wv.x, acc0[4 * j + 0]); acc1[4 * j + 0] = fmaf(x1, wv.x, acc1[4 * j + 0]);
+          acc0[4 * j + 1] = fmaf(x0, wv.y, acc0[4 * j + 1]); acc1[4 * j + 1] = fmaf(x1, wv.y, acc1[4 * j + 1]);
+          acc0[4 * j + 2] = fmaf(x0, wv.z, acc0[4 * j + 2]); acc1[4 * j + 2] = fmaf(x1, wv.z, acc1[4 * j + 2]);
+          acc0[4 * j + 3] = fmaf(x0, wv.w, acc0[4 * j + 3]); acc1[4 * j + 3] = fmaf(x1, wv.w, acc1[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  const int oy = oy0 + ty;
+  const int oxa = ox0 + tx, oxb = ox0 + tx + 32;
+  const bool oka = oy < OH && oxa < OW, okb = oy < OH && oxb < OW;
+
+  if (up_out != nullptr) {   // side output: the upsampled+scaled disparity plane (centre tap of input channel 0)
+    const float* rowp = sIn + (0 * T::IH + ty * S + pad) * T::ROW;
+    if (oka) up_out[((size_t)b * OH + oy) * OW + oxa] = rowp[col_index<S, T::IWP>(tx * S + pad)];
+    if (okb) up_out[((size_t)b * OH + oy) * OW + oxb] = rowp[col_index<S, T::IWP>((tx + 32) * S + pad)];
+  }
+
+  // z = conv + bias ; per-channel partial stats over valid pixels
+  float s1 = 0.f, s2 = 0.f;   // lane j of a warp ends up owning channel j
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float bj = e.bias ? e.bias[j] : 0.f;
+    acc0[j] += bj; acc1[j] += bj;
+    if (e.stats) {
+      float a = (oka ? acc0[j] : 0.f) + (okb ? acc1[j] : 0.f);
+      float q = (oka ? acc0[j] * acc0[j] : 0.f) + (okb ? acc1[j] * acc1[j] : 0.f);
+      a = warp_sum(a); q = warp_sum(q);
+      if (tx == j) { s1 = a; s2 = q; }
+    }
+  }
+  if (e.stats) {
+    sRed[ty * 64 + tx] = s1; sRed[ty * 64 + 32 + tx] = s2;
+    __syncthreads();
+    if (t < 64) {
+      float a = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) a += sRed[wv * 64 + t];
+      e.stats[(size_t)blockIdx.x * 64 + t] = a;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (e.scale) { const float sc = e.scale[j], sh = e.shift[j]; acc0[j] = fmaf(acc0[j], sc, sh); acc1[j] = fmaf(acc1[j], sc, sh); }
+    if (e.lrelu) { acc0[j] = lrelu(acc0[j]); acc1[j] = lrelu(acc1[j]); }
+  }
+  if (oka) {
+    float4* yp = reinterpret_cast<float4*>(y + (((size_t)b * OH + oy) * OW + oxa) * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yp[j] = make_float4(acc0[4 * j], acc0[4 * j + 1], acc0[4 * j + 2], acc0[4 * j + 3]);
+  }
+  if (okb) {
+    float4* yp = reinterpret_cast<float4*>(y + (((size_t)b * OH + oy) * OW + oxb) * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yp[j] = make_float4(acc1[4 * j], acc1[4 * j + 1], acc1[4 * j + 2], acc1[4 * j + 3]);
+  }
+}
+
+}  // namespace
+
+extern "C" int snb_conv5x5s2_c3(const float* img, const float* w, const float* bias, float* y, int B, int H, int W, void* stream) {
+  SNB_REQUIRE(img && w && y && B > 0 && H > 0 && W > 0, "snb_conv5x5s2_c3: bad args");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;      // floor((n + 2*2 - 5)/2) + 1
+  using T = TileDims<3, 5, 2>;
+  ImgLoader ld{img, 3, H, W};
+  snb_conv_epilogue e{bias, nullptr, nullptr, nullptr, nullptr, 0};
+  auto kern = conv_small_kernel<3, 5, 2, ImgLoader>;
+  SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  const int tiles = B * ((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
+  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, y, nullptr, OH, OW, 2, e);
+  SNB_LAUNCH_CHECK("conv5x5s2_c3");
+  return 0;
+}
+
+extern "C" int snb_refine_in_conv_num_tiles(int B, int H, int W) {
+  return B * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+}
+
+extern "C" int snb_refine_in_conv(const float* coarse, const float* rgb, const float* w, float* up, float* z,
+                                  int B, int h, int w_, int H, int W, float disp_scale, const snb_conv_epilogue* e, void* stream) {
+  SNB_REQUIRE(coarse && rgb && w && up && z && e && B > 0 && h > 0 && w_ > 0 && H > 0 && W > 0, "snb_refine_in_conv: bad args");
+  using T = TileDims<4, 3, 1>;
+  RefineLoader ld{coarse, rgb, h, w_, H, W, (float)h / (float)H, (float)w_ / (float)W, disp_scale};
+  auto kern = conv_small_kernel<4, 3, 1, RefineLoader>;
+  SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  const int tiles = snb_refine_in_conv_num_tiles(B, H, W);
+  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, z, up, H, W, 1, *e);
+  SNB_LAUNCH_CHECK("refine_in_conv");
+  return 0;
+}

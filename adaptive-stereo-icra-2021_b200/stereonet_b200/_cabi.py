@@ -1,0 +1,63 @@
+"""ctypes binding of libsnb200.so (include/snb200.h).  Fails loudly when the library is missing: there is no fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SNB200_LIB", os.path.join(os.path.dirname(_HERE), "libsnb200.so"))
+
+
+class ConvGeom(C.Structure):
+  _fields_ = [(n, C.c_int) for n in ("B", "D", "H", "W", "OD", "OH", "OW", "KD", "KH", "KW", "stride", "dil", "pd", "ph", "pw")]
+
+
+class ConvEpilogue(C.Structure):
+  _fields_ = [("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
+              ("stats", C.c_void_p), ("lrelu", C.c_int)]
+
+
+_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_GP, _EP = C.POINTER(ConvGeom), C.POINTER(ConvEpilogue)
+
+# name -> (restype, argtypes); every symbol include/snb200.h declares
+SIGNATURES = {
+  "snb_last_error": (C.c_char_p, []),
+  "snb_version": (_I, []),
+  "snb_conv_c32_num_tiles": (_I, [_GP]),
+  "snb_prep_conv_weights": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+  "snb_cost_volume_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+  "snb_cost_volume_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+  "snb_conv_c32": (_I, [_P, _P, _P, _GP, _EP, _P]),
+  "snb_conv5x5s2_c3": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+  "snb_refine_in_conv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _EP, _P]),
+  "snb_refine_in_conv_num_tiles": (_I, [_I, _I, _I]),
+  "snb_conv_c32_taps": (_I, [_P, _P, _P, _LL, _I, _I, _P]),
+  "snb_tapsum_softargmin": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+  "snb_tapsum_refine_out": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+  "snb_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
+  "snb_upsample_bilinear_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
+  "snb_bn_finalize": (_I, [_P, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+  "snb_bn_apply": (_I, [_P, _P, _P, _P, _P, _LL, _I, _P]),
+}
+
+_lib = None
+
+
+def lib():
+  """Load (once) and return the C-ABI library."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RuntimeError(
+          f"stereonet_b200: {LIB_PATH} is missing. Build it with `python adaptive-stereo-icra-2021_b200/build.py` "
+          "(nvcc, sm_100a). There is no CPU / eager fallback for this path.")
+    l = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+      fn = getattr(l, name)
+      fn.restype, fn.argtypes = res, args
+    _lib = l
+  return _lib
+
+
+def check(rc, what):
+  if rc != 0:
+    raise RuntimeError(f"{what} failed: {lib().snb_last_error().decode()}")

@@ -1,0 +1,135 @@
+"""Fused layer entry points used by the nn.Modules: pick the no-grad (inference / validation) kernels or the
+autograd.Function wrappers (adaptation step) and keep the derived-tensor caches (repacked weights, folded BN)."""
+import torch
+
+from .. import ops
+
+# (id(param)) -> (version, derived tensor).  Keyed on the parameter's in-place version counter so an optimizer step
+# (adapt.py:393) invalidates the entry; holds only derived read-only tensors.
+_CACHE = {}
+
+
+def _cached(key, tensors, make):
+  ver = tuple((t.data_ptr(), t._version) for t in tensors)
+  hit = _CACHE.get(key)
+  if hit is not None and hit[0] == ver:
+    return hit[1]
+  val = make()
+  _CACHE[key] = (ver, val)
+  return val
+
+
+def clear_cache():
+  _CACHE.clear()
+
+
+def wprep(conv, mode=0):
+  return _cached((id(conv), "w", mode), [conv.weight], lambda: ops.prep_conv_weights(conv.weight, mode))
+
+
+def bn_fold(bn):
+  """Eval-mode BatchNorm as per-channel scale/shift (running statistics, eps 1e-5)."""
+  def make():
+    with torch.no_grad():
+      scale = bn.weight * torch.rsqrt(bn.running_var + ops.BN_EPS)
+      shift = bn.bias - bn.running_mean * scale
+      return scale.contiguous(), shift.contiguous()
+  return _cached((id(bn), "fold"), [bn.weight, bn.bias, bn.running_mean, bn.running_var], make)
+
+
+def _needs_grad(*tensors_or_modules):
+  if not torch.is_grad_enabled():
+    return False
+  for t in tensors_or_modules:
+    if isinstance(t, torch.Tensor):
+      if t.requires_grad:
+        return True
+    elif t is not None:
+      if any(p.requires_grad for p in t.parameters()):
+        return True
+  return False
+
+
+def _no_backward():
+  raise NotImplementedError("stereonet_b200: backward kernels are not wired for this op yet; "
+                            "run under torch.no_grad() (there is no eager fallback)")
+
+
+# ------------------------------------------------------------------------------------------------ feature extractor
+def conv5x5s2_first(img, conv):
+  if _needs_grad(conv):
+    from . import functions
+    return functions.Conv5x5s2First.apply(img, conv.weight, conv.bias)
+  return ops.conv5x5s2_c3(img, conv.weight, conv.bias)
+
+
+def conv_plain(x, conv, ksize, stride):
+  """Conv2d 32->32 with bias only (downsample[1:], conv_alone)."""
+  g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
+  if _needs_grad(x, conv):
+    from . import functions
+    return functions.ConvC32.apply(x, conv.weight, conv.bias, ksize, stride, 1)
+  y, _ = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach())
+  return y
+
+
+# ------------------------------------------------------------------------------------------------ conv + BN + LeakyReLU
+def conv_bn_lrelu(x, conv, bn, dil, residual, training):
+  """[x +] LeakyReLU(BN(conv(x))) for 3x3 (2-D, dilated) and 3x3x3 convs (stereo_net.py:8-18,21-30,44-51,155-160)."""
+  g = ops.geom(x.shape, 3, stride=1, dil=dil)
+  if _needs_grad(x, conv, bn):
+    from . import functions
+    return functions.conv_bn_lrelu_autograd(x, conv, bn, dil, residual, training)
+  if not training:
+    scale, shift = bn_fold(bn)
+    y, _ = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach(), scale=scale, shift=shift,
+                        residual=x if residual else None, lrelu=True)
+    return y
+  z, stats = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach(), want_stats=True)
+  scale, shift, _, _ = ops.bn_finalize(stats, z.numel() // 32, bn)
+  return ops.bn_apply(z, scale, shift, residual=x if residual else None, lrelu=True)
+
+
+# ------------------------------------------------------------------------------------------------ stereo head
+def cost_volume(left, right, D):
+  if _needs_grad(left, right):
+    from . import functions
+    return functions.CostVolume.apply(left, right, D)
+  return ops.cost_volume(left, right, D)
+
+
+def conv3d_out_softargmin(x, conv, want_cost):
+  if _needs_grad(x, conv):
+    from . import functions
+    return functions.conv3d_out_softargmin_autograd(x, conv, want_cost)
+  taps = ops.conv_c32_taps(x, conv.weight, 27)
+  return ops.tapsum_softargmin(taps, conv.bias, want_cost)
+
+
+def upsample(pred, H, W, mul):
+  if _needs_grad(pred):
+    from . import functions
+    return functions.Upsample.apply(pred, H, W, mul)
+  return ops.upsample_bilinear(pred, H, W, mul)
+
+
+# ------------------------------------------------------------------------------------------------ refinement
+def refine_head(coarse, rgb, conv, bn, training):
+  if _needs_grad(coarse, conv, bn):
+    from . import functions
+    return functions.refine_head_autograd(coarse, rgb, conv, bn, training)
+  if not training:
+    scale, shift = bn_fold(bn)
+    up, x, _ = ops.refine_in_conv(coarse, rgb, conv.weight, conv.bias.detach(), scale=scale, shift=shift, lrelu=True)
+    return up, x
+  up, z, stats = ops.refine_in_conv(coarse, rgb, conv.weight, conv.bias.detach(), want_stats=True)
+  scale, shift, _, _ = ops.bn_finalize(stats, z.numel() // 32, bn)
+  return up, ops.bn_apply(z, scale, shift, residual=None, lrelu=True)
+
+
+def refine_tail(x, conv, up):
+  if _needs_grad(x, conv, up):
+    from . import functions
+    return functions.refine_tail_autograd(x, conv, up)
+  taps = ops.conv_c32_taps(x, conv.weight, 9)
+  return ops.tapsum_refine_out(taps, conv.bias, up)

@@ -1,0 +1,213 @@
+"""Thin torch-tensor wrappers over the C-ABI (libsnb200.so).  Device memory, streams and shapes are handled here;
+every arithmetic instruction runs in the library's CUDA kernels.  Activations are contiguous channels-last fp32
+tensors: [B,H,W,32] or [B,D,H,W,32]."""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import ConvEpilogue, ConvGeom, check
+
+BN_EPS = 1e-5        # nn.BatchNorm2d/3d defaults used by the reference (stereo_net.py:17,29)
+BN_MOMENTUM = 0.1
+
+LAUNCHES = 0         # number of library kernels launched (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+  global LAUNCHES
+  LAUNCHES += n
+
+
+def _p(t):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+  return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _req(t, name, ndim=None):
+  if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+    raise RuntimeError(f"stereonet_b200: `{name}` must be a contiguous fp32 CUDA tensor "
+                       f"(got {type(t).__name__} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)})")
+  if ndim is not None and t.dim() != ndim:
+    raise RuntimeError(f"stereonet_b200: `{name}` must have {ndim} dims, got {tuple(t.shape)}")
+  return t
+
+
+def geom(x_shape, ksize, stride=1, dil=1, pad=None):
+  """ConvGeom for a channels-last input of shape [B,H,W,32] (2-D) or [B,D,H,W,32] (3-D), cubic/square kernel."""
+  three_d = len(x_shape) == 5
+  if three_d:
+    B, D, H, W, _ = x_shape
+  else:
+    B, H, W, _ = x_shape
+    D = 1
+  if pad is None:
+    pad = dil * (ksize - 1) // 2
+  OH = (H + 2 * pad - dil * (ksize - 1) - 1) // stride + 1
+  OW = (W + 2 * pad - dil * (ksize - 1) - 1) // stride + 1
+  g = ConvGeom(B, D, H, W, D, OH, OW, ksize if three_d else 1, ksize, ksize, stride, dil, 1 if three_d else 0, pad, pad)
+  if three_d:
+    g.OD = D + 2 * 1 - (ksize - 1) - 1 + 1
+  return g
+
+
+def out_shape(g, three_d):
+  return (g.B, g.OD, g.OH, g.OW, 32) if three_d else (g.B, g.OH, g.OW, 32)
+
+
+def prep_conv_weights(w, mode=0):
+  """[Cout,Cin,*k] -> [taps,Cin,Cout] (mode 0) or the flipped/transposed data-gradient layout (mode 1)."""
+  w = _req(w.detach().contiguous(), "weight")
+  cout, cin = w.shape[0], w.shape[1]
+  taps = w[0, 0].numel()
+  out = torch.empty((taps, cin, cout) if mode == 0 else (taps, cout, cin), device=w.device, dtype=torch.float32)
+  check(_cabi.lib().snb_prep_conv_weights(_p(w), _p(out), cout, cin, taps, mode, _stream(w)), "snb_prep_conv_weights")
+  _count()
+  return out
+
+
+def cost_volume(left, right, D):
+  _req(left, "left_features", 4); _req(right, "right_features", 4)
+  B, H, W, Cc = left.shape
+  if Cc != 32 or right.shape != left.shape:
+    raise RuntimeError(f"stereonet_b200: feature maps must be [B,H,W,32] and equal-shaped, got {tuple(left.shape)} {tuple(right.shape)}")
+  cost = torch.empty((B, D, H, W, 32), device=left.device, dtype=torch.float32)
+  check(_cabi.lib().snb_cost_volume_fwd(_p(left), _p(right), _p(cost), B, D, H, W, _stream(left)), "snb_cost_volume_fwd")
+  _count()
+  return cost
+
+
+def cost_volume_bwd(dcost):
+  _req(dcost, "dcost", 5)
+  B, D, H, W, _ = dcost.shape
+  dl = torch.empty((B, H, W, 32), device=dcost.device, dtype=torch.float32)
+  dr = torch.empty_like(dl)
+  check(_cabi.lib().snb_cost_volume_bwd(_p(dcost), _p(dl), _p(dr), B, D, H, W, _stream(dcost)), "snb_cost_volume_bwd")
+  _count()
+  return dl, dr
+
+
+def conv_c32(x, wprep, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, out=None):
+  """32->32 convolution + fused epilogue.  Returns (y, stats) with stats = [ntiles,2,32] partial sums or None."""
+  three_d = x.dim() == 5
+  _req(x, "x"); _req(wprep, "wprep")
+  y = out if out is not None else torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
+  stats = None
+  if want_stats:
+    nt = _cabi.lib().snb_conv_c32_num_tiles(C.byref(g))
+    stats = torch.empty((nt, 2, 32), device=x.device, dtype=torch.float32)
+  if residual is not None:
+    _req(residual, "residual")
+    if residual.shape != y.shape:
+      raise RuntimeError("stereonet_b200: residual shape mismatch")
+  e = ConvEpilogue(_p(bias), _p(scale), _p(shift), _p(residual), _p(stats), 1 if lrelu else 0)
+  check(_cabi.lib().snb_conv_c32(_p(x), _p(wprep), _p(y), C.byref(g), C.byref(e), _stream(x)), "snb_conv_c32")
+  _count()
+  return y, stats
+
+
+def conv5x5s2_c3(img, w, bias):
+  _req(img, "rgb_img", 4)
+  B, Cc, H, W = img.shape
+  if Cc != 3:
+    raise RuntimeError(f"stereonet_b200: expected a [B,3,H,W] image, got {tuple(img.shape)}")
+  OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+  y = torch.empty((B, OH, OW, 32), device=img.device, dtype=torch.float32)
+  check(_cabi.lib().snb_conv5x5s2_c3(_p(img), _p(_req(w.detach(), "w")), _p(bias.detach()), _p(y), B, H, W, _stream(img)),
+        "snb_conv5x5s2_c3")
+  _count()
+  return y
+
+
+def refine_in_conv(coarse, rgb, w, bias, scale=None, shift=None, lrelu=False, want_stats=False):
+  """Fused upsample + scale + concat + Conv2d(4->32).  Returns (up [B,H,W], z [B,H,W,32], stats)."""
+  _req(coarse, "coarse_disparity", 3); _req(rgb, "guidance_rgb", 4)
+  B, h, w_ = coarse.shape
+  H, W = rgb.shape[-2:]
+  up = torch.empty((B, H, W), device=rgb.device, dtype=torch.float32)
+  z = torch.empty((B, H, W, 32), device=rgb.device, dtype=torch.float32)
+  stats = None
+  if want_stats:
+    nt = _cabi.lib().snb_refine_in_conv_num_tiles(B, H, W)
+    stats = torch.empty((nt, 2, 32), device=rgb.device, dtype=torch.float32)
+  e = ConvEpilogue(_p(bias), _p(scale), _p(shift), None, _p(stats), 1 if lrelu else 0)
+  check(_cabi.lib().snb_refine_in_conv(_p(coarse), _p(rgb), _p(_req(w.detach(), "w")), _p(up), _p(z), B, h, w_, H, W,
+                                       float(W) / float(w_), C.byref(e), _stream(rgb)), "snb_refine_in_conv")
+  _count()
+  return up, z, stats
+
+
+def conv_c32_taps(x, w, ntaps):
+  """Channel contraction of a 32->1 conv: x [B,(D),H,W,32] -> taps [B,(D),ntaps,H,W]."""
+  _req(x, "x")
+  H, W = x.shape[-3], x.shape[-2]
+  nslices = x.numel() // (32 * H * W)
+  taps = torch.empty(tuple(x.shape[:-3]) + (ntaps, H, W), device=x.device, dtype=torch.float32)
+  check(_cabi.lib().snb_conv_c32_taps(_p(x), _p(_req(w.detach(), "w")), _p(taps), nslices, H * W, ntaps, _stream(x)),
+        "snb_conv_c32_taps")
+  _count()
+  return taps
+
+
+def tapsum_softargmin(taps, bias, want_cost):
+  B, D, _, H, W = taps.shape
+  pred = torch.empty((B, H, W), device=taps.device, dtype=torch.float32)
+  cost = torch.empty((B, D, H, W), device=taps.device, dtype=torch.float32) if want_cost else None
+  check(_cabi.lib().snb_tapsum_softargmin(_p(taps), _p(bias.detach()), _p(cost), _p(pred), B, D, H, W, _stream(taps)),
+        "snb_tapsum_softargmin")
+  _count()
+  return cost, pred
+
+
+def tapsum_refine_out(taps, bias, up):
+  B, _, H, W = taps.shape
+  out = torch.empty((B, H, W), device=taps.device, dtype=torch.float32)
+  check(_cabi.lib().snb_tapsum_refine_out(_p(taps), _p(bias.detach()), _p(up), _p(out), B, H, W, _stream(taps)),
+        "snb_tapsum_refine_out")
+  _count()
+  return out
+
+
+def upsample_bilinear(x, H, W, mul):
+  _req(x, "x", 3)
+  B, h, w = x.shape
+  out = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+  check(_cabi.lib().snb_upsample_bilinear(_p(x), _p(out), B, h, w, H, W, float(mul), _stream(x)), "snb_upsample_bilinear")
+  _count()
+  return out
+
+
+def upsample_bilinear_bwd(dout, h, w, mul):
+  _req(dout, "dout", 3)
+  B, H, W = dout.shape
+  din = torch.empty((B, h, w), device=dout.device, dtype=torch.float32)
+  check(_cabi.lib().snb_upsample_bilinear_bwd(_p(dout), _p(din), B, h, w, H, W, float(mul), _stream(dout)),
+        "snb_upsample_bilinear_bwd")
+  _count()
+  return din
+
+
+def bn_finalize(stats, count, bn, update_running=True):
+  """Reduce conv-epilogue partials into per-channel scale/shift (+ mean, invstd); updates bn's running stats in place."""
+  dev = stats.device
+  out = torch.empty((4, 32), device=dev, dtype=torch.float32)
+  rm = bn.running_mean if update_running else None
+  rv = bn.running_var if update_running else None
+  check(_cabi.lib().snb_bn_finalize(_p(stats), stats.shape[0], int(count), _p(bn.weight.detach()), _p(bn.bias.detach()),
+                                    _p(rm), _p(rv), BN_MOMENTUM, BN_EPS, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                    _stream(stats)), "snb_bn_finalize")
+  _count()
+  if update_running and bn.num_batches_tracked is not None:
+    bn.num_batches_tracked += 1
+  return out[0], out[1], out[2], out[3]
+
+
+def bn_apply(z, scale, shift, residual=None, lrelu=True):
+  y = torch.empty_like(z)
+  check(_cabi.lib().snb_bn_apply(_p(z), _p(scale), _p(shift), _p(residual), _p(y), z.numel() // 32, 1 if lrelu else 0,
+                                 _stream(z)), "snb_bn_apply")
+  _count()
+  return y

@@ -1,0 +1,80 @@
+"""Inference engine: CUDA-graph replay of the whole forward (feature_net x2 + stereo_net) with static device buffers
+and pinned-host staging.  At batch 1 every kernel is 3-100 us, so per-launch host latency would otherwise dominate
+(SURVEY.md §7 step 7).  One engine per (process, GPU); the weights stay whatever the wrapped modules hold, so a graph
+must be re-captured (`invalidate()`) after the parameters are re-allocated (in-place optimizer updates are picked up
+through the derived-weight caches only on re-capture)."""
+import torch
+
+from . import ops
+
+
+class StereoEngine:
+  def __init__(self, feature_net, stereo_net, output_cost_volume=False, use_graph=True):
+    self.feature_net, self.stereo_net = feature_net, stereo_net
+    self.output_cost_volume = output_cost_volume
+    self.use_graph = use_graph
+    self._graphs = {}
+
+  def invalidate(self):
+    self._graphs.clear()
+
+  def _forward(self, left, right):
+    fl, fr = self.feature_net(left), self.feature_net(right)
+    return self.stereo_net(left, fl, fr, "l", output_cost_volume=self.output_cost_volume)
+
+  def _entry(self, shape, device):
+    key = (tuple(shape), str(device), self.feature_net.training)
+    e = self._graphs.get(key)
+    if e is not None:
+      return e
+    left = torch.zeros(shape, device=device, dtype=torch.float32)
+    right = torch.zeros(shape, device=device, dtype=torch.float32)
+    with torch.no_grad():
+      side = torch.cuda.Stream(device=device)
+      side.wait_stream(torch.cuda.current_stream(device))
+      with torch.cuda.stream(side):
+        for _ in range(2):                       # warm the derived-weight caches / allocator outside the capture
+          self._forward(left, right)
+      torch.cuda.current_stream(device).wait_stream(side)
+      n0 = ops.LAUNCHES
+      if self.use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+          out = self._forward(left, right)
+      else:
+        graph, out = None, self._forward(left, right)
+      launches = ops.LAUNCHES - n0
+    e = dict(left=left, right=right, graph=graph, out=out, launches=launches)
+    self._graphs[key] = e
+    return e
+
+  @torch.no_grad()
+  def run_static(self, shape, device):
+    """Replay on whatever currently sits in the static input buffers. Returns (outputs dict, launches per step)."""
+    e = self._entry(shape, device)
+    if e["graph"] is not None:
+      e["graph"].replay()
+    else:
+      e["out"] = self._forward(e["left"], e["right"])
+    return e["out"], e["launches"]
+
+  @torch.no_grad()
+  def __call__(self, left, right):
+    """Device tensors in, dict of device tensors out (valid until the next call)."""
+    e = self._entry(left.shape, left.device)
+    e["left"].copy_(left, non_blocking=True)
+    e["right"].copy_(right, non_blocking=True)
+    return self.run_static(left.shape, left.device)[0]
+
+  @torch.no_grad()
+  def infer_host(self, left_host, right_host, out_host, key=None):
+    """Host (pinned) images in, host (pinned) full-resolution disparity out; everything stream-ordered."""
+    dev = next(self.stereo_net.parameters()).device
+    e = self._entry(left_host.shape, dev)
+    e["left"].copy_(left_host, non_blocking=True)
+    e["right"].copy_(right_host, non_blocking=True)
+    out, _ = self.run_static(left_host.shape, dev)
+    if key is None:
+      key = "pred_disp_l/{}".format(self.stereo_net.input_scale)
+    out_host.copy_(out[key], non_blocking=True)
+    return out_host

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — StereoNet forward (BASELINE.json configs[1]: KITTI 376x1248, D=192, k=3, batch 1 per GPU).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores (oracle port)
+
+A step = one pass of the hot path over one synthetic stereo pair per GPU: feature_net(L), feature_net(R),
+stereo_net(L, fl, fr, 'l').  Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md §6).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "adaptive-stereo-icra-2021_b200")
+for p in (ROOT, PKG):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+H, W, K_DOWN, MAXDISP = 376, 1248, 3, 192
+METRIC = "StereoNet pairs/s @KITTI 376x1248 D=192"
+WORKLOAD = "StereoNet k=3 D=192 fp32 forward, KITTI 1x3x376x1248 per GPU (BASELINE.json configs[1])"
+
+
+def peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    d = json.load(open(path))
+    return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"), src="measured")
+  return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------- synthetic data
+def synthetic_pair(seed, h=H, w=W, batch=1):
+  """Textured left image, ground-plane disparity ramp, right = left warped by the known disparity.
+  Plain torch on the host; no oracle import on the product path."""
+  import torch.nn.functional as F
+  g = torch.Generator().manual_seed(seed)
+  noise = torch.randn((batch, 3, h, w), generator=g)
+  low = F.avg_pool2d(F.avg_pool2d(noise, 9, 1, 4), 9, 1, 4) * 6.0
+  left = (0.5 + 0.25 * low + 0.1 * torch.randn((batch, 3, h, w), generator=g)).clamp(0, 1)
+  ramp = 4.0 + 60.0 * torch.arange(h, dtype=torch.float32) / (h - 1)
+  rows, cols = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+  flow = torch.stack([cols, rows], dim=-1).float().expand(batch, -1, -1, -1).clone()
+  flow[..., 0] = flow[..., 0] + ramp.view(1, h, 1)
+  flow[..., 0] = (2 * flow[..., 0] / w) - 1.0
+  flow[..., 1] = (2 * flow[..., 1] / h) - 1.0
+  right = F.grid_sample(left, flow, mode="bilinear", padding_mode="border", align_corners=False)
+  return left.contiguous(), right.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+  Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], None, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx = float(r[1])
+        for n, v in zip(names, r[3:7]):
+          if v.lower().startswith("active"):
+            reasons.add(n)
+      except Exception:
+        pass
+    sm.sort()
+    # under load = upper half of the samples (the sampler also sees the idle gaps around the region)
+    med = sm[(len(sm) * 3) // 4] if sm else None
+    return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference(steps, warmup, budget_s):
+  """The reference algorithm (oracle port of adaptive_stereo/models/stereo_net.py) on the host cores, eval/no-grad,
+  same shapes and seeded weights as the GPU arm.  Each step = one KITTI-sized pair."""
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import stereonet_oracle as O
+  cores = os.cpu_count() or 1
+  try:
+    cores = len(os.sched_getaffinity(0))
+  except Exception:
+    pass
+  torch.set_num_threads(cores)
+  fsd, ssd = O.make_feature_state(K_DOWN, 11), O.make_stereo_state(22, sharpen=40.0)
+  left, right = synthetic_pair(1000)
+  done, t_total = 0, 0.0
+  with torch.no_grad():
+    for _ in range(warmup):
+      O.predict_disparity_left(fsd, ssd, left, right, K_DOWN)
+    t_begin = time.perf_counter()
+    while done < steps:
+      t0 = time.perf_counter()
+      O.predict_disparity_left(fsd, ssd, left, right, K_DOWN)
+      t_total += time.perf_counter() - t0
+      done += 1
+      if time.perf_counter() - t_begin > budget_s:
+        break
+  return dict(value=done / t_total, unit="pairs/s", cores=cores, kind="port", steps=done, ms_per_step=1e3 * t_total / done,
+              sample=f"{done} full forward passes of the oracle port (torch CPU fp32, {cores} threads) on one synthetic KITTI pair")
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def time_kernel(fn, iters, flush, stream):
+  """Average duration (ms) of fn() alone, L2 flushed before every launch, CUDA events on the launching stream."""
+  evs = []
+  for _ in range(3):
+    fn()
+  for _ in range(iters):
+    flush.zero_()                       # > L2 (126 MB): evicts the kernel's inputs/outputs
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream); fn(); b.record(stream)
+    evs.append((a, b))
+  torch.cuda.synchronize()
+  ts = sorted(a.elapsed_time(b) for a, b in evs)
+  return sum(ts) / len(ts), ts[len(ts) // 2]
+
+
+def gpu_arm(args):
+  import stereonet_b200 as S
+  from stereonet_b200 import ops
+  from stereonet_b200.autograd import fused
+  from stereonet_b200.runtime import StereoEngine
+  import torch.distributed as dist
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus and world > 1:
+    raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  torch.manual_seed(123)                                   # the reference's seed (adapt.py:29, train.py:141)
+  fnet = S.FeatureExtractorNetwork(K_DOWN).to(dev).eval()  # seeded random init of the reference architecture
+  snet = S.StereoNet(K_DOWN, 1, 0, maxdisp=MAXDISP).to(dev).eval()
+  engine = StereoEngine(fnet, snet, output_cost_volume=True, use_graph=not args.no_graph)
+
+  left, right = synthetic_pair(1000 + rank)
+  shape = tuple(left.shape)
+  left_pin, right_pin = left.pin_memory(), right.pin_memory()
+  out_pin = torch.empty((1, 1, H, W), dtype=torch.float32).pin_memory()
+  e = engine._entry(shape, dev)
+  e["left"].copy_(left_pin); e["right"].copy_(right_pin)
+  stream = torch.cuda.current_stream(dev)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- device-resident throughput: inputs already in HBM, K graph replays
+  for _ in range(max(args.warmup, 3)):
+    engine.run_static(shape, dev)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  barrier()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record(stream)
+  for _ in range(args.steps):
+    _, launches = engine.run_static(shape, dev)
+  ev1.record(stream)
+  barrier()
+  ms_dev = ev0.elapsed_time(ev1)
+
+  # ---- end to end through the public engine API: pinned host images in, host disparity out, every step
+  for _ in range(3):
+    engine.infer_host(left_pin, right_pin, out_pin)
+  barrier()
+  ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev2.record(stream)
+  for _ in range(args.steps):
+    engine.infer_host(left_pin, right_pin, out_pin)
+  ev3.record(stream)
+  barrier()
+  ms_e2e = ev2.elapsed_time(ev3)
+  clocks = sampler.stop() if rank == 0 else None
+
+  t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)              # max over ranks
+  ms_dev, ms_e2e = t.tolist()
+
+  result = None
+  if rank == 0:
+    pk = peaks()
+    # ---- per-kernel roofline numbers, each kernel timed alone with an L2 flush before every launch
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    hc, wc, D = (H - 1) // 8 + 1, (W - 1) // 8 + 1, (MAXDISP + 1) // 8
+    with torch.no_grad():
+      fl = torch.randn(1, hc, wc, 32, device=dev); fr = torch.randn(1, hc, wc, 32, device=dev)
+      cv_ms, cv_med = time_kernel(lambda: ops.cost_volume(fl, fr, D), 20, flush, stream)
+      cv_bytes = 4 * 32 * hc * wc * (2 + D)
+      x3 = torch.randn(1, D, hc, wc, 32, device=dev)
+      conv3, bn3 = snet.filter[0][0][0], snet.filter[0][0][1]
+      f3_ms, _ = time_kernel(lambda: fused.conv_bn_lrelu(x3, conv3, bn3, 1, False, False), 10, flush, stream)
+      f3_flops = 2 * 27 * 32 * 32 * D * hc * wc
+      x2 = torch.randn(1, H, W, 32, device=dev)
+      blk = snet.edge_aware_refinements[0].residual_astrous_blocks[2]
+      r2_ms, _ = time_kernel(lambda: blk.forward_cl(x2), 10, flush, stream)
+      r2_flops = 2 * 9 * 32 * 32 * H * W
+      taps = ops.conv_c32_taps(x3, snet.conv3d_alone.weight, 27)
+      sa_ms, _ = time_kernel(lambda: ops.tapsum_softargmin(taps, snet.conv3d_alone.bias, True), 20, flush, stream)
+      sa_bytes = 4 * hc * wc * (27 * D + D + 1)
+    kernels = {
+      "cost_volume": {"bound": "hbm", "ms": cv_ms, "achieved": cv_bytes / cv_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": cv_bytes / cv_ms / 1e6 / pk["hbm"], "frac_of_nominal_8TBs": cv_bytes / cv_ms / 1e6 / 8000.0,
+                      "algorithmic_bytes": cv_bytes},
+      "filter_conv3d_32x32": {"bound": "tensor", "ms": f3_ms, "achieved": f3_flops / f3_ms / 1e9, "peak": pk["tensor"],
+                              "unit": "TFLOP/s", "frac": f3_flops / f3_ms / 1e9 / pk["tensor"], "algorithmic_flops": f3_flops},
+      "refine_conv2d_32x32_dil4": {"bound": "tensor", "ms": r2_ms, "achieved": r2_flops / r2_ms / 1e9, "peak": pk["tensor"],
+                                   "unit": "TFLOP/s", "frac": r2_flops / r2_ms / 1e9 / pk["tensor"], "algorithmic_flops": r2_flops},
+      "tapsum_softargmin": {"bound": "hbm", "ms": sa_ms, "achieved": sa_bytes / sa_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": sa_bytes / sa_ms / 1e6 / pk["hbm"], "algorithmic_bytes": sa_bytes},
+    }
+    # dominant kernel of the step = the 32->32 convolution (4 x 3-D filter + 6 x refinement launches per pair)
+    dom_name = "filter_conv3d_32x32" if 4 * f3_ms >= 6 * r2_ms else "refine_conv2d_32x32_dil4"
+    dom = kernels[dom_name]
+    roofline = {"kernel": dom_name, "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                "frac": dom["frac"], "traffic": None, "peak_source": pk["src"] + " (bf16 cuBLAS burst; kernel timed alone)",
+                "conv_backend": os.environ.get("SNB200_CONV", "default")}
+    del flush
+
+    cpu = cpu_reference(steps=args.cpu_steps, warmup=1, budget_s=25.0) if world == 1 and not args.skip_cpu else None
+
+    in_bytes = 2 * left.numel() * 4
+    out_bytes = out_pin.numel() * 4
+    result = {
+      "metric": METRIC, "value": world * args.steps / (ms_dev / 1e3), "unit": "pairs/s", "n_gpus": world,
+      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (textured left, right = left warped by a known disparity ramp; seeded random-init weights)",
+      "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": 1, "k": K_DOWN, "maxdisp": MAXDISP,
+                 "l2": "per-step working set ~0.7 GB of intermediates >> 126 MB L2; per-kernel numbers flush L2 before every launch",
+                 "cuda_graph": not args.no_graph, "parallelism": f"independent pairs per GPU x{world}, no collective"},
+      "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+              "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+              "api": "stereonet_b200.runtime.StereoEngine.infer_host (pinned host images -> host disparity)"},
+      "gpu_launches": launches * args.steps,
+      "launches_per_step": launches,
+      "roofline": roofline, "kernels": kernels, "clocks": clocks,
+    }
+    if cpu is not None:
+      result["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return result
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=50)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--skip-cpu", action="store_true")
+  ap.add_argument("--cpu-steps", type=int, default=12)
+  args = ap.parse_args()
+
+  rank = int(os.environ.get("RANK", "0"))
+  if args.impl == "reference":
+    if rank != 0:
+      return
+    c = cpu_reference(steps=args.steps, warmup=min(args.warmup, 2), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": c["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": c["steps"],
+            "warmup": min(args.warmup, 2), "ms_per_step": c["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": c["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return
+  res = gpu_arm(args)
+  if res is not None:
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,138 @@
+"""GPU end-to-end parity: the drop-in nn.Modules (C-ABI kernels underneath) against
+  (1) the committed golden vectors produced by the reference module itself, and
+  (2) the oracle on the CPU at BASELINE.json's full sizes (KITTI 376x1248, D=192),
+plus size-independent properties (determinism, batch independence in eval mode).
+Tolerances are the north star's: max|d disp| <= 1e-2 px and |d EPE| <= 1e-3 px in fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import stereonet_oracle as O
+import stereonet_b200 as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+from test_oracle_golden import CASES, build  # noqa: E402
+
+MAX_DISP_TOL = 1e-2
+EPE_TOL = 1e-3
+
+
+def make_nets(cfg, fsd, ssd):
+  f = S.FeatureExtractorNetwork(cfg["k"]).to(DEV)
+  s = S.StereoNet(cfg["k"], 1, cfg["s"], maxdisp=192).to(DEV)
+  f.load_state_dict(fsd, strict=True)
+  s.load_state_dict(ssd, strict=True)
+  return f, s
+
+
+def report(tag, got, ref):
+  err = float(np.abs(got - ref).max())
+  print(f"[parity] {tag}: max|diff| = {err:.3e} (ref range [{ref.min():.3f}, {ref.max():.3f}])")
+  return err
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_eval_forward_vs_reference_golden(name):
+  cfg = CASES[name]
+  g = np.load(os.path.join(GOLD, name + ".npz"))
+  fsd, ssd, left, right, gt = build(cfg)
+  f, s = make_nets(cfg, fsd, ssd)
+  f.eval(); s.eval()
+  with torch.no_grad():
+    l, r = left.to(DEV), right.to(DEV)
+    fl, fr = f(l), f(r)
+    out = s(l, fl, fr, "l", output_cost_volume=True)
+  assert tuple(fl.shape) == tuple(g["eval/left_features"].shape)
+  assert report(name + " left_features", fl.cpu().numpy(), g["eval/left_features"]) <= 2e-4
+  assert report(name + " right_features", fr.cpu().numpy(), g["eval/right_features"]) <= 2e-4
+  k, sc = cfg["k"], cfg["s"]
+  keys = [f"cost_volume_l/{sc + k}", f"pred_disp_l/{sc + k}", f"pred_disp_l/{sc}"]
+  assert sorted(out) == sorted(keys)
+  for key in keys:
+    ref = g["eval/" + key]
+    assert tuple(out[key].shape) == tuple(ref.shape), key
+    err = report(f"{name} {key}", out[key].cpu().numpy(), ref)
+    assert err <= (MAX_DISP_TOL if key.startswith("pred_disp") else 2e-3), key
+  epe = O.epe(out[f"pred_disp_l/{sc}"].cpu(), gt).item()
+  assert abs(epe - float(g["eval/epe"])) <= EPE_TOL
+  fcs = O.feature_contrast_mean(out[f"cost_volume_l/{sc + k}"].cpu()).mean().item()
+  assert abs(fcs - float(g["eval/fcs"])) <= 1e-3
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["train"]])
+def test_train_mode_forward_vs_reference_golden(name):
+  """Batch-statistics BN forward (adapt.py:313-314) incl. the running-stat updates, no gradients."""
+  cfg = CASES[name]
+  g = np.load(os.path.join(GOLD, name + ".npz"))
+  fsd, ssd, left, right, _ = build(cfg)
+  f, s = make_nets(cfg, fsd, ssd)
+  f.train(); s.train()
+  with torch.no_grad():
+    l, r = left.to(DEV), right.to(DEV)
+    fl, fr = f(l), f(r)
+    out = s(l, fl, fr, "l", output_cost_volume=True)
+  assert report(name + " train left_features", fl.cpu().numpy(), g["train/left_features"]) <= 5e-4
+  for key, v in out.items():
+    err = report(f"{name} train {key}", v.cpu().numpy(), g["train/" + key])
+    assert err <= (MAX_DISP_TOL if key.startswith("pred_disp") else 5e-3), key
+  for tag, net in (("s", s), ("f", f)):
+    sd = net.state_dict()
+    for key in g.files:
+      if key.startswith(f"post/{tag}/") and ("running_" in key or "num_batches" in key) and ".conv2." not in key:
+        n = key.split("/", 2)[2]
+        np.testing.assert_allclose(sd[n].cpu().numpy(), g[key], rtol=2e-4, atol=2e-5, err_msg=key)
+
+
+@pytest.fixture(scope="module")
+def kitti():
+  cfg = dict(B=1, H=376, W=1248, k=3, s=0, sharpen=40.0)
+  fsd, ssd = O.make_feature_state(3, 11), O.make_stereo_state(22, sharpen=40.0)
+  left, right, gt = O.make_stereo_pair(1, 376, 1248, seed=1000, max_disp_px=60.0)
+  f, s = make_nets(cfg, fsd, ssd)
+  f.eval(); s.eval()
+  return cfg, fsd, ssd, left, right, gt, f, s
+
+
+def test_kitti_full_size_vs_oracle(kitti):
+  """BASELINE.json configs[1]: 1x3x376x1248, k=3, D=192 — the oracle finishes this in about a second on the CPU."""
+  cfg, fsd, ssd, left, right, gt, f, s = kitti
+  with torch.no_grad():
+    l, r = left.to(DEV), right.to(DEV)
+    out = s(l, f(l), f(r), "l", output_cost_volume=True)
+    ref = O.predict_disparity_left(fsd, ssd, left, right, 3)
+  for key, v in ref.items():
+    err = report("kitti " + key, out[key].cpu().numpy(), v.numpy())
+    assert err <= (MAX_DISP_TOL if key.startswith("pred_disp") else 2e-3), key
+  assert abs(O.epe(out["pred_disp_l/0"].cpu(), gt).item() - O.epe(ref["pred_disp_l/0"], gt).item()) <= EPE_TOL
+
+
+def test_kitti_determinism_and_batch_independence(kitti):
+  cfg, fsd, ssd, left, right, gt, f, s = kitti
+  l2, r2, _ = O.make_stereo_pair(1, 376, 1248, seed=1001, max_disp_px=40.0)
+  with torch.no_grad():
+    l, r = left.to(DEV), right.to(DEV)
+    a = s(l, f(l), f(r), "l", output_cost_volume=True)
+    b = s(l, f(l), f(r), "l", output_cost_volume=True)
+    for key in a:
+      assert torch.equal(a[key], b[key]), key                      # bitwise run-to-run determinism
+    lb, rb = torch.cat([l, l2.to(DEV)]), torch.cat([r, r2.to(DEV)])
+    c = s(lb, f(lb), f(rb), "l", output_cost_volume=True)
+    for key in a:
+      assert torch.equal(a[key][0], c[key][0]), key                # eval mode: samples never mix
+
+
+def test_output_is_channels_last_view_and_accepts_nchw_features(kitti):
+  cfg, fsd, ssd, left, right, gt, f, s = kitti
+  with torch.no_grad():
+    l, r = left.to(DEV)[:, :, :64, :128].contiguous(), right.to(DEV)[:, :, :64, :128].contiguous()
+    fl, fr = f(l), f(r)
+    assert tuple(fl.shape) == (1, 32, 8, 16)
+    a = s(l, fl, fr, "l")
+    b = s(l, fl.contiguous(), fr.contiguous(), "l")               # plain NCHW-contiguous features are accepted too
+    assert sorted(a) == ["pred_disp_l/0", "pred_disp_l/3"]
+    for key in a:
+      assert torch.equal(a[key], b[key])
