@@ -15,7 +15,7 @@ struct TileDims {
   static constexpr int IW = (TW - 1) * S + KS;
   static constexpr int IWP = (S == 2) ? ((IW + 1) / 2 + 1) : IW + 1;       // per-parity row pitch (+1 pad)
   static constexpr int ROW = (S == 2) ? 2 * IWP : IWP;
-  static constexpr int IN_FLOATS = CIN * IH * ROW;
+  static constexpr int IN_FLOATS = (CIN * IH * ROW + 3) & ~3;   // keep the weight block 16-B aligned
   static constexpr int W_FLOATS = CIN * KS * KS * 32;
   static constexpr int SMEM_BYTES = (IN_FLOATS + W_FLOATS + 64 * 8) * 4;
 };

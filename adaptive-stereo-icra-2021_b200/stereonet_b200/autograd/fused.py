@@ -4,27 +4,27 @@ import torch
 
 from .. import ops
 
-# (id(param)) -> (version, derived tensor).  Keyed on the parameter's in-place version counter so an optimizer step
-# (adapt.py:393) invalidates the entry; holds only derived read-only tensors.
-_CACHE = {}
-
-
-def _cached(key, tensors, make):
+# Derived read-only tensors (repacked weights, folded BN) live ON the owning nn.Module (attribute `_snb_cache`), keyed
+# on the in-place version counters of the source parameters, so an optimizer step (adapt.py:393) or load_state_dict
+# invalidates them and they die with the module (no process-global state).
+def _cached(owner, key, tensors, make):
+  cache = owner.__dict__.setdefault("_snb_cache", {})
   ver = tuple((t.data_ptr(), t._version) for t in tensors)
-  hit = _CACHE.get(key)
+  hit = cache.get(key)
   if hit is not None and hit[0] == ver:
     return hit[1]
   val = make()
-  _CACHE[key] = (ver, val)
+  cache[key] = (ver, val)
   return val
 
 
-def clear_cache():
-  _CACHE.clear()
+def clear_cache(module):
+  for m in module.modules():
+    m.__dict__.pop("_snb_cache", None)
 
 
 def wprep(conv, mode=0):
-  return _cached((id(conv), "w", mode), [conv.weight], lambda: ops.prep_conv_weights(conv.weight, mode))
+  return _cached(conv, ("w", mode), [conv.weight], lambda: ops.prep_conv_weights(conv.weight, mode))
 
 
 def bn_fold(bn):
@@ -34,7 +34,7 @@ def bn_fold(bn):
       scale = bn.weight * torch.rsqrt(bn.running_var + ops.BN_EPS)
       shift = bn.bias - bn.running_mean * scale
       return scale.contiguous(), shift.contiguous()
-  return _cached((id(bn), "fold"), [bn.weight, bn.bias, bn.running_mean, bn.running_var], make)
+  return _cached(bn, "fold", [bn.weight, bn.bias, bn.running_mean, bn.running_var], make)
 
 
 def _needs_grad(*tensors_or_modules):

@@ -23,6 +23,8 @@ REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 # name: (B, H, W, k, input_scale, sharpen, with_train)
+TRAIN_SHARPEN_RATIO = 0.25
+
 CASES = {
   "k3_small_dgtw":   dict(B=1, H=64, W=128, k=3, s=0, sharpen=1.0, train=False),    # D'=24 > W'=16
   "k3_b2_sharp":     dict(B=2, H=96, W=256, k=3, s=0, sharpen=40.0, train=True),
@@ -82,6 +84,10 @@ def run_case(name, cfg, sn, lw, lf, fc):
   out["eval/epe"] = torch.abs(o[f"pred_disp_l/{s}"] - gt)[gt > 0].mean().numpy()
 
   if cfg["train"]:
+    # train-mode BN renormalises the filter activations, so the same conv3d_alone gain gives a ~3x wider cost range
+    # than in eval mode; use a milder gain to stay in a trained-model-like range (about [-22, 12]).
+    ssd_t = O.make_stereo_state(seed=22, sharpen=cfg["sharpen"] * TRAIN_SHARPEN_RATIO)
+    snet.load_state_dict(ssd_t, strict=True)
     # ---- one adaptation step exactly as adapt.py:313-337,381-394 (Adam lr 5e-5, clip on stereo_net only)
     fnet.train(); snet.train()
     opt = torch.optim.Adam([{"params": snet.parameters()}, {"params": fnet.parameters()}], lr=5e-5)
@@ -124,7 +130,8 @@ def run_case(name, cfg, sn, lw, lf, fc):
   c = out[f"eval/cost_volume_l/{s + k}"]
   print(f"{name}: cost range [{c.min():.2f}, {c.max():.2f}] fcs {out['eval/fcs']:.3f} epe {out['eval/epe']:.3f} "
         f"disp mean {out[f'eval/pred_disp_l/{s}'].mean():.3f} std {out[f'eval/pred_disp_l/{s}'].std():.3f}"
-        + (f" loss {out['train/loss']:.5f} gnorm {out['train/grad_norm_stereo']:.4f}" if cfg["train"] else ""))
+        + (f" loss {out['train/loss']:.5f} gnorm {out['train/grad_norm_stereo']:.4f} train cost range "
+           f"[{out[f'train/cost_volume_l/{s + k}'].min():.1f}, {out[f'train/cost_volume_l/{s + k}'].max():.1f}]" if cfg["train"] else ""))
 
 
 if __name__ == "__main__":

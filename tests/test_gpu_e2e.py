@@ -15,7 +15,7 @@ import stereonet_b200 as S
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-from test_oracle_golden import CASES, build  # noqa: E402
+from test_oracle_golden import CASES, TRAIN_SHARPEN_RATIO, build  # noqa: E402
 
 MAX_DISP_TOL = 1e-2
 EPE_TOL = 1e-3
@@ -69,6 +69,7 @@ def test_train_mode_forward_vs_reference_golden(name):
   cfg = CASES[name]
   g = np.load(os.path.join(GOLD, name + ".npz"))
   fsd, ssd, left, right, _ = build(cfg)
+  ssd = O.make_stereo_state(seed=22, sharpen=cfg["sharpen"] * TRAIN_SHARPEN_RATIO)
   f, s = make_nets(cfg, fsd, ssd)
   f.train(); s.train()
   with torch.no_grad():

@@ -9,6 +9,7 @@ import torch
 import stereonet_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TRAIN_SHARPEN_RATIO = 0.25      # oracle/gen_golden.py: milder conv3d_alone gain for the train-mode step
 CASES = {
   "k3_small_dgtw": dict(B=1, H=64, W=128, k=3, s=0, sharpen=1.0, train=False),
   "k3_b2_sharp":   dict(B=2, H=96, W=256, k=3, s=0, sharpen=40.0, train=True),
@@ -70,6 +71,7 @@ def test_adapt_step_matches_reference(name):
   cfg = CASES[name]
   g = np.load(os.path.join(GOLD, name + ".npz"))
   fsd, ssd, left, right, _ = build(cfg)
+  ssd = O.make_stereo_state(seed=22, sharpen=cfg["sharpen"] * TRAIN_SHARPEN_RATIO)
   fsd, ssd = O.clone_state(fsd, True), O.clone_state(ssd, True)
   adam = {}
   loss, outputs, grads = O.adapt_step(fsd, ssd, left, right, cfg["k"], adam, lr=5e-5, input_scale=cfg["s"])
