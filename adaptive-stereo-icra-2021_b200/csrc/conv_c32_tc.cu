@@ -1,0 +1,410 @@
+// 32->32 stride-1 3x3 (dilated, 2-D) / 3x3x3 (3-D) convolution as an implicit GEMM on the 5th-gen tensor cores.
+// Replaces the nn.Conv3d cost-filter layers (stereo_net.py:155-160,185-186) and the nn.Conv2d of every BasicBlock
+// (stereo_net.py:37-39,44-51; feature extractor :73-77 and refinement :96-100), incl. folded BN, LeakyReLU, residual.
+//
+// GEMM view (per (b,d) slice, "flat padded" pixel index q = h*P + w with pitch P = W + dil, columns >= W read as zero):
+//   M tile  = 128 consecutive q               (TMEM lanes)
+//   K       = (kd,kh) windows x 32 cin        (one window = one pipeline stage: A tile 128 x 32 fp32 = 16 KB)
+//   N       = 96 = 3 kw x 32 cout             (kw is folded into N: the three kw taps share one un-shifted A window, so
+//                                              the 128x32 A tile is read from smem once per window, not three times —
+//                                              with N = 32 the MMA would be bound by the A-operand smem feed)
+//   Y_kw[m] accumulates in TMEM (3 x 32 fp32 columns); the epilogue forms out[m] = Y0[m-dil] + Y1[m] + Y2[m+dil] in
+//   smem, so a tile yields 128 - 2*dil output positions (tiles overlap by 2*dil rows).
+// Operands are TF32 (tcgen05.mma.kind::tf32, fp32 accumulate in TMEM).  passes = 3 runs the error-compensated split
+//   x*w ~= xh*wh + xl*wh + xh*wl   (xh = top 19 bits, xl = x - xh)  -> ~2^-21 relative, i.e. fp32-grade results;
+// passes = 1 is plain single-pass TF32 (reported separately, north star).
+//
+// Warp roles (416 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-7  loaders : LDG.128 channels-last rows -> hi/lo split -> STS into the SWIZZLE_128B K-major A image,
+//                        zero rows for padding; warp 0 also issues the TMA bulk copy of the window's B image (3-D)
+//   warp  8    MMA     : one elected thread issues tcgen05.mma (M128 N96 K8) and tcgen05.commit on the mbarriers
+//   warps 9-12 epilogue: tcgen05.ld TMEM -> smem shift-add -> bias/BN/LeakyReLU/residual/stats -> coalesced STG
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int NSTAGE = 3;
+constexpr int A_BYTES = 128 * 128;                       // one 128x32 fp32 operand image (hi or lo)
+constexpr int B_BYTES = 96 * 128;                        // one 96x32 fp32 operand image (hi or lo)
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 56 KB (multiple of 1024)
+constexpr int OUT_BYTES = 128 * 128;
+constexpr int NACC = 4;                                  // TMEM accumulator slots of 128 columns (96 used)
+constexpr int NUM_LOADER_WARPS = 8;
+constexpr int NTHREADS = (NUM_LOADER_WARPS + 1 + 4) * 32;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + OUT_BYTES + 2048 /*barriers, misc*/ + 1024 /*alignment slack*/;
+constexpr int WIMG_FLOATS_PER_WINDOW = 2 * B_BYTES / 4;  // hi + lo
+
+// instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9 = 10-12 = 2), K-major A and B,
+// N>>3 at bits 17-22, M>>4 at bits 24-28   (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(16 B, unused)<<16 | SBO(1024 B = 8 rows x 128 B)<<32 | version 1<<46 | layout 2<<61
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Bounded mbarrier wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 1.9 GHz
+  }
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+struct Params {
+  const float* x; const float* wimg; float* y;
+  int B, D, H, W;          // stride-1 "same" conv: output dims = input dims
+  int nwin;                // 3 (2-D: kh) or 9 (3-D: kd,kh)
+  int dil, P;              // dilation, flat pitch W + dil
+  int tiles_per_slice, ntiles, step;   // step = 128 - 2*dil output positions per tile
+  int passes;              // 1 or 3
+  snb_conv_epilogue e;
+};
+
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b < 0) ? q - 1 : q; }
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_c32_tc_kernel(const Params p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
+  unsigned char* sOutB = base + NSTAGE * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOutB + OUT_BYTES);
+  uint64_t* full = bars;                 // [NSTAGE]  loaders (+TMA bytes) -> MMA
+  uint64_t* empty = bars + NSTAGE;       // [NSTAGE]  MMA commit -> loaders
+  uint64_t* tfull = bars + 2 * NSTAGE;   // [NACC]    MMA commit -> epilogue
+  uint64_t* tempty = tfull + NACC;       // [NACC]    epilogue -> MMA
+  uint64_t* wbar = tempty + NACC;        // resident-weights barrier (2-D)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][64]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool stream_b = p.nwin > NSTAGE;       // 3-D: weights do not fit next to the A ring -> streamed per window
+
+  if (warp == NUM_LOADER_WARPS) {
+    if (lane == 0) {
+      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], NUM_LOADER_WARPS + 1); mbar_init(&empty[i], 1); }
+      for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+      mbar_init(wbar, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NUM_LOADER_WARPS) {
+    // =============================================================== loaders
+    const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes cover one 128-B row; rows rgrp + 32*j
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
+      const int b = slice / p.D, d = slice - b * p.D;
+      const int q0 = tt * p.step - p.dil;
+      int h0[4], w0[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = q0 + rgrp + 32 * j;
+        h0[j] = floordiv(q, p.P);
+        w0[j] = q - h0[j] * p.P;
+      }
+      for (int widx = 0; widx < p.nwin; ++widx) {
+        const int kd = (p.nwin == 9) ? widx / 3 : 0, kh = widx - kd * 3;
+        const int di = (p.nwin == 9) ? d + kd - 1 : d;
+        const bool slice_ok = (unsigned)di < (unsigned)p.D;
+        unsigned char* st = base + stage * STAGE_BYTES;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (tid == 0) {
+          if (stream_b) {
+            mbar_expect_tx(&full[stage], 2 * B_BYTES);
+            bulk_g2s(st + 2 * A_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &full[stage]);
+          } else {
+            mbar_arrive(&full[stage]);
+          }
+        }
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int h = h0[j] + (kh - 1) * p.dil;
+          const bool ok = slice_ok && w0[j] < p.W && (unsigned)h < (unsigned)p.H;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v[j] = __ldg(reinterpret_cast<const float4*>(
+                         p.x + ((((size_t)b * p.D + di) * p.H + h) * p.W + w0[j]) * 32 + chunk * 4));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rgrp + 32 * j;
+          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          float4 hi;
+          hi.x = __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u);
+          hi.y = __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u);
+          hi.z = __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u);
+          hi.w = __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          if (p.passes == 3) {
+            const float4 lo = make_float4(v[j].x - hi.x, v[j].y - hi.y, v[j].z - hi.z, v[j].w - hi.w);
+            *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+          }
+        }
+        fence_async_smem();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == NUM_LOADER_WARPS) {
+    // =============================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      if (!stream_b) {       // 2-D: window kh always lands in stage kh -> keep its B image resident there
+        mbar_expect_tx(wbar, (uint32_t)p.nwin * 2 * B_BYTES);
+        for (int w = 0; w < p.nwin; ++w)
+          bulk_g2s(base + w * STAGE_BYTES + 2 * A_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, wbar);
+        mbar_wait(wbar, 0);
+      }
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & (NACC - 1);
+        const uint32_t accphase = (it / NACC) & 1;
+        mbar_wait(&tempty[acc], accphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 128;
+        for (int widx = 0; widx < p.nwin; ++widx) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = base_u32 + stage * STAGE_BYTES;
+          const uint32_t sb = sa + 2 * A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {           // K = 8 tf32 = 32 bytes per MMA
+            const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sb + ks * 32);
+            mma_tf32(tmem_d, ah, bh, (widx | ks) != 0);
+            if (p.passes == 3) {
+              mma_tf32(tmem_d, make_desc(sa + A_BYTES + ks * 32), bh, 1);
+              mma_tf32(tmem_d, ah, make_desc(sb + B_BYTES + ks * 32), 1);
+            }
+          }
+          mma_commit(&empty[stage]);                 // smem slot reusable once these MMAs have read it
+          if (widx == p.nwin - 1) mma_commit(&tfull[acc]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== epilogue (4 warps, TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;                  // TMEM lane == tile row
+    const int et = tid - (NUM_LOADER_WARPS + 1) * 32;
+    const int chunk = et & 7, rg = et >> 3;          // final pass: rows rg + 16*j, 16-B chunk `chunk`
+    float* sOut = reinterpret_cast<float*>(sOutB);
+    const snb_conv_epilogue& e = p.e;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bias4;
+    if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
+    if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & (NACC - 1);
+      const uint32_t accphase = (it / NACC) & 1;
+      const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
+      const int q0 = tt * p.step - p.dil;
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 128;
+      float v[32];
+      // pass 1: centre tap kw=1 -> out[m]
+      tmem_ld32(taddr + 32, v);
+      {
+        float* row = sOut + m * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(row + ((c ^ (m & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      epi_bar();
+      // pass 2: kw=0 reads input w-dil: Y0[m] belongs to out[m + dil]
+      tmem_ld32(taddr, v);
+      if (m + p.dil < 128) {
+        const int r = m + p.dil;
+        float* row = sOut + r * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* q4 = reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 2));
+          float4 o = *q4;
+          o.x += v[4 * c]; o.y += v[4 * c + 1]; o.z += v[4 * c + 2]; o.w += v[4 * c + 3];
+          *q4 = o;
+        }
+      }
+      epi_bar();
+      // pass 3: kw=2 reads input w+dil: Y2[m] belongs to out[m - dil]
+      tmem_ld32(taddr + 64, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);      // this warp is done with the TMEM slot
+      if (m >= p.dil) {
+        const int r = m - p.dil;
+        float* row = sOut + r * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* q4 = reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 2));
+          float4 o = *q4;
+          o.x += v[4 * c]; o.y += v[4 * c + 1]; o.z += v[4 * c + 2]; o.w += v[4 * c + 3];
+          *q4 = o;
+        }
+      }
+      epi_bar();
+      // final pass: coalesced (8 lanes = one 128-B position) bias / stats / BN / LeakyReLU / residual / store
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = rg + 16 * j;
+        const int q = q0 + r;
+        const int h = floordiv(q, p.P), w = q - h * p.P;
+        const bool ok = r >= p.dil && r < 128 - p.dil && q >= 0 && h < p.H && w < p.W;
+        if (!ok) continue;
+        float4 o = *reinterpret_cast<const float4*>(sOut + r * 32 + ((chunk ^ (r & 7)) << 2));
+        o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+        s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+        s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+        if (e.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
+        if (e.lrelu) { o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w); }
+        const size_t gi = (((size_t)slice * p.H + h) * p.W + w) * 32 + chunk * 4;
+        if (e.residual) {
+          const float4 rr = __ldg(reinterpret_cast<const float4*>(e.residual + gi));
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(p.y + gi) = o;
+      }
+      if (e.stats) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 8); s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 16);
+          s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], 8); s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { sRed[quad * 64 + lane * 4 + c] = s1[c]; sRed[quad * 64 + 32 + lane * 4 + c] = s2[c]; }
+        }
+        epi_bar();
+        if (et < 64) e.stats[(size_t)tile * 64 + et] = sRed[et] + sRed[64 + et] + sRed[128 + et] + sRed[192 + et];
+      }
+      epi_bar();     // sOut / sRed are rewritten by the next tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NUM_LOADER_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
+  }
+}
+
+// w [32 cout][32 cin][kd*kh*kw taps] -> per (kd,kh) window: B_hi[n = kw*32 + cout][k = cin] then B_lo, each in the
+// SWIZZLE_128B K-major smem image (row n = 128 B, 16-B chunk c stored at c ^ (n & 7)).  mode 1: data-gradient weights.
+__global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int nwin, int mode) {
+  const int taps = nwin * 3;
+  const int total = nwin * 96 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 31;                 // K index (input channel of this GEMM)
+    const int n = (i >> 5) % 96;          // N index = kw*32 + output channel of this GEMM
+    const int win = i / (96 * 32);
+    const int kw = n >> 5, co = n & 31;
+    const int tap = win * 3 + kw;
+    float v;
+    if (mode == 0) v = w[((size_t)co * 32 + k) * taps + tap];
+    else           v = w[((size_t)k * 32 + co) * taps + (taps - 1 - tap)];   // dgrad: swap channels, flip taps
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
+    out[o] = hi;
+    out[o + B_BYTES / 4] = v - hi;
+  }
+}
+
+}  // namespace tc
+
+static int tc_setup(const snb_conv_geom* g, tc::Params& p, const char* who) {
+  SNB_REQUIRE(g != nullptr, "%s: null geometry", who);
+  SNB_REQUIRE(g->stride == 1 && g->KH == 3 && g->KW == 3 && (g->KD == 1 || g->KD == 3), "%s: needs a stride-1 3x3(x3) conv", who);
+  SNB_REQUIRE(g->OD == g->D && g->OH == g->H && g->OW == g->W && g->ph == g->dil && g->pw == g->dil &&
+              g->pd == (g->KD == 3 ? 1 : 0), "%s: needs 'same' padding", who);
+  SNB_REQUIRE(g->dil >= 1 && g->dil <= 16, "%s: dilation out of range", who);
+  p.B = g->B; p.D = g->D; p.H = g->H; p.W = g->W;
+  p.nwin = g->KD * 3; p.dil = g->dil; p.P = g->W + g->dil;
+  p.step = 128 - 2 * g->dil;
+  p.tiles_per_slice = snb_ceil_div((long long)g->H * p.P, p.step);
+  const long long nt = (long long)g->B * g->D * p.tiles_per_slice;
+  SNB_REQUIRE(nt < (1ll << 30), "%s: too many tiles", who);
+  p.ntiles = (int)nt;
+  return 0;
+}
+
+extern "C" int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g) {
+  tc::Params p;
+  if (tc_setup(g, p, "snb_conv_c32_tc_num_tiles")) return -1;
+  return p.ntiles;
+}
+
+extern "C" int snb_conv_weights_tc_floats(int kd) { return kd * 3 * tc::WIMG_FLOATS_PER_WINDOW; }
+
+extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream) {
+  SNB_REQUIRE(w && out && (kd == 1 || kd == 3) && (mode == 0 || mode == 1), "snb_prep_conv_weights_tc: bad args");
+  const int nwin = kd * 3;
+  tc::prep_weights_tc_kernel<<<snb_ceil_div(nwin * 96 * 32, 256), 256, 0, (cudaStream_t)stream>>>(w, out, nwin, mode);
+  SNB_LAUNCH_CHECK("prep_weights_tc_kernel");
+  return 0;
+}
+
+extern "C" int snb_conv_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                               int passes, void* stream) {
+  tc::Params p;
+  if (int rc = tc_setup(g, p, "snb_conv_c32_tc")) return rc;
+  SNB_REQUIRE(x && wimg && y && e, "snb_conv_c32_tc: null pointer");
+  SNB_REQUIRE(passes == 1 || passes == 3, "snb_conv_c32_tc: passes must be 1 or 3");
+  SNB_REQUIRE(!e->scale || e->shift, "snb_conv_c32_tc: scale without shift");
+  p.x = x; p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e;
+  int dev = 0, sms = 148;
+  SNB_CUDA(cudaGetDevice(&dev));
+  SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+  tc::conv_c32_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  SNB_LAUNCH_CHECK("conv_c32_tc_kernel");
+  return 0;
+}

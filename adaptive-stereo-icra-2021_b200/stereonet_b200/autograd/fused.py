@@ -23,6 +23,32 @@ def clear_cache(module):
     m.__dict__.pop("_snb_cache", None)
 
 
+import os
+
+# Convolution backend for the stride-1 3x3 / 3x3x3 32->32 layers: "tc3" = tcgen05 3xTF32 (fp32-grade, default),
+# "tc1" = tcgen05 single-pass TF32 (faster, ~1e-3 relative), "ffma" = fp32 CUDA-core kernel.  All three are this
+# library's own kernels; the switch exists for measurement and cross-checking, not as a fallback.
+CONV_BACKEND = os.environ.get("SNB200_CONV", "ffma")
+
+
+def set_conv_backend(name):
+  global CONV_BACKEND
+  if name not in ("tc3", "tc1", "ffma"):
+    raise ValueError(name)
+  CONV_BACKEND = name
+
+
+def wprep_tc(conv, mode=0):
+  return _cached(conv, ("wtc", mode), [conv.weight], lambda: ops.prep_conv_weights_tc(conv.weight, mode))
+
+
+def conv3x3_c32(x, conv, g, **kw):
+  """Backend dispatch for the 'same' 3x3(x3) convolution + fused epilogue."""
+  if CONV_BACKEND == "ffma":
+    return ops.conv_c32(x, wprep(conv), g, **kw)
+  return ops.conv_c32_tc(x, wprep_tc(conv), g, passes=3 if CONV_BACKEND == "tc3" else 1, **kw)
+
+
 def wprep(conv, mode=0):
   return _cached(conv, ("w", mode), [conv.weight], lambda: ops.prep_conv_weights(conv.weight, mode))
 
@@ -69,7 +95,10 @@ def conv_plain(x, conv, ksize, stride):
   if _needs_grad(x, conv):
     from . import functions
     return functions.ConvC32.apply(x, conv.weight, conv.bias, ksize, stride, 1)
-  y, _ = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach())
+  if ksize == 3 and stride == 1:
+    y, _ = conv3x3_c32(x, conv, g, bias=conv.bias.detach())
+  else:
+    y, _ = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach())
   return y
 
 
@@ -82,10 +111,10 @@ def conv_bn_lrelu(x, conv, bn, dil, residual, training):
     return functions.conv_bn_lrelu_autograd(x, conv, bn, dil, residual, training)
   if not training:
     scale, shift = bn_fold(bn)
-    y, _ = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach(), scale=scale, shift=shift,
-                        residual=x if residual else None, lrelu=True)
+    y, _ = conv3x3_c32(x, conv, g, bias=conv.bias.detach(), scale=scale, shift=shift,
+                       residual=x if residual else None, lrelu=True)
     return y
-  z, stats = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach(), want_stats=True)
+  z, stats = conv3x3_c32(x, conv, g, bias=conv.bias.detach(), want_stats=True)
   scale, shift, _, _ = ops.bn_finalize(stats, z.numel() // 32, bn)
   return ops.bn_apply(z, scale, shift, residual=x if residual else None, lrelu=True)
 

@@ -109,6 +109,37 @@ def conv_c32(x, wprep, g, bias=None, scale=None, shift=None, residual=None, lrel
   return y, stats
 
 
+def prep_conv_weights_tc(w, mode=0):
+  """[32,32,(3,)3,3] -> tensor-core B-operand image (see snb_prep_conv_weights_tc)."""
+  w = _req(w.detach().contiguous(), "weight")
+  if w.shape[0] != 32 or w.shape[1] != 32 or tuple(w.shape[-2:]) != (3, 3):
+    raise RuntimeError(f"stereonet_b200: tensor-core conv needs a [32,32,(3,)3,3] weight, got {tuple(w.shape)}")
+  kd = 3 if w.dim() == 5 else 1
+  out = torch.empty((_cabi.lib().snb_conv_weights_tc_floats(kd),), device=w.device, dtype=torch.float32)
+  check(_cabi.lib().snb_prep_conv_weights_tc(_p(w), _p(out), kd, mode, _stream(w)), "snb_prep_conv_weights_tc")
+  _count()
+  return out
+
+
+def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3):
+  """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32."""
+  three_d = x.dim() == 5
+  _req(x, "x"); _req(wimg, "wimg")
+  y = torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
+  stats = None
+  if want_stats:
+    nt = _cabi.lib().snb_conv_c32_tc_num_tiles(C.byref(g))
+    stats = torch.empty((nt, 2, 32), device=x.device, dtype=torch.float32)
+  if residual is not None:
+    _req(residual, "residual")
+    if residual.shape != y.shape:
+      raise RuntimeError("stereonet_b200: residual shape mismatch")
+  e = ConvEpilogue(_p(bias), _p(scale), _p(shift), _p(residual), _p(stats), 1 if lrelu else 0)
+  check(_cabi.lib().snb_conv_c32_tc(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv_c32_tc")
+  _count()
+  return y, stats
+
+
 def conv5x5s2_c3(img, w, bias):
   _req(img, "rgb_img", 4)
   B, Cc, H, W = img.shape

@@ -73,6 +73,18 @@ SNB_API int snb_cost_volume_bwd(const float* dcost, float* dleft, float* dright,
  * residual add) at stereo_net.py:10-17,23-29,44-51,64-70,77,81-85,185-186.  wprep from snb_prep_conv_weights. */
 SNB_API int snb_conv_c32(const float* x, const float* wprep, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e, void* stream);
 
+/* Same contract as snb_conv_c32 for stride-1 "same" 3x3 (dilated) / 3x3x3 convolutions, on the tcgen05 tensor cores
+ * (TF32 operands from shared memory, fp32 accumulators in TMEM; kw folded into N = 96).  passes = 3: error-compensated
+ * 3xTF32 split (fp32-grade results); passes = 1: plain single-pass TF32.  wimg from snb_prep_conv_weights_tc.
+ * `stats` rows are indexed by this kernel's own tiles: snb_conv_c32_tc_num_tiles(). */
+SNB_API int snb_conv_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                    int passes, void* stream);
+SNB_API int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g);
+/* Repack [32][32][kd*3*3] weights into the tensor-core B-operand smem image (hi/lo TF32 split, SWIZZLE_128B K-major,
+ * one 24 KB block per (kd,kh) window).  kd = 1 (2-D) or 3 (3-D).  mode 0: forward, 1: data gradient. */
+SNB_API int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream);
+SNB_API int snb_conv_weights_tc_floats(int kd);
+
 /* Small-Cin first layers.
  * snb_conv5x5s2_c3: FeatureExtractorNetwork.downsample[0] (stereo_net.py:64-70,81): NCHW image [B,3,H,W] -> [B,OH,OW,32]. */
 SNB_API int snb_conv5x5s2_c3(const float* img, const float* w /*[32][3][5][5]*/, const float* bias, float* y,

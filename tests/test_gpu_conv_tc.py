@@ -1,0 +1,62 @@
+"""GPU parity of the tcgen05 (tensor-core, TF32) 32->32 convolution against plain fp32 torch on the CPU.
+passes=3 (error-compensated 3xTF32) must be fp32-grade: 1e-5 of the output magnitude; passes=1 is plain TF32: 3e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from stereonet_b200 import ops
+from test_gpu_kernels import cl, uncl, rnd, close, DEV
+
+pytestmark = pytest.mark.gpu
+TOL = {3: 1e-5, 1: 3e-3}
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("B,H,W,dil", [(1, 19, 45, 1), (2, 23, 37, 2), (1, 40, 50, 4), (1, 33, 41, 8), (1, 8, 128, 1),
+                                       (1, 47, 156, 1), (1, 130, 260, 2)])
+def test_conv_tc_2d(B, H, W, dil, passes):
+  x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
+  ref = F.conv2d(x, w, b, padding=dil, dilation=dil)
+  g = ops.geom((B, H, W, 32), 3, dil=dil)
+  y, _ = ops.conv_c32_tc(cl(x), ops.prep_conv_weights_tc(w.to(DEV)), g, bias=b.to(DEV), passes=passes)
+  close(uncl(y), ref, TOL[passes], f"tc conv2d dil={dil} passes={passes}")
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("B,D,H,W", [(1, 24, 9, 20), (2, 6, 7, 33), (1, 12, 17, 16), (1, 24, 47, 156)])
+def test_conv_tc_3d_full_epilogue(B, D, H, W, passes):
+  x, w, b = rnd(B, 32, D, H, W, seed=1), rnd(32, 32, 3, 3, 3, seed=2, scale=0.05), rnd(32, seed=3)
+  scale, shift = rnd(32, seed=4).abs() + 0.5, rnd(32, seed=5)
+  z = F.conv3d(x, w, b, padding=1)
+  ref = F.leaky_relu(z * scale.view(1, 32, 1, 1, 1) + shift.view(1, 32, 1, 1, 1), 0.2) + x
+  g = ops.geom((B, D, H, W, 32), 3)
+  xc = cl(x)
+  y, stats = ops.conv_c32_tc(xc, ops.prep_conv_weights_tc(w.to(DEV)), g, bias=b.to(DEV), scale=scale.to(DEV),
+                             shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True, passes=passes)
+  close(uncl(y), ref, TOL[passes], f"tc conv3d passes={passes}")
+  s = stats.double().sum(0).cpu()
+  close(s[0], z.double().sum((0, 2, 3, 4)), 10 * TOL[passes], "sum z")
+  close(s[1], (z.double() ** 2).sum((0, 2, 3, 4)), 10 * TOL[passes], "sum z^2")
+
+
+def test_conv_tc_kitti_refinement_size():
+  x, w, b = rnd(1, 32, 376, 1248, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
+  for dil in (1, 8):
+    ref = F.conv2d(x, w, b, padding=dil, dilation=dil)
+    y, _ = ops.conv_c32_tc(cl(x), ops.prep_conv_weights_tc(w.to(DEV)), ops.geom((1, 376, 1248, 32), 3, dil=dil), bias=b.to(DEV))
+    close(uncl(y), ref, 1e-5, f"tc conv2d 376x1248 dil={dil}")
+
+
+def test_conv_tc_dgrad_weights():
+  x = rnd(1, 32, 14, 27, seed=1).requires_grad_()
+  w = rnd(32, 32, 3, 3, seed=2, scale=0.1)
+  gy = rnd(1, 32, 14, 27, seed=3)
+  F.conv2d(x, w, None, padding=2, dilation=2).backward(gy)
+  dx, _ = ops.conv_c32_tc(cl(gy), ops.prep_conv_weights_tc(w.to(DEV), mode=1), ops.geom((1, 14, 27, 32), 3, dil=2))
+  close(uncl(dx), x.grad, 1e-5, "tc dgrad 2d")
+  x = rnd(1, 32, 6, 9, 11, seed=1).requires_grad_()
+  w = rnd(32, 32, 3, 3, 3, seed=2, scale=0.05)
+  gy = rnd(1, 32, 6, 9, 11, seed=3)
+  F.conv3d(x, w, None, padding=1).backward(gy)
+  dx, _ = ops.conv_c32_tc(cl(gy), ops.prep_conv_weights_tc(w.to(DEV), mode=1), ops.geom((1, 6, 9, 11, 32), 3))
+  close(uncl(dx), x.grad, 1e-5, "tc dgrad 3d")
