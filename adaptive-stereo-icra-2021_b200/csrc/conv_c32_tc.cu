@@ -14,11 +14,11 @@
 //   x*w ~= xh*wh + xl*wh + xh*wl   (xh = top 19 bits, xl = x - xh)  -> ~2^-21 relative, i.e. fp32-grade results;
 // passes = 1 is plain single-pass TF32 (reported separately, north star).
 //
-// Warp roles (416 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (544 threads, 1 CTA/SM, persistent over tiles):
 //   warps 0-7  loaders : LDG.128 channels-last rows -> hi/lo split -> STS into the SWIZZLE_128B K-major A image,
 //                        zero rows for padding; warp 0 also issues the TMA bulk copy of the window's B image (3-D)
 //   warp  8    MMA     : one elected thread issues tcgen05.mma (M128 N96 K8) and tcgen05.commit on the mbarriers
-//   warps 9-12 epilogue: tcgen05.ld TMEM -> smem shift-add -> bias/BN/LeakyReLU/residual/stats -> coalesced STG
+//   warps 9-16 epilogue: tcgen05.ld TMEM -> smem (Y0|Y1|Y2) -> shift-add + bias/BN/LeakyReLU/residual/stats -> coalesced STG
 #include "common.cuh"
 
 namespace tc {
@@ -27,11 +27,12 @@ constexpr int NSTAGE = 3;
 constexpr int A_BYTES = 128 * 128;                       // one 128x32 fp32 operand image (hi or lo)
 constexpr int B_BYTES = 96 * 128;                        // one 96x32 fp32 operand image (hi or lo)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 56 KB (multiple of 1024)
-constexpr int OUT_BYTES = 128 * 128;
+constexpr int OUT_BYTES = 3 * 128 * 128;                  // Y0 | Y1 | Y2 staging tiles (128 x 32 fp32 each)
 constexpr int NACC = 4;                                  // TMEM accumulator slots of 128 columns (96 used)
 constexpr int NUM_LOADER_WARPS = 8;
-constexpr int NTHREADS = (NUM_LOADER_WARPS + 1 + 4) * 32;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + OUT_BYTES + 2048 /*barriers, misc*/ + 1024 /*alignment slack*/;
+constexpr int NUM_EPI_WARPS = 8;                         // two per TMEM lane quadrant (16 of the 32 columns each)
+constexpr int NTHREADS = (NUM_LOADER_WARPS + 1 + NUM_EPI_WARPS) * 32;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + OUT_BYTES + 3072 /*barriers, misc*/ + 1024 /*alignment slack*/;
 constexpr int WIMG_FLOATS_PER_WINDOW = 2 * B_BYTES / 4;  // hi + lo
 
 // instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9 = 10-12 = 2), K-major A and B,
@@ -75,6 +76,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Bounded mbarrier wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
@@ -83,7 +97,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 struct Params {
   const float* x; const float* wimg; float* y;
@@ -110,7 +124,7 @@ conv_c32_tc_kernel(const Params p) {
   uint64_t* tempty = tfull + NACC;       // [NACC]    epilogue -> MMA
   uint64_t* wbar = tempty + NACC;        // resident-weights barrier (2-D)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-  float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][64]
+  float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool stream_b = p.nwin > NSTAGE;       // 3-D: weights do not fit next to the A ring -> streamed per window
@@ -118,7 +132,7 @@ conv_c32_tc_kernel(const Params p) {
   if (warp == NUM_LOADER_WARPS) {
     if (lane == 0) {
       for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], NUM_LOADER_WARPS + 1); mbar_init(&empty[i], 1); }
-      for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+      for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
       mbar_init(wbar, 1);
       mbar_fence_init();
     }
@@ -133,54 +147,78 @@ conv_c32_tc_kernel(const Params p) {
 
   if (warp < NUM_LOADER_WARPS) {
     // =============================================================== loaders
+    // Software-pipelined: the global loads of window i+PF are in flight (registers) while window i is split and
+    // stored to smem, so a loader thread never sits out a full L2/HBM round trip per window.
+    constexpr int PF = 3;
     const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes cover one 128-B row; rows rgrp + 32*j
-    uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
-      const int b = slice / p.D, d = slice - b * p.D;
-      const int q0 = tt * p.step - p.dil;
-      int h0[4], w0[4];
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_items = my_tiles * p.nwin;                 // item = (tile, window)
+    // ---- load cursor state
+    int l_item = 0, l_widx = 0, l_b = 0, l_d = 0;
+    int l_tile = blockIdx.x;
+    int h0[4], w0[4];
+    auto decode_tile = [&]() {
+      const int slice = l_tile / p.tiles_per_slice, tt = l_tile - slice * p.tiles_per_slice;
+      l_b = slice / p.D; l_d = slice - l_b * p.D;
+      const int q = tt * p.step - p.dil + rgrp;
+      int h = floordiv(q, p.P), w = q - h * p.P;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {      // rows rgrp + 32*j: one division per tile, then increments
+        h0[j] = h; w0[j] = w;
+        w += 32;
+        while (w >= p.P) { w -= p.P; ++h; }
+      }
+    };
+    auto issue_loads = [&](float4 (&v)[4]) {
+      if (l_widx == 0) decode_tile();
+      const int kd = (p.nwin == 9) ? l_widx / 3 : 0, kh = l_widx - kd * 3;
+      const int di = (p.nwin == 9) ? l_d + kd - 1 : l_d;
+      const bool slice_ok = (unsigned)di < (unsigned)p.D;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = q0 + rgrp + 32 * j;
-        h0[j] = floordiv(q, p.P);
-        w0[j] = q - h0[j] * p.P;
+        const int h = h0[j] + (kh - 1) * p.dil;
+        const bool ok = slice_ok && w0[j] < p.W && (unsigned)h < (unsigned)p.H;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v[j] = __ldg(reinterpret_cast<const float4*>(
+                       p.x + ((((size_t)l_b * p.D + di) * p.H + h) * p.W + w0[j]) * 32 + chunk * 4));
       }
-      for (int widx = 0; widx < p.nwin; ++widx) {
-        const int kd = (p.nwin == 9) ? widx / 3 : 0, kh = widx - kd * 3;
-        const int di = (p.nwin == 9) ? d + kd - 1 : d;
-        const bool slice_ok = (unsigned)di < (unsigned)p.D;
+      ++l_item;
+      if (++l_widx == p.nwin) { l_widx = 0; l_tile += gridDim.x; }
+    };
+    float4 v[PF][4];
+#pragma unroll
+    for (int k = 0; k < PF; ++k)
+      if (l_item < n_items) issue_loads(v[k]);
+
+    uint32_t stage = 0, phase = 0;
+    int s_widx = 0;
+    for (int item0 = 0; item0 < n_items; item0 += PF) {
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        if (item0 + k >= n_items) break;
         unsigned char* st = base + stage * STAGE_BYTES;
         mbar_wait(&empty[stage], phase ^ 1);
         if (tid == 0) {
           if (stream_b) {
             mbar_expect_tx(&full[stage], 2 * B_BYTES);
-            bulk_g2s(st + 2 * A_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &full[stage]);
+            bulk_g2s(st + 2 * A_BYTES, p.wimg + (size_t)s_widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &full[stage]);
           } else {
             mbar_arrive(&full[stage]);
           }
-        }
-        float4 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int h = h0[j] + (kh - 1) * p.dil;
-          const bool ok = slice_ok && w0[j] < p.W && (unsigned)h < (unsigned)p.H;
-          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) v[j] = __ldg(reinterpret_cast<const float4*>(
-                         p.x + ((((size_t)b * p.D + di) * p.H + h) * p.W + w0[j]) * 32 + chunk * 4));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = rgrp + 32 * j;
           const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          const float4 x4 = v[k][j];
           float4 hi;
-          hi.x = __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u);
-          hi.y = __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u);
-          hi.z = __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u);
-          hi.w = __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u);
+          hi.x = __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u);
+          hi.y = __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u);
+          hi.z = __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u);
+          hi.w = __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u);
           *reinterpret_cast<float4*>(st + off) = hi;
           if (p.passes == 3) {
-            const float4 lo = make_float4(v[j].x - hi.x, v[j].y - hi.y, v[j].z - hi.z, v[j].w - hi.w);
+            const float4 lo = make_float4(x4.x - hi.x, x4.y - hi.y, x4.z - hi.z, x4.w - hi.w);
             *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
           }
         }
@@ -188,6 +226,8 @@ conv_c32_tc_kernel(const Params p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (++s_widx == p.nwin) s_widx = 0;
+        if (l_item < n_items) issue_loads(v[k]);   // refill this register slot with window item+PF
       }
     }
   } else if (warp == NUM_LOADER_WARPS) {
@@ -229,13 +269,20 @@ conv_c32_tc_kernel(const Params p) {
     }
     __syncwarp();
   } else {
-    // =============================================================== epilogue (4 warps, TMEM lane quadrant = warp % 4)
+    // =============================================================== epilogue (8 warps; TMEM lane quadrant = warp % 4)
+    // Step 1: TMEM -> smem, the three kw partials Y0|Y1|Y2 as separate 128x32 tiles (row = TMEM lane, 16-B chunks
+    //         XOR-swizzled).  Step 2 (after one barrier): every thread owns one 16-B chunk of 4 rows and forms
+    //         out[r] = Y0[r-dil] + Y1[r] + Y2[r+dil] + bias -> stats -> BN scale/shift -> LeakyReLU -> + residual -> STG,
+    //         8 lanes per 128-B position so global traffic is fully coalesced.
+    const int ew = warp - (NUM_LOADER_WARPS + 1);    // 0..7
     const int quad = warp & 3;
+    const int half = ew >> 2;                        // which 16 of the 32 output channels this warp moves out of TMEM
     const int m = quad * 32 + lane;                  // TMEM lane == tile row
     const int et = tid - (NUM_LOADER_WARPS + 1) * 32;
-    const int chunk = et & 7, rg = et >> 3;          // final pass: rows rg + 16*j, 16-B chunk `chunk`
-    float* sOut = reinterpret_cast<float*>(sOutB);
+    const int chunk = et & 7, rg = et >> 3;          // step 2: rows rg + 32*j, 16-B chunk `chunk`
+    float* sY = reinterpret_cast<float*>(sOutB);
     const snb_conv_epilogue& e = p.e;
+    const bool has_res = e.residual != nullptr, has_stats = e.stats != nullptr;
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bias4;
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
@@ -245,73 +292,68 @@ conv_c32_tc_kernel(const Params p) {
       const uint32_t accphase = (it / NACC) & 1;
       const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
       const int q0 = tt * p.step - p.dil;
-      mbar_wait(&tfull[acc], accphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 128;
-      float v[32];
-      // pass 1: centre tap kw=1 -> out[m]
-      tmem_ld32(taddr + 32, v);
+      // coordinates of this thread's 4 output rows (one division per tile, then increments)
+      int hh[4], ww[4]; bool okr[4];
       {
-        float* row = sOut + m * 32;
+        int q = q0 + rg;
+        int h = floordiv(q, p.P), w = q - h * p.P;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(row + ((c ^ (m & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      }
-      epi_bar();
-      // pass 2: kw=0 reads input w-dil: Y0[m] belongs to out[m + dil]
-      tmem_ld32(taddr, v);
-      if (m + p.dil < 128) {
-        const int r = m + p.dil;
-        float* row = sOut + r * 32;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4* q4 = reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 2));
-          float4 o = *q4;
-          o.x += v[4 * c]; o.y += v[4 * c + 1]; o.z += v[4 * c + 2]; o.w += v[4 * c + 3];
-          *q4 = o;
+        for (int j = 0; j < 4; ++j) {
+          const int r = rg + 32 * j;
+          hh[j] = h; ww[j] = w;
+          okr[j] = r >= p.dil && r < 128 - p.dil && h >= 0 && h < p.H && w < p.W;
+          w += 32;
+          while (w >= p.P) { w -= p.P; ++h; }
         }
       }
-      epi_bar();
-      // pass 3: kw=2 reads input w+dil: Y2[m] belongs to out[m - dil]
-      tmem_ld32(taddr + 64, v);
+      // residual rows do not depend on the MMA: put their loads in flight before waiting on TMEM
+      float4 res[4];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (okr[j]) res[j] = __ldg(reinterpret_cast<const float4*>(
+                               e.residual + (((size_t)slice * p.H + hh[j]) * p.W + ww[j]) * 32 + chunk * 4));
+        }
+      }
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 128 + half * 16;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float v[16];
+        tmem_ld16(taddr + kw * 32, v);
+        float* row = sY + kw * (128 * 32) + m * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(row + (((half * 4 + c) ^ (m & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);      // this warp is done with the TMEM slot
-      if (m >= p.dil) {
-        const int r = m - p.dil;
-        float* row = sOut + r * 32;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4* q4 = reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 2));
-          float4 o = *q4;
-          o.x += v[4 * c]; o.y += v[4 * c + 1]; o.z += v[4 * c + 2]; o.w += v[4 * c + 3];
-          *q4 = o;
-        }
-      }
       epi_bar();
-      // final pass: coalesced (8 lanes = one 128-B position) bias / stats / BN / LeakyReLU / residual / store
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = rg + 16 * j;
-        const int q = q0 + r;
-        const int h = floordiv(q, p.P), w = q - h * p.P;
-        const bool ok = r >= p.dil && r < 128 - p.dil && q >= 0 && h < p.H && w < p.W;
-        if (!ok) continue;
-        float4 o = *reinterpret_cast<const float4*>(sOut + r * 32 + ((chunk ^ (r & 7)) << 2));
-        o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
-        s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
-        s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+      for (int j = 0; j < 4; ++j) {
+        if (!okr[j]) continue;
+        const int r = rg + 32 * j;
+        const int r0 = r - p.dil, r2 = r + p.dil;    // kw=0 reads input w-dil: Y0[r-dil]; kw=2: Y2[r+dil]
+        const float4 a = *reinterpret_cast<const float4*>(sY + r0 * 32 + ((chunk ^ (r0 & 7)) << 2));
+        const float4 b = *reinterpret_cast<const float4*>(sY + 128 * 32 + r * 32 + ((chunk ^ (r & 7)) << 2));
+        const float4 c = *reinterpret_cast<const float4*>(sY + 2 * 128 * 32 + r2 * 32 + ((chunk ^ (r2 & 7)) << 2));
+        float4 o;
+        o.x = (a.x + b.x) + c.x + bias4.x; o.y = (a.y + b.y) + c.y + bias4.y;
+        o.z = (a.z + b.z) + c.z + bias4.z; o.w = (a.w + b.w) + c.w + bias4.w;
+        if (has_stats) {
+          s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+          s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+        }
         if (e.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
         if (e.lrelu) { o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w); }
-        const size_t gi = (((size_t)slice * p.H + h) * p.W + w) * 32 + chunk * 4;
-        if (e.residual) {
-          const float4 rr = __ldg(reinterpret_cast<const float4*>(e.residual + gi));
-          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-        }
-        *reinterpret_cast<float4*>(p.y + gi) = o;
+        if (has_res) { o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w; }
+        *reinterpret_cast<float4*>(p.y + (((size_t)slice * p.H + hh[j]) * p.W + ww[j]) * 32 + chunk * 4) = o;
       }
-      if (e.stats) {
+      if (has_stats) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 8); s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 16);
@@ -319,12 +361,17 @@ conv_c32_tc_kernel(const Params p) {
         }
         if (lane < 8) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { sRed[quad * 64 + lane * 4 + c] = s1[c]; sRed[quad * 64 + 32 + lane * 4 + c] = s2[c]; }
+          for (int c = 0; c < 4; ++c) { sRed[ew * 64 + lane * 4 + c] = s1[c]; sRed[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
         }
         epi_bar();
-        if (et < 64) e.stats[(size_t)tile * 64 + et] = sRed[et] + sRed[64 + et] + sRed[128 + et] + sRed[192 + et];
+        if (et < 64) {
+          float a = 0.f;
+#pragma unroll
+          for (int wq = 0; wq < NUM_EPI_WARPS; ++wq) a += sRed[wq * 64 + et];
+          e.stats[(size_t)tile * 64 + et] = a;
+        }
       }
-      epi_bar();     // sOut / sRed are rewritten by the next tile
+      epi_bar();     // sY / sRed are rewritten by the next tile
     }
   }
 

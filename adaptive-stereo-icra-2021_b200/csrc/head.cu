@@ -40,8 +40,8 @@ conv_c32_taps_kernel(const float* __restrict__ x, const float* __restrict__ w, f
   float acc[NTP];
 #pragma unroll
   for (int j = 0; j < NTP; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {     // not unrolled: a full unroll hoists all 32xNT weights into registers and spills
     const float4 xa = *reinterpret_cast<const float4*>(&sA[t][(c ^ (t & 7)) * 4]);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {

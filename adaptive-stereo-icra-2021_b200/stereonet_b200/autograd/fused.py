@@ -28,7 +28,7 @@ import os
 # Convolution backend for the stride-1 3x3 / 3x3x3 32->32 layers: "tc3" = tcgen05 3xTF32 (fp32-grade, default),
 # "tc1" = tcgen05 single-pass TF32 (faster, ~1e-3 relative), "ffma" = fp32 CUDA-core kernel.  All three are this
 # library's own kernels; the switch exists for measurement and cross-checking, not as a fallback.
-CONV_BACKEND = os.environ.get("SNB200_CONV", "ffma")
+CONV_BACKEND = os.environ.get("SNB200_CONV", "tc3")
 
 
 def set_conv_backend(name):

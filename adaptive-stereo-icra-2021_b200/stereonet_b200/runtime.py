@@ -18,8 +18,18 @@ class StereoEngine:
   def invalidate(self):
     self._graphs.clear()
 
-  def _forward(self, left, right):
-    fl, fr = self.feature_net(left), self.feature_net(right)
+  def _forward(self, pair):
+    """pair = [left; right] stacked on the batch dim.  In eval mode both images go through the feature extractor as
+    one batch (no op mixes samples when BN uses running statistics, SURVEY.md §8e: bit-identical to two calls, half
+    the launches); in train mode the two calls stay separate because BN batch statistics are per call
+    (adapt.py:72: feature_net(left), feature_net(right))."""
+    B = pair.shape[0] // 2
+    left, right = pair[:B], pair[B:]
+    if self.feature_net.training:
+      fl, fr = self.feature_net(left), self.feature_net(right)
+    else:
+      feats = self.feature_net(pair)
+      fl, fr = feats[:B], feats[B:]
     return self.stereo_net(left, fl, fr, "l", output_cost_volume=self.output_cost_volume)
 
   def _entry(self, shape, device):
@@ -27,24 +37,24 @@ class StereoEngine:
     e = self._graphs.get(key)
     if e is not None:
       return e
-    left = torch.zeros(shape, device=device, dtype=torch.float32)
-    right = torch.zeros(shape, device=device, dtype=torch.float32)
+    pair = torch.zeros((2 * shape[0],) + tuple(shape[1:]), device=device, dtype=torch.float32)
+    left, right = pair[:shape[0]], pair[shape[0]:]
     with torch.no_grad():
       side = torch.cuda.Stream(device=device)
       side.wait_stream(torch.cuda.current_stream(device))
       with torch.cuda.stream(side):
         for _ in range(2):                       # warm the derived-weight caches / allocator outside the capture
-          self._forward(left, right)
+          self._forward(pair)
       torch.cuda.current_stream(device).wait_stream(side)
       n0 = ops.LAUNCHES
       if self.use_graph:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-          out = self._forward(left, right)
+          out = self._forward(pair)
       else:
-        graph, out = None, self._forward(left, right)
+        graph, out = None, self._forward(pair)
       launches = ops.LAUNCHES - n0
-    e = dict(left=left, right=right, graph=graph, out=out, launches=launches)
+    e = dict(pair=pair, left=left, right=right, graph=graph, out=out, launches=launches)
     self._graphs[key] = e
     return e
 
@@ -55,7 +65,7 @@ class StereoEngine:
     if e["graph"] is not None:
       e["graph"].replay()
     else:
-      e["out"] = self._forward(e["left"], e["right"])
+      e["out"] = self._forward(e["pair"])
     return e["out"], e["launches"]
 
   @torch.no_grad()
