@@ -31,10 +31,19 @@ __device__ __forceinline__ void load_tap(SmemC32& s, int stage, const float* __r
   for (int j = 0; j < 8; ++j) {
     const int r = (t >> 3) + 16 * j;
     const int4 c = s.coord[r];
-    const int id = c.y + kd - g.pd;
-    const int ih = c.z * g.stride + kh * g.dil - g.ph;
-    const int iw = c.w * g.stride + kw * g.dil - g.pw;
-    const bool ok = (c.x >= 0) && (unsigned)id < (unsigned)g.D && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
+    int id, ih, iw;
+    bool ok = c.x >= 0;
+    if (!g.transposed) {
+      id = c.y + kd - g.pd;
+      ih = c.z * g.stride + kh * g.dil - g.ph;
+      iw = c.w * g.stride + kw * g.dil - g.pw;
+    } else {          // data gradient: written position o reads (o + p - k*dil)/stride when divisible
+      id = c.y + g.pd - kd;
+      const int th = c.z + g.ph - kh * g.dil, tw = c.w + g.pw - kw * g.dil;
+      ok = ok && th >= 0 && tw >= 0 && (th % g.stride) == 0 && (tw % g.stride) == 0;
+      ih = th / g.stride; iw = tw / g.stride;
+    }
+    ok = ok && (unsigned)id < (unsigned)g.D && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
     const size_t off = ok ? ((((size_t)c.x * g.D + id) * g.H + ih) * g.W + iw) * 32 + chunk * 4 : 0;
     cp_async16(&s.a[stage][r][(chunk ^ (r & 7)) * 4], x + off, ok);
   }
@@ -161,8 +170,9 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
     const int t = i % taps;
     const int ci = (i / taps) % cin;
     const int co = i / (taps * cin);
-    if (mode == 0) out[((size_t)t * cin + ci) * cout + co] = w[i];                 // [t][cin][cout]
-    else           out[((size_t)(taps - 1 - t) * cout + co) * cin + ci] = w[i];    // [t'][cout as K][cin as N]
+    if (mode == 0)      out[((size_t)t * cin + ci) * cout + co] = w[i];                 // [t][cin][cout]
+    else if (mode == 1) out[((size_t)(taps - 1 - t) * cout + co) * cin + ci] = w[i];    // [t'][cout as K][cin as N]
+    else                out[((size_t)t * cout + co) * cin + ci] = w[i];                 // [t][cout as K][cin as N]
   }
 }
 
@@ -195,7 +205,7 @@ extern "C" int snb_conv_c32(const float* x, const float* wprep, float* y, const 
 }
 
 extern "C" int snb_prep_conv_weights(const float* w, float* out, int cout, int cin, int taps, int mode, void* stream) {
-  SNB_REQUIRE(w && out && cout > 0 && cin > 0 && taps > 0 && (mode == 0 || mode == 1), "snb_prep_conv_weights: bad args");
+  SNB_REQUIRE(w && out && cout > 0 && cin > 0 && taps > 0 && mode >= 0 && mode <= 2, "snb_prep_conv_weights: bad args");
   const int n = cout * cin * taps;
   prep_weights_kernel<<<snb_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, out, cout, cin, taps, mode);
   SNB_LAUNCH_CHECK("prep_weights_kernel");

@@ -427,7 +427,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
 
 static int tc_setup(const snb_conv_geom* g, tc::Params& p, const char* who) {
   SNB_REQUIRE(g != nullptr, "%s: null geometry", who);
-  SNB_REQUIRE(g->stride == 1 && g->KH == 3 && g->KW == 3 && (g->KD == 1 || g->KD == 3), "%s: needs a stride-1 3x3(x3) conv", who);
+  SNB_REQUIRE(g->transposed == 0 && g->stride == 1 && g->KH == 3 && g->KW == 3 && (g->KD == 1 || g->KD == 3), "%s: needs a stride-1 3x3(x3) conv", who);
   SNB_REQUIRE(g->OD == g->D && g->OH == g->H && g->OW == g->W && g->ph == g->dil && g->pw == g->dil &&
               g->pd == (g->KD == 3 ? 1 : 0), "%s: needs 'same' padding", who);
   SNB_REQUIRE(g->dil >= 1 && g->dil <= 16, "%s: dilation out of range", who);

@@ -146,6 +146,69 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
   }
 }
 
+// Weight gradient of the small-Cin convolutions: dW[k][co] = sum_p dy[p][co] * in[k @ p], k = (ci,kh,kw).
+// Same tiling / input-tile loader as the forward kernel; the dy tile (512 positions x 32) is staged with cp.async.
+// 256 threads = 32 couts x 8 groups, group g owns k = g, g+8, ...  Writes partial[tile][K][32].
+template <int CIN, int KS, int S, class Loader>
+__global__ void __launch_bounds__(256)
+conv_small_wgrad_kernel(Loader ld, const float* __restrict__ dy, float* __restrict__ partial, int OH, int OW, int pad) {
+  using T = TileDims<CIN, KS, S>;
+  constexpr int K = CIN * KS * KS;
+  constexpr int JMAX = (K + 7) / 8;
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;
+  float* sDy = smem + T::IN_FLOATS;            // [512][32]
+  const int t = threadIdx.x;
+  const int tiles_x = (OW + TW - 1) / TW, tiles_y = (OH + TH - 1) / TH;
+  const int tile = blockIdx.x;
+  const int b = tile / (tiles_x * tiles_y);
+  const int trem = tile - b * tiles_x * tiles_y;
+  const int oy0 = (trem / tiles_x) * TH, ox0 = (trem % tiles_x) * TW;
+  const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
+  {
+    const int chunk = t & 7;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int p = (t >> 3) + 32 * j;          // 0..511
+      const int oy = oy0 + (p >> 6), ox = ox0 + (p & 63);
+      const bool ok = oy < OH && ox < OW;
+      cp_async16(sDy + p * 32 + chunk * 4, dy + (ok ? (((size_t)b * OH + oy) * OW + ox) * 32 + chunk * 4 : 0), ok);
+    }
+    cp_async_commit();
+  }
+  for (int i = t; i < CIN * T::IH * T::IW; i += 256) {
+    const int c = i % T::IW;
+    const int r = (i / T::IW) % T::IH;
+    const int ci = i / (T::IW * T::IH);
+    sIn[(ci * T::IH + r) * T::ROW + col_index<S, T::IWP>(c)] = ld(b, ci, iy0 + r, ix0 + c);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const int co = t & 31, grp = t >> 5;
+  int basej[JMAX];
+  float acc[JMAX];
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j) {
+    int k = grp + 8 * j;
+    if (k >= K) k = K - 1;                      // clamped duplicates are discarded at the end
+    const int kw = k % KS, kh = (k / KS) % KS, ci = k / (KS * KS);
+    basej[j] = (ci * T::IH + kh) * T::ROW + ((S == 2) ? (kw & 1) * T::IWP + (kw >> 1) : kw);
+    acc[j] = 0.f;
+  }
+  for (int p = 0; p < TH * TW; ++p) {
+    const float g = sDy[p * 32 + co];
+    const int o = (p >> 6) * S * T::ROW + (p & 63);
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) acc[j] = fmaf(g, sIn[basej[j] + o], acc[j]);
+  }
+  float* out = partial + (size_t)blockIdx.x * K * 32;
+#pragma unroll
+  for (int j = 0; j < JMAX; ++j) {
+    const int k = grp + 8 * j;
+    if (k < K) out[k * 32 + co] = acc[j];
+  }
+}
+
 }  // namespace
 
 extern "C" int snb_conv5x5s2_c3(const float* img, const float* w, const float* bias, float* y, int B, int H, int W, void* stream) {
@@ -176,5 +239,36 @@ extern "C" int snb_refine_in_conv(const float* coarse, const float* rgb, const f
   const int tiles = snb_refine_in_conv_num_tiles(B, H, W);
   kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, z, up, H, W, 1, *e);
   SNB_LAUNCH_CHECK("refine_in_conv");
+  return 0;
+}
+
+extern "C" int snb_conv5x5s2_c3_num_tiles(int B, int H, int W) {
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  return B * ((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
+}
+
+extern "C" int snb_conv5x5s2_c3_wgrad(const float* img, const float* dy, float* partial, int B, int H, int W, void* stream) {
+  SNB_REQUIRE(img && dy && partial && B > 0 && H > 0 && W > 0, "snb_conv5x5s2_c3_wgrad: bad args");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  using T = TileDims<3, 5, 2>;
+  ImgLoader ld{img, 3, H, W};
+  auto kern = conv_small_wgrad_kernel<3, 5, 2, ImgLoader>;
+  const int smem = (T::IN_FLOATS + 512 * 32) * 4;
+  SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<snb_conv5x5s2_c3_num_tiles(B, H, W), 256, smem, (cudaStream_t)stream>>>(ld, dy, partial, OH, OW, 2);
+  SNB_LAUNCH_CHECK("conv5x5s2_c3_wgrad");
+  return 0;
+}
+
+extern "C" int snb_refine_in_wgrad(const float* coarse, const float* rgb, const float* dz, float* partial,
+                                   int B, int h, int w_, int H, int W, float disp_scale, void* stream) {
+  SNB_REQUIRE(coarse && rgb && dz && partial && B > 0 && h > 0 && w_ > 0 && H > 0 && W > 0, "snb_refine_in_wgrad: bad args");
+  using T = TileDims<4, 3, 1>;
+  RefineLoader ld{coarse, rgb, h, w_, H, W, (float)h / (float)H, (float)w_ / (float)W, disp_scale};
+  auto kern = conv_small_wgrad_kernel<4, 3, 1, RefineLoader>;
+  const int smem = (T::IN_FLOATS + 512 * 32) * 4;
+  SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<snb_refine_in_conv_num_tiles(B, H, W), 256, smem, (cudaStream_t)stream>>>(ld, dz, partial, H, W, 1);
+  SNB_LAUNCH_CHECK("refine_in_wgrad");
   return 0;
 }

@@ -119,13 +119,13 @@ tapsum_softargmin_kernel(const float* __restrict__ taps, const float* __restrict
 
 __global__ void __launch_bounds__(256)
 tapsum_refine_out_kernel(const float* __restrict__ taps, const float* __restrict__ bias, const float* __restrict__ up,
-                         float* __restrict__ out, int H, int W) {
+                         float* __restrict__ out, int H, int W, int relu) {
   const int x = blockIdx.x * 256 + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
   const size_t plane = (size_t)H * W;
   const float* tp = taps + (size_t)b * 9 * plane;
-  float c = bias[0];
+  float c = bias ? bias[0] : 0.f;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int yy = y + kh - 1;
@@ -137,8 +137,8 @@ tapsum_refine_out_kernel(const float* __restrict__ taps, const float* __restrict
     }
   }
   const size_t o = (size_t)b * plane + (size_t)y * W + x;
-  const float v = up[o] + c;
-  out[o] = v > 0.f ? v : 0.f;
+  const float v = (up ? up[o] : 0.f) + c;
+  out[o] = (relu && v < 0.f) ? 0.f : v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -210,9 +210,9 @@ extern "C" int snb_tapsum_softargmin(const float* taps, const float* bias, float
 }
 
 extern "C" int snb_tapsum_refine_out(const float* taps, const float* bias, const float* up, float* out,
-                                     int B, int H, int W, void* stream) {
-  SNB_REQUIRE(taps && bias && up && out && B > 0 && H > 0 && W > 0, "snb_tapsum_refine_out: bad args");
-  tapsum_refine_out_kernel<<<dim3(snb_ceil_div(W, 256), H, B), 256, 0, (cudaStream_t)stream>>>(taps, bias, up, out, H, W);
+                                     int B, int H, int W, int relu, void* stream) {
+  SNB_REQUIRE(taps && out && B > 0 && H > 0 && W > 0, "snb_tapsum_refine_out: bad args");
+  tapsum_refine_out_kernel<<<dim3(snb_ceil_div(W, 256), H, B), 256, 0, (cudaStream_t)stream>>>(taps, bias, up, out, H, W, relu);
   SNB_LAUNCH_CHECK("tapsum_refine_out_kernel");
   return 0;
 }

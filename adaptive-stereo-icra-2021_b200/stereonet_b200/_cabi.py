@@ -7,7 +7,7 @@ LIB_PATH = os.environ.get("SNB200_LIB", os.path.join(os.path.dirname(_HERE), "li
 
 
 class ConvGeom(C.Structure):
-  _fields_ = [(n, C.c_int) for n in ("B", "D", "H", "W", "OD", "OH", "OW", "KD", "KH", "KW", "stride", "dil", "pd", "ph", "pw")]
+  _fields_ = [(n, C.c_int) for n in ("B", "D", "H", "W", "OD", "OH", "OW", "KD", "KH", "KW", "stride", "dil", "pd", "ph", "pw", "transposed")]
 
 
 class ConvEpilogue(C.Structure):
@@ -37,11 +37,24 @@ SIGNATURES = {
   "snb_refine_in_conv_num_tiles": (_I, [_I, _I, _I]),
   "snb_conv_c32_taps": (_I, [_P, _P, _P, _LL, _I, _I, _P]),
   "snb_tapsum_softargmin": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-  "snb_tapsum_refine_out": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+  "snb_tapsum_refine_out": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
   "snb_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_upsample_bilinear_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_bn_finalize": (_I, [_P, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
   "snb_bn_apply": (_I, [_P, _P, _P, _P, _P, _LL, _I, _P]),
+  "snb_bwd_num_blocks": (_I, [_LL]),
+  "snb_bn_lrelu_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P]),
+  "snb_bn_lrelu_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _P, _P]),
+  "snb_reduce_partials": (_I, [_P, _I, _I, _P, _F, _P]),
+  "snb_channel_sum": (_I, [_P, _P, _LL, _P]),
+  "snb_conv_c32_wgrad": (_I, [_P, _P, _P, _GP, _P]),
+  "snb_conv_c32_wgrad_num_partials": (_I, [_GP]),
+  "snb_conv5x5s2_c3_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+  "snb_conv5x5s2_c3_num_tiles": (_I, [_I, _I, _I]),
+  "snb_refine_in_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+  "snb_softargmin_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+  "snb_relu_bwd": (_I, [_P, _P, _P, _LL, _P]),
+  "snb_conv_c32_taps_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -63,6 +63,20 @@ def bn_fold(bn):
   return _cached(bn, "fold", [bn.weight, bn.bias, bn.running_mean, bn.running_var], make)
 
 
+def bn_invstd(bn):
+  def make():
+    with torch.no_grad():
+      return torch.rsqrt(bn.running_var + ops.BN_EPS).contiguous()
+  return _cached(bn, "invstd", [bn.running_var], make)
+
+
+def conv3x3_c32_dgrad(dy, conv, g, residual=None):
+  """Data gradient of a stride-1 'same' 3x3(x3) conv: the same convolution kernels with flipped/transposed weights."""
+  if CONV_BACKEND == "ffma":
+    return ops.conv_c32(dy, wprep(conv, 1), g, residual=residual)
+  return ops.conv_c32_tc(dy, wprep_tc(conv, 1), g, residual=residual, passes=3 if CONV_BACKEND == "tc3" else 1)
+
+
 def _needs_grad(*tensors_or_modules):
   if not torch.is_grad_enabled():
     return False
@@ -94,7 +108,7 @@ def conv_plain(x, conv, ksize, stride):
   g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
   if _needs_grad(x, conv):
     from . import functions
-    return functions.ConvC32.apply(x, conv.weight, conv.bias, ksize, stride, 1)
+    return functions.ConvC32.apply(x, conv.weight, conv.bias, conv, ksize, stride)
   if ksize == 3 and stride == 1:
     y, _ = conv3x3_c32(x, conv, g, bias=conv.bias.detach())
   else:

@@ -48,10 +48,15 @@ def geom(x_shape, ksize, stride=1, dil=1, pad=None):
     pad = dil * (ksize - 1) // 2
   OH = (H + 2 * pad - dil * (ksize - 1) - 1) // stride + 1
   OW = (W + 2 * pad - dil * (ksize - 1) - 1) // stride + 1
-  g = ConvGeom(B, D, H, W, D, OH, OW, ksize if three_d else 1, ksize, ksize, stride, dil, 1 if three_d else 0, pad, pad)
+  g = ConvGeom(B, D, H, W, D, OH, OW, ksize if three_d else 1, ksize, ksize, stride, dil, 1 if three_d else 0, pad, pad, 0)
   if three_d:
     g.OD = D + 2 * 1 - (ksize - 1) - 1 + 1
   return g
+
+
+def geom_transposed(g):
+  """Geometry of the data gradient of conv `g`: reads dy [B,OD,OH,OW], writes dx [B,D,H,W] (snb_conv_geom.transposed)."""
+  return ConvGeom(g.B, g.OD, g.OH, g.OW, g.D, g.H, g.W, g.KD, g.KH, g.KW, g.stride, g.dil, g.pd, g.ph, g.pw, 1)
 
 
 def out_shape(g, three_d):
@@ -64,6 +69,8 @@ def prep_conv_weights(w, mode=0):
   cout, cin = w.shape[0], w.shape[1]
   taps = w[0, 0].numel()
   out = torch.empty((taps, cin, cout) if mode == 0 else (taps, cout, cin), device=w.device, dtype=torch.float32)
+  if mode not in (0, 1, 2):
+    raise ValueError(mode)
   check(_cabi.lib().snb_prep_conv_weights(_p(w), _p(out), cout, cin, taps, mode, _stream(w)), "snb_prep_conv_weights")
   _count()
   return out
@@ -193,11 +200,11 @@ def tapsum_softargmin(taps, bias, want_cost):
   return cost, pred
 
 
-def tapsum_refine_out(taps, bias, up):
+def tapsum_refine_out(taps, bias, up, relu=True):
   B, _, H, W = taps.shape
   out = torch.empty((B, H, W), device=taps.device, dtype=torch.float32)
-  check(_cabi.lib().snb_tapsum_refine_out(_p(taps), _p(bias.detach()), _p(up), _p(out), B, H, W, _stream(taps)),
-        "snb_tapsum_refine_out")
+  check(_cabi.lib().snb_tapsum_refine_out(_p(taps), _p(None if bias is None else bias.detach()), _p(up), _p(out), B, H, W,
+                                          1 if relu else 0, _stream(taps)), "snb_tapsum_refine_out")
   _count()
   return out
 
@@ -242,3 +249,111 @@ def bn_apply(z, scale, shift, residual=None, lrelu=True):
                                  _stream(z)), "snb_bn_apply")
   _count()
   return y
+
+
+# ------------------------------------------------------------------------------------------------ backward wrappers
+def reduce_partials(partial, mul=1.0):
+  """[n, len] per-block partials -> [len] (fixed-order double accumulation on the device)."""
+  n = partial.shape[0]
+  ln = partial.numel() // n
+  out = torch.empty((ln,), device=partial.device, dtype=torch.float32)
+  check(_cabi.lib().snb_reduce_partials(_p(partial), n, ln, _p(out), float(mul), _stream(partial)), "snb_reduce_partials")
+  _count()
+  return out
+
+
+def bn_lrelu_bwd(z, dy, scale, shift, mean, invstd, train, lrelu=True):
+  """Backward of y = LeakyReLU(z*scale + shift) with (train) batch-stat BatchNorm.  Returns dz, dgamma, dbeta, dbias."""
+  _req(z, "z"); _req(dy, "dy")
+  npos = z.numel() // 32
+  nb = _cabi.lib().snb_bwd_num_blocks(npos)
+  part = torch.empty((nb, 64), device=z.device, dtype=torch.float32)
+  check(_cabi.lib().snb_bn_lrelu_bwd_reduce(_p(z), _p(dy), _p(scale), _p(shift), _p(mean), _p(invstd), _p(part), npos,
+                                            1 if lrelu else 0, _stream(z)), "snb_bn_lrelu_bwd_reduce")
+  _count()
+  sums = reduce_partials(part)
+  dz = torch.empty_like(z)
+  dzpart = torch.empty((nb, 32), device=z.device, dtype=torch.float32)
+  check(_cabi.lib().snb_bn_lrelu_bwd_apply(_p(z), _p(dy), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), npos,
+                                           1 if train else 0, 1 if lrelu else 0, _p(dz), _p(dzpart), _stream(z)),
+        "snb_bn_lrelu_bwd_apply")
+  _count()
+  return dz, sums[32:], sums[:32], reduce_partials(dzpart)
+
+
+def channel_sum(x):
+  _req(x, "x")
+  npos = x.numel() // 32
+  nb = _cabi.lib().snb_bwd_num_blocks(npos)
+  part = torch.empty((nb, 32), device=x.device, dtype=torch.float32)
+  check(_cabi.lib().snb_channel_sum(_p(x), _p(part), npos, _stream(x)), "snb_channel_sum")
+  _count()
+  return reduce_partials(part)
+
+
+def conv_c32_wgrad(x, dz, g, wshape):
+  """Weight gradient of a 32->32 conv in PyTorch layout `wshape` = [32,32,*k]."""
+  _req(x, "x"); _req(dz, "dz")
+  n = _cabi.lib().snb_conv_c32_wgrad_num_partials(C.byref(g))
+  taps = g.KD * g.KH * g.KW
+  part = torch.empty((n, taps * 1024), device=x.device, dtype=torch.float32)
+  check(_cabi.lib().snb_conv_c32_wgrad(_p(x), _p(dz), _p(part), C.byref(g), _stream(x)), "snb_conv_c32_wgrad")
+  _count()
+  dw = reduce_partials(part).view(taps, 32, 32)                  # [tap][cin][cout]
+  return dw.permute(2, 1, 0).reshape(wshape).contiguous()       # layout change only
+
+
+def conv5x5s2_c3_wgrad(img, dy):
+  B, _, H, W = img.shape
+  n = _cabi.lib().snb_conv5x5s2_c3_num_tiles(B, H, W)
+  part = torch.empty((n, 75 * 32), device=img.device, dtype=torch.float32)
+  check(_cabi.lib().snb_conv5x5s2_c3_wgrad(_p(img), _p(_req(dy, "dy")), _p(part), B, H, W, _stream(img)), "snb_conv5x5s2_c3_wgrad")
+  _count()
+  return reduce_partials(part).view(3, 5, 5, 32).permute(3, 0, 1, 2).contiguous()
+
+
+def refine_in_wgrad(coarse, rgb, dz):
+  B, h, w_ = coarse.shape
+  H, W = rgb.shape[-2:]
+  n = _cabi.lib().snb_refine_in_conv_num_tiles(B, H, W)
+  part = torch.empty((n, 36 * 32), device=rgb.device, dtype=torch.float32)
+  check(_cabi.lib().snb_refine_in_wgrad(_p(coarse), _p(rgb), _p(_req(dz, "dz")), _p(part), B, h, w_, H, W, float(W) / float(w_),
+                                        _stream(rgb)), "snb_refine_in_wgrad")
+  _count()
+  return reduce_partials(part).view(4, 3, 3, 32).permute(3, 0, 1, 2).contiguous()
+
+
+def softargmin_bwd(cost, pred, dpred, dcost_extra=None):
+  B, D, H, W = cost.shape
+  dcost = torch.empty_like(cost)
+  check(_cabi.lib().snb_softargmin_bwd(_p(_req(cost, "cost")), _p(pred), _p(dpred), _p(dcost_extra), _p(dcost), B, D, H, W,
+                                       _stream(cost)), "snb_softargmin_bwd")
+  _count()
+  return dcost
+
+
+def relu_bwd(out, dout):
+  dres = torch.empty_like(out)
+  check(_cabi.lib().snb_relu_bwd(_p(_req(out, "out")), _p(_req(dout, "dout")), _p(dres), out.numel(), _stream(out)), "snb_relu_bwd")
+  _count()
+  return dres
+
+
+def conv_c32_taps_bwd(x, w, g, ntaps):
+  """Backward of the 32->1 conv given g = d(conv output) [B,(D),H,W].  Returns dx, dw [1,32,*k], db [1]."""
+  _req(x, "x"); _req(g, "g")
+  if x.dim() == 5:
+    B, D, H, W, _ = x.shape
+  else:
+    B, H, W, _ = x.shape
+    D = 1
+  npos = B * D * H * W
+  nblk = (npos + 127) // 128
+  part = torch.empty((nblk, ntaps * 32 + 1), device=x.device, dtype=torch.float32)
+  dx = torch.empty_like(x)
+  check(_cabi.lib().snb_conv_c32_taps_bwd(_p(x), _p(_req(w.detach(), "w")), _p(g), _p(dx), _p(part), B, D, H, W, ntaps, _stream(x)),
+        "snb_conv_c32_taps_bwd")
+  _count()
+  red = reduce_partials(part)
+  dw = red[:ntaps * 32].view(ntaps, 32).t().reshape(w.shape).contiguous()
+  return dx, dw, red[ntaps * 32:].clone()

@@ -40,6 +40,9 @@ typedef struct {
   int stride;         /* H/W stride (depth stride is always 1) */
   int dil;            /* H/W dilation (depth dilation is always 1) */
   int pd, ph, pw;     /* zero padding */
+  int transposed;     /* 0: y = conv(x).  1: data gradient of that conv (x := dy [B,D,H,W], y := dx [B,OD,OH,OW]):
+                         tap (kd,kh,kw) reads x at ((o + p - k*dil) / stride) when divisible; weights from
+                         snb_prep_conv_weights mode 2.  Needed for the stride-2 5x5 layers (stereo_net.py:64-70). */
 } snb_conv_geom;
 
 /* Epilogue of the 32->32 convolution: z = conv + bias; stats += (sum z, sum z^2) per channel;
@@ -60,7 +63,8 @@ SNB_API int snb_version(void);
 SNB_API int snb_conv_c32_num_tiles(const snb_conv_geom* g);
 
 /* Repack a PyTorch conv weight [Cout][Cin][taps] into the kernels' [taps][Cin][Cout] layout.
- * mode 0: forward weights.  mode 1: data-gradient weights (taps flipped, Cin/Cout swapped). */
+ * mode 0: forward weights.  mode 1: data-gradient weights (taps flipped, Cin/Cout swapped) for a stride-1 'same' conv run as
+ * a plain convolution.  mode 2: Cin/Cout swapped, taps NOT flipped, for snb_conv_geom.transposed = 1. */
 SNB_API int snb_prep_conv_weights(const float* w, float* out, int cout, int cin, int taps, int mode, void* stream);
 
 /* Difference cost volume — replaces the host-side zero+H2D+24-slice loop of stereo_net.py:173-184.
@@ -111,9 +115,10 @@ SNB_API int snb_conv_c32_taps(const float* x, const float* w /*[1][32][ntaps]*/,
 SNB_API int snb_tapsum_softargmin(const float* taps /*[B,D,27,H,W]*/, const float* bias /*[1]*/, float* cost_out /*[B,D,H,W]*/,
                           float* pred /*[B,H,W]*/, int B, int D, int H, int W, void* stream);
 
-/* Second half of conv2d_out fused with the residual add + ReLU (stereo_net.py:121): out = relu(up + bias + sum taps). */
+/* Second half of conv2d_out fused with the residual add + ReLU (stereo_net.py:121): out = relu(up + bias + sum taps).
+ * bias / up may be NULL and relu = 0 turns it into a plain 3x3 tap gather (used by the refinement-head data gradient). */
 SNB_API int snb_tapsum_refine_out(const float* taps /*[B,9,H,W]*/, const float* bias, const float* up, float* out,
-                          int B, int H, int W, void* stream);
+                          int B, int H, int W, int relu, void* stream);
 
 /* out[b,y,x] = mul * bilinear(in[b], size (H,W), align_corners=False) — stereo_net.py:201-202 (mul = 2**k). */
 SNB_API int snb_upsample_bilinear(const float* in, float* out, int B, int h, int w, int H, int W, float mul, void* stream);
@@ -129,6 +134,43 @@ SNB_API int snb_bn_finalize(const float* stats, int ntiles, long long count, con
 /* y = [residual +] LeakyReLU(z*scale + shift) over n positions x 32 channels. */
 SNB_API int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,
                  long long npos, int lrelu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backward pass of the adaptation step (autograd of stereo_net.py:79-85,168-207, triggered at adapt.py:390).
+ * Data gradients of the 3x3 / 3x3x3 convolutions reuse snb_conv_c32 / snb_conv_c32_tc with mode-1 weights; the
+ * stride-2 5x5 layers use snb_conv_c32 with snb_conv_geom.transposed = 1 and mode-2 weights.
+ * --------------------------------------------------------------------------------------------------------------- */
+/* Number of blocks (rows of the partial buffers) the elementwise backward kernels use for npos positions. */
+SNB_API int snb_bwd_num_blocks(long long npos);
+/* BatchNorm(+LeakyReLU) backward, pass 1: partial[blk][0:32] = sum du, [32:64] = sum du*zhat with
+ * u = z*scale + shift, du = dy * (u > 0 ? 1 : 0.2) (or dy when lrelu = 0), zhat = (z - mean) * invstd. */
+SNB_API int snb_bn_lrelu_bwd_reduce(const float* z, const float* dy, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, float* partial, long long npos, int lrelu, void* stream);
+/* pass 2: dz = scale * (du - train * (sums[0:32]/N + zhat * sums[32:64]/N)); dzpart[blk][32] = per-block sum of dz. */
+SNB_API int snb_bn_lrelu_bwd_apply(const float* z, const float* dy, const float* scale, const float* shift, const float* mean,
+                           const float* invstd, const float* sums, long long npos, int train, int lrelu,
+                           float* dz, float* dzpart, void* stream);
+/* out[j] = mul * sum_i partial[i][j], i < n, j < len (fixed order, double accumulation). */
+SNB_API int snb_reduce_partials(const float* partial, int n, int len, float* out, float mul, void* stream);
+/* partial[blk][32] = per-channel sums of x [npos][32] (bias gradient of a plain convolution). */
+SNB_API int snb_channel_sum(const float* x, float* partial, long long npos, void* stream);
+/* Weight gradient of a 32->32 convolution: partial[cta][taps][cin][cout]; sum over cta with snb_reduce_partials. */
+SNB_API int snb_conv_c32_wgrad(const float* x, const float* dz, float* partial, const snb_conv_geom* g, void* stream);
+SNB_API int snb_conv_c32_wgrad_num_partials(const snb_conv_geom* g);
+/* Weight gradients of the small-Cin layers: partial[tile][k = (ci,kh,kw)][cout]. */
+SNB_API int snb_conv5x5s2_c3_wgrad(const float* img, const float* dy, float* partial, int B, int H, int W, void* stream);
+SNB_API int snb_conv5x5s2_c3_num_tiles(int B, int H, int W);
+SNB_API int snb_refine_in_wgrad(const float* coarse, const float* rgb, const float* dz, float* partial,
+                        int B, int h, int w_, int H, int W, float disp_scale, void* stream);
+/* Soft-argmin backward: dcost[b,d,y,x] = p_d * (d - pred) * dpred (+ dcost_extra), p = softmax_d(cost). */
+SNB_API int snb_softargmin_bwd(const float* cost, const float* pred, const float* dpred, const float* dcost_extra, float* dcost,
+                       int B, int D, int H, int W, void* stream);
+/* dres = dout * (out > 0)  (ReLU of stereo_net.py:121). */
+SNB_API int snb_relu_bwd(const float* out, const float* dout, float* dres, long long n, void* stream);
+/* Backward of a 32->1 3x3(x3) convolution given g = d(output) [B,D,H,W]: dx [B,D,H,W,32] and per-CTA partials
+ * [ceil(npos/128)][ntaps*32 + 1] holding dw[tap][c] and, last, db. */
+SNB_API int snb_conv_c32_taps_bwd(const float* x, const float* w, const float* g, float* dx, float* partial,
+                          int B, int D, int H, int W, int ntaps, void* stream);
 
 #ifdef __cplusplus
 }
