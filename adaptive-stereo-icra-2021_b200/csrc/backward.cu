@@ -85,14 +85,21 @@ bn_lrelu_bwd_apply_kernel(const float4* __restrict__ z, const float4* __restrict
   }
 }
 
-// out[j] = sum_i partial[i][j] (double accumulation, fixed order -> deterministic)
+// out[j] = mul * sum_i partial[i][j]: block = 32 columns x 8 row groups, double accumulation, fixed order -> deterministic
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int n, int len, float* __restrict__ out, float mul) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= len) return;
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int i = 0; i < n; ++i) s += (double)partial[(size_t)i * len + j];
-  out[j] = (float)(s * (double)mul);
+  if (j < len)
+    for (int i = ty; i < n; i += 8) s += (double)partial[(size_t)i * len + j];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < len) {
+    double a = ((red[0][tx] + red[1][tx]) + (red[2][tx] + red[3][tx])) + ((red[4][tx] + red[5][tx]) + (red[6][tx] + red[7][tx]));
+    out[j] = (float)(a * (double)mul);
+  }
 }
 
 // per-channel column sums of a [npos][32] tensor -> partial[blk][32]
@@ -122,13 +129,29 @@ channel_sum_kernel(const float4* __restrict__ x, float* __restrict__ partial, lo
 // (4 position groups x 32 threads, each 4 ci x 8 co) accumulate the 32x32 block, reduce the 4 groups through smem and add
 // into a smem accumulator [taps][32][32].  Partials [cta][taps][32][32] are summed by reduce_partials_kernel.
 struct SmemWgrad {
-  float x[128][32];      // swizzled rows
+  float x[2][128][32];   // swizzled rows, double buffered over taps
   float dz[128][32];     // swizzled rows
-  float red[4][32][33];  // cross-group reduction scratch (padded)
+  float red[8][32][33];  // cross-group reduction scratch (padded)
   int4 coord[128];
 };
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void wgrad_load_x(SmemWgrad& s, int buf, const float* __restrict__ x, const snb_conv_geom& g, int tap) {
+  const int t = threadIdx.x;
+  const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kd = tap / (g.KW * g.KH);
+  const int chunkc = t & 7;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = (t >> 3) + 32 * j;
+    const int4 c = s.coord[r];
+    const int id = c.y + kd - g.pd, ih = c.z * g.stride + kh * g.dil - g.ph, iw = c.w * g.stride + kw * g.dil - g.pw;
+    const bool ok = (c.x >= 0) && (unsigned)id < (unsigned)g.D && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
+    const size_t off = ok ? ((((size_t)c.x * g.D + id) * g.H + ih) * g.W + iw) * 32 + chunkc * 4 : 0;
+    cp_async16(&s.x[buf][r][(chunkc ^ (r & 7)) * 4], x + off, ok);
+  }
+}
+
+// 256 threads = 8 position groups (16 positions each) x 32 threads (4 ci x 8 co each).
+__global__ void __launch_bounds__(256)
 conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ partial,
                       snb_conv_geom g, long long npos, int chunks_per_cta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -136,7 +159,7 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
   float* sAcc = reinterpret_cast<float*>(smem_raw + sizeof(SmemWgrad));     // [taps][32 ci][32 co]
   const int t = threadIdx.x;
   const int ntaps = g.KD * g.KH * g.KW;
-  for (int i = t; i < ntaps * 1024; i += 128) sAcc[i] = 0.f;
+  for (int i = t; i < ntaps * 1024; i += 256) sAcc[i] = 0.f;
   const int grp = t >> 5, l = t & 31;
   const int cig = l >> 2, cog = l & 3;             // ci = cig*4 .. +3 ; co = cog*8 .. +7
   const long long chunk0 = (long long)blockIdx.x * chunks_per_cta;
@@ -146,8 +169,8 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
     const long long chunk = chunk0 + cc;
     if (chunk >= nchunks) break;
     const long long pos0 = chunk * 128;
-    __syncthreads();
-    {
+    __syncthreads();                       // previous chunk fully consumed (x, dz, coord, red)
+    if (t < 128) {
       long long p = pos0 + t;
       int4 c;
       if (p < npos) {
@@ -160,27 +183,22 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
     {   // dz tile (output positions are contiguous in memory)
       const int chunkc = t & 7;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = (t >> 3) + 16 * j;
+      for (int j = 0; j < 4; ++j) {
+        const int r = (t >> 3) + 32 * j;
         const bool ok = pos0 + r < npos;
         cp_async16(&s.dz[r][(chunkc ^ (r & 7)) * 4], dz + (ok ? (pos0 + r) * 32 + chunkc * 4 : 0), ok);
       }
     }
-    __syncthreads();          // coord visible
+    __syncthreads();                       // coord visible
+    wgrad_load_x(s, 0, x, g, 0);
+    cp_async_commit();
     for (int tap = 0; tap < ntaps; ++tap) {
-      const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kd = tap / (g.KW * g.KH);
-      {
-        const int chunkc = t & 7;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = (t >> 3) + 16 * j;
-          const int4 c = s.coord[r];
-          const int id = c.y + kd - g.pd, ih = c.z * g.stride + kh * g.dil - g.ph, iw = c.w * g.stride + kw * g.dil - g.pw;
-          const bool ok = (c.x >= 0) && (unsigned)id < (unsigned)g.D && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
-          const size_t off = ok ? ((((size_t)c.x * g.D + id) * g.H + ih) * g.W + iw) * 32 + chunkc * 4 : 0;
-          cp_async16(&s.x[r][(chunkc ^ (r & 7)) * 4], x + off, ok);
-        }
+      const int buf = tap & 1;
+      if (tap + 1 < ntaps) {
+        wgrad_load_x(s, buf ^ 1, x, g, tap + 1);      // buffer buf^1 was last read two barriers ago
         cp_async_commit();
+        cp_async_wait<1>();
+      } else {
         cp_async_wait<0>();
       }
       __syncthreads();
@@ -190,9 +208,9 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
-      for (int pp = 0; pp < 32; ++pp) {
-        const int r = grp * 32 + pp;
-        const float4 xv = *reinterpret_cast<const float4*>(&s.x[r][(cig ^ (r & 7)) * 4]);
+      for (int pp = 0; pp < 16; ++pp) {
+        const int r = grp * 16 + pp;
+        const float4 xv = *reinterpret_cast<const float4*>(&s.x[buf][r][(cig ^ (r & 7)) * 4]);
         const float4 d0 = *reinterpret_cast<const float4*>(&s.dz[r][((cog * 2) ^ (r & 7)) * 4]);
         const float4 d1 = *reinterpret_cast<const float4*>(&s.dz[r][((cog * 2 + 1) ^ (r & 7)) * 4]);
         const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -210,18 +228,17 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
         for (int j = 0; j < 8; ++j) s.red[grp][cig * 4 + i][cog * 8 + j] = acc[i][j];
       __syncthreads();
       float* accp = sAcc + (size_t)tap * 1024;
-      for (int i = t; i < 1024; i += 128) {
+      for (int i = t; i < 1024; i += 256) {
         const int ci = i >> 5, co = i & 31;
-        accp[i] += (s.red[0][ci][co] + s.red[1][ci][co]) + (s.red[2][ci][co] + s.red[3][ci][co]);
+        accp[i] += ((s.red[0][ci][co] + s.red[1][ci][co]) + (s.red[2][ci][co] + s.red[3][ci][co])) +
+                   ((s.red[4][ci][co] + s.red[5][ci][co]) + (s.red[6][ci][co] + s.red[7][ci][co]));
       }
-      // the next tap's cp.async into s.x may only start after every thread finished reading it: the barrier above
-      // (after the compute loop) already guarantees that; s.red is rewritten only after the next compute loop + barrier.
-      __syncthreads();
+      // s.red is rewritten after the next tap's barrier; s.x[buf] is refilled only at tap+2, after that barrier too
     }
   }
   __syncthreads();
   float* out = partial + (size_t)blockIdx.x * ntaps * 1024;
-  for (int i = t; i < ntaps * 1024; i += 128) out[i] = sAcc[i];
+  for (int i = t; i < ntaps * 1024; i += 256) out[i] = sAcc[i];
 }
 
 // ------------------------------------------------------------------------------------------------ soft-argmin backward
@@ -343,7 +360,7 @@ conv_c32_taps_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 static int grid_for(long long n4) {
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -374,7 +391,7 @@ extern "C" int snb_bn_lrelu_bwd_apply(const float* z, const float* dy, const flo
 
 extern "C" int snb_reduce_partials(const float* partial, int n, int len, float* out, float mul, void* stream) {
   SNB_REQUIRE(partial && out && n > 0 && len > 0, "snb_reduce_partials: bad args");
-  reduce_partials_kernel<<<snb_ceil_div(len, 256), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul);
+  reduce_partials_kernel<<<snb_ceil_div(len, 32), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul);
   SNB_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
@@ -415,7 +432,7 @@ extern "C" int snb_conv_c32_wgrad(const float* x, const float* dz, float* partia
   const int smem = (int)(sizeof(SmemWgrad) + (size_t)ntaps * 4096);
   SNB_REQUIRE(smem <= 227 * 1024, "snb_conv_c32_wgrad: too many taps for shared memory");
   SNB_CUDA(cudaFuncSetAttribute(conv_c32_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv_c32_wgrad_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(x, dz, partial, *g, npos, per);
+  conv_c32_wgrad_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(x, dz, partial, *g, npos, per);
   SNB_LAUNCH_CHECK("conv_c32_wgrad_kernel");
   return 0;
 }

@@ -97,11 +97,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+template <bool PROF>
 __device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t parity) {
+  if (!PROF) { mbar_wait(bar, parity); return 0; }
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   return clock64() - t0;
 }
+template <bool PROF> __device__ __forceinline__ long long prof_clock() { return PROF ? clock64() : 0; }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
@@ -118,6 +121,8 @@ struct Params {
 
 __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b < 0) ? q - 1 : q; }
 
+// PROF = true adds clock64() timers around every wait (snb_conv_c32_tc_profile); the product path is PROF = false.
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_c32_tc_kernel(const Params p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -199,13 +204,13 @@ conv_c32_tc_kernel(const Params p) {
 
     uint32_t stage = 0, phase = 0;
     int s_widx = 0;
-    long long t_wait = 0; const long long t_begin = clock64();
+    long long t_wait = 0; const long long t_begin = prof_clock<PROF>();
     for (int item0 = 0; item0 < n_items; item0 += PF) {
 #pragma unroll
       for (int k = 0; k < PF; ++k) {
         if (item0 + k >= n_items) break;
         unsigned char* st = base + stage * STAGE_BYTES;
-        t_wait += mbar_wait_timed(&empty[stage], phase ^ 1);
+        t_wait += mbar_wait_timed<PROF>(&empty[stage], phase ^ 1);
         if (tid == 0) {
           if (stream_b) {
             mbar_expect_tx(&full[stage], 2 * B_BYTES);
@@ -238,7 +243,7 @@ conv_c32_tc_kernel(const Params p) {
         if (l_item < n_items) issue_loads(v[k]);   // refill this register slot with window item+PF
       }
     }
-    if (p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_wait; p.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
+    if (PROF && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_wait; p.dbg[blockIdx.x * 16 + 1] = prof_clock<PROF>() - t_begin; }
   } else if (warp == NUM_LOADER_WARPS) {
     // =============================================================== MMA issuer (one thread)
     if (lane == 0) {
@@ -250,15 +255,15 @@ conv_c32_tc_kernel(const Params p) {
       }
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      long long t_full = 0, t_tempty = 0; const long long t_begin = clock64();
+      long long t_full = 0, t_tempty = 0; const long long t_begin = prof_clock<PROF>();
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int acc = it & (NACC - 1);
         const uint32_t accphase = (it / NACC) & 1;
-        t_tempty += mbar_wait_timed(&tempty[acc], accphase ^ 1);
+        t_tempty += mbar_wait_timed<PROF>(&tempty[acc], accphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 128;
         for (int widx = 0; widx < p.nwin; ++widx) {
-          t_full += mbar_wait_timed(&full[stage], phase);
+          t_full += mbar_wait_timed<PROF>(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = base_u32 + stage * STAGE_BYTES;
           const uint32_t sb = sa + 2 * A_BYTES;
@@ -276,7 +281,7 @@ conv_c32_tc_kernel(const Params p) {
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 16 + 2] = t_full; p.dbg[blockIdx.x * 16 + 3] = t_tempty; p.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
+      if (PROF && p.dbg) { p.dbg[blockIdx.x * 16 + 2] = t_full; p.dbg[blockIdx.x * 16 + 3] = t_tempty; p.dbg[blockIdx.x * 16 + 4] = prof_clock<PROF>() - t_begin; }
     }
     __syncwarp();
   } else {
@@ -298,13 +303,13 @@ conv_c32_tc_kernel(const Params p) {
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
     int it = 0;
-    long long t_tfull = 0, t_bar = 0, t_pre = 0, t_tmem = 0, t_out = 0; const long long t_begin = clock64();
+    long long t_tfull = 0, t_bar = 0, t_pre = 0, t_tmem = 0, t_out = 0; const long long t_begin = prof_clock<PROF>();
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int acc = it & (NACC - 1);
       const uint32_t accphase = (it / NACC) & 1;
       const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
       const int q0 = tt * p.step - p.dil;
-      const long long tA = clock64();
+      const long long tA = prof_clock<PROF>();
       // coordinates of this thread's 4 output rows (one division per tile, then increments)
       int hh[4], ww[4]; bool okr[4];
       {
@@ -329,10 +334,10 @@ conv_c32_tc_kernel(const Params p) {
                                e.residual + (((size_t)slice * p.H + hh[j]) * p.W + ww[j]) * 32 + chunk * 4));
         }
       }
-      t_pre += clock64() - tA;
-      t_tfull += mbar_wait_timed(&tfull[acc], accphase);
+      t_pre += prof_clock<PROF>() - tA;
+      t_tfull += mbar_wait_timed<PROF>(&tfull[acc], accphase);
       tc_fence_after();
-      const long long tB = clock64();
+      const long long tB = prof_clock<PROF>();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 128 + half * 16;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
@@ -346,9 +351,9 @@ conv_c32_tc_kernel(const Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);      // this warp is done with the TMEM slot
-      t_tmem += clock64() - tB;
-      { const long long tb = clock64(); epi_bar(); t_bar += clock64() - tb; }
-      const long long tC = clock64();
+      t_tmem += prof_clock<PROF>() - tB;
+      { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }
+      const long long tC = prof_clock<PROF>();
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -388,10 +393,10 @@ conv_c32_tc_kernel(const Params p) {
           e.stats[(size_t)tile * 64 + et] = a;
         }
       }
-      t_out += clock64() - tC;
-      { const long long tb = clock64(); epi_bar(); t_bar += clock64() - tb; }     // sY / sRed are rewritten by the next tile
+      t_out += prof_clock<PROF>() - tC;
+      { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }     // sY / sRed are rewritten by the next tile
     }
-    if (p.dbg && et == 0) { p.dbg[blockIdx.x * 16 + 5] = t_tfull; p.dbg[blockIdx.x * 16 + 6] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 7] = t_bar; p.dbg[blockIdx.x * 16 + 8] = t_pre; p.dbg[blockIdx.x * 16 + 9] = t_tmem; p.dbg[blockIdx.x * 16 + 10] = t_out; }
+    if (PROF && p.dbg && et == 0) { p.dbg[blockIdx.x * 16 + 5] = t_tfull; p.dbg[blockIdx.x * 16 + 6] = prof_clock<PROF>() - t_begin; p.dbg[blockIdx.x * 16 + 7] = t_bar; p.dbg[blockIdx.x * 16 + 8] = t_pre; p.dbg[blockIdx.x * 16 + 9] = t_tmem; p.dbg[blockIdx.x * 16 + 10] = t_out; }
   }
 
   tc_fence_before();
@@ -483,8 +488,13 @@ static int conv_c32_tc_launch(const float* x, const float* wimg, float* y, const
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.ntiles < sms ? p.ntiles : sms;
-  SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-  tc::conv_c32_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  if (dbg) {
+    SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    tc::conv_c32_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  } else {
+    SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    tc::conv_c32_tc_kernel<false><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  }
   SNB_LAUNCH_CHECK("conv_c32_tc_kernel");
   return 0;
 }

@@ -130,6 +130,23 @@ def cpu_reference(steps, warmup, budget_s):
               sample=f"{done} full forward passes of the oracle port (torch CPU fp32, {cores} threads) on one synthetic KITTI pair")
 
 
+def cpu_reference_adapt(steps):
+  """One adaptation step of the oracle port on the host cores (adapt.py:313-337,381-394 restated in oracle/)."""
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import stereonet_oracle as O
+  cores = torch.get_num_threads()
+  fsd = O.clone_state(O.make_feature_state(K_DOWN, 11), True)
+  ssd = O.clone_state(O.make_stereo_state(22, sharpen=10.0), True)
+  left, right = synthetic_pair(1000)
+  adam = {}
+  O.adapt_step(fsd, ssd, left, right, K_DOWN, adam)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    O.adapt_step(fsd, ssd, left, right, K_DOWN, adam)
+  dt = (time.perf_counter() - t0) / steps
+  return {"value": 1.0 / dt, "unit": "steps/s", "cores": cores, "kind": "port", "sample": f"{steps} adaptation steps of the oracle port"}
+
+
 # ------------------------------------------------------------------------------------------------- GPU arm
 def time_kernel(fn, iters, flush, stream):
   """Average duration (ms) of fn() alone, L2 flushed before every launch, CUDA events on the launching stream."""
@@ -210,10 +227,36 @@ def gpu_arm(args):
   ms_e2e = ev2.elapsed_time(ev3)
   clocks = sampler.stop() if rank == 0 else None
 
-  t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+  # ---- online-adaptation step (BASELINE.json configs[2]/[4]): train-mode fwd + photometric loss + bwd + clip + Adam.
+  # N > 1: shared-model data parallel, one stream per rank, ONE flat-bucket NCCL all-reduce of the used gradients.
+  ms_adapt, adapt_steps, adapt_launches = float("nan"), 0, 0
+  if not args.skip_adapt:
+    from stereonet_b200.adapt import AdaptStepper, make_optimizer
+    from stereonet_b200 import parallel
+    fnet.train(); snet.train()
+    stepper = AdaptStepper(fnet, snet, make_optimizer(fnet, snet, lr=5e-5), H, W, clip_grad_norm=True)
+    dl, dr = left.to(dev), right.to(dev)
+    used = parallel.used_parameters(snet, fnet)
+    sync = (lambda: parallel.allreduce_gradients(used)) if world > 1 else None
+    adapt_steps = max(3, args.steps // 5)
+    for _ in range(3):
+      stepper.step(dl, dr, sync_grads=sync)
+    barrier()
+    n0 = ops.LAUNCHES
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev4.record(stream)
+    for _ in range(adapt_steps):
+      stepper.step(dl, dr, sync_grads=sync)
+    ev5.record(stream)
+    barrier()
+    ms_adapt = ev4.elapsed_time(ev5)
+    adapt_launches = (ops.LAUNCHES - n0) // adapt_steps
+    fnet.eval(); snet.eval()
+
+  t = torch.tensor([ms_dev, ms_e2e, ms_adapt], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)              # max over ranks
-  ms_dev, ms_e2e = t.tolist()
+  ms_dev, ms_e2e, ms_adapt = t.tolist()
 
   result = None
   if rank == 0:
@@ -273,8 +316,16 @@ def gpu_arm(args):
       "launches_per_step": launches,
       "roofline": roofline, "kernels": kernels, "clocks": clocks,
     }
+    if adapt_steps:
+      result["adapt"] = {"metric": "online adaptation steps/s @KITTI 376x1248 (train-mode fwd + Monodepth loss + bwd + clip + Adam lr 5e-5)",
+                         "value": world * adapt_steps / (ms_adapt / 1e3), "unit": "steps/s", "ms_per_step": ms_adapt / adapt_steps,
+                         "steps": adapt_steps, "library_launches_per_step": adapt_launches,
+                         "parallelism": "single stream" if world == 1 else f"shared-model DP x{world}, one NCCL all-reduce of 288066 grads per step",
+                         "note": "loss / Adam / clip are the caller's plain PyTorch ops as in adapt.py; model fwd+bwd are libsnb200 kernels"}
     if cpu is not None:
       result["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+      if adapt_steps and not args.skip_cpu_adapt:
+        result["adapt"]["cpu_baseline"] = cpu_reference_adapt(steps=2)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
@@ -290,6 +341,8 @@ def main():
   ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--skip-cpu", action="store_true")
   ap.add_argument("--cpu-steps", type=int, default=12)
+  ap.add_argument("--skip-adapt", action="store_true")
+  ap.add_argument("--skip-cpu-adapt", action="store_true")
   args = ap.parse_args()
 
   rank = int(os.environ.get("RANK", "0"))
