@@ -14,99 +14,14 @@
 //   x*w ~= xh*wh + xl*wh + xh*wl   (xh = top 19 bits, xl = x - xh)  -> ~2^-21 relative, i.e. fp32-grade results;
 // passes = 1 is plain single-pass TF32 (reported separately, north star).
 //
-// Warp roles (544 threads, 1 CTA/SM, persistent over tiles):
-//   warps 0-7  loaders : LDG.128 channels-last rows -> hi/lo split -> STS into the SWIZZLE_128B K-major A image,
+// Warp roles (512 threads = 4 warps per SM sub-partition -> 128 registers/thread; 1 CTA/SM, persistent over tiles):
+//   warps 0-6  loaders : LDG.128 channels-last rows -> hi/lo split -> STS into the SWIZZLE_128B K-major A image,
 //                        zero rows for padding; warp 0 also issues the TMA bulk copy of the window's B image (3-D)
-//   warp  8    MMA     : one elected thread issues tcgen05.mma (M128 N96 K8) and tcgen05.commit on the mbarriers
-//   warps 9-16 epilogue: tcgen05.ld TMEM -> smem (Y0|Y1|Y2) -> shift-add + bias/BN/LeakyReLU/residual/stats -> coalesced STG
-#include "common.cuh"
+//   warp  7    MMA     : one elected thread issues tcgen05.mma (M128 N96 K8) and tcgen05.commit on the mbarriers
+//   warps 8-15 epilogue: tcgen05.ld TMEM -> smem (Y0|Y1|Y2) -> shift-add + bias/BN/LeakyReLU/residual/stats -> coalesced STG
+#include "tc_common.cuh"
 
 namespace tc {
-
-constexpr int NSTAGE = 3;
-constexpr int A_BYTES = 128 * 128;                       // one 128x32 fp32 operand image (hi or lo)
-constexpr int B_BYTES = 96 * 128;                        // one 96x32 fp32 operand image (hi or lo)
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 56 KB (multiple of 1024)
-constexpr int OUT_BYTES = 3 * 128 * 128;                  // Y0 | Y1 | Y2 staging tiles (128 x 32 fp32 each)
-constexpr int NACC = 4;                                  // TMEM accumulator slots of 128 columns (96 used)
-constexpr int NUM_LOADER_WARPS = 8;
-constexpr int NUM_EPI_WARPS = 8;                         // two per TMEM lane quadrant (16 of the 32 columns each)
-constexpr int NTHREADS = (NUM_LOADER_WARPS + 1 + NUM_EPI_WARPS) * 32;
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + OUT_BYTES + 3072 /*barriers, misc*/ + 1024 /*alignment slack*/;
-constexpr int WIMG_FLOATS_PER_WINDOW = 2 * B_BYTES / 4;  // hi + lo
-
-// instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9 = 10-12 = 2), K-major A and B,
-// N>>3 at bits 17-22, M>>4 at bits 24-28   (cute::UMMA::InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  // K-major, SWIZZLE_128B: start>>4 | LBO(16 B, unused)<<16 | SBO(1024 B = 8 rows x 128 B)<<32 | version 1<<46 | layout 2<<61
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Bounded mbarrier wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 1.9 GHz
-  }
-}
-
-template <bool PROF>
-__device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t parity) {
-  if (!PROF) { mbar_wait(bar, parity); return 0; }
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  return clock64() - t0;
-}
-template <bool PROF> __device__ __forceinline__ long long prof_clock() { return PROF ? clock64() : 0; }
-
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 struct Params {
   const float* x; const float* wimg; float* y;
@@ -119,7 +34,6 @@ struct Params {
   long long* dbg;          // optional [grid][8] cycle counters (diagnostics), or NULL
 };
 
-__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b < 0) ? q - 1 : q; }
 
 // PROF = true adds clock64() timers around every wait (snb_conv_c32_tc_profile); the product path is PROF = false.
 template <bool PROF>
@@ -162,42 +76,42 @@ conv_c32_tc_kernel(const Params p) {
     // Software-pipelined: the global loads of window i+PF are in flight (registers) while window i is split and
     // stored to smem, so a loader thread never sits out a full L2/HBM round trip per window.
     constexpr int PF = 3;
-    const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes cover one 128-B row; rows rgrp + 32*j
+    const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes cover one 128-B row; rows rgrp + LSTRIDE*j (< 128)
     const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * p.nwin;                 // item = (tile, window)
     // ---- load cursor state
     int l_item = 0, l_widx = 0, l_b = 0, l_d = 0;
     int l_tile = blockIdx.x;
-    int h0[4], w0[4];
+    int h0[LROWS], w0[LROWS];
     auto decode_tile = [&]() {
       const int slice = l_tile / p.tiles_per_slice, tt = l_tile - slice * p.tiles_per_slice;
       l_b = slice / p.D; l_d = slice - l_b * p.D;
       const int q = tt * p.step - p.dil + rgrp;
       int h = floordiv(q, p.P), w = q - h * p.P;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {      // rows rgrp + 32*j: one division per tile, then increments
+      for (int j = 0; j < LROWS; ++j) {  // rows rgrp + LSTRIDE*j: one division per tile, then increments
         h0[j] = h; w0[j] = w;
-        w += 32;
+        w += LSTRIDE;
         while (w >= p.P) { w -= p.P; ++h; }
       }
     };
-    auto issue_loads = [&](float4 (&v)[4]) {
+    auto issue_loads = [&](float4 (&v)[LROWS]) {
       if (l_widx == 0) decode_tile();
       const int kd = (p.nwin == 9) ? l_widx / 3 : 0, kh = l_widx - kd * 3;
       const int di = (p.nwin == 9) ? l_d + kd - 1 : l_d;
       const bool slice_ok = (unsigned)di < (unsigned)p.D;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < LROWS; ++j) {
         const int h = h0[j] + (kh - 1) * p.dil;
-        const bool ok = slice_ok && w0[j] < p.W && (unsigned)h < (unsigned)p.H;
+        const bool ok = slice_ok && rgrp + LSTRIDE * j < 128 && w0[j] < p.W && (unsigned)h < (unsigned)p.H;
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) v[j] = __ldg(reinterpret_cast<const float4*>(
+        if (ok) v[j] = __ldcg(reinterpret_cast<const float4*>(
                        p.x + ((((size_t)l_b * p.D + di) * p.H + h) * p.W + w0[j]) * 32 + chunk * 4));
       }
       ++l_item;
       if (++l_widx == p.nwin) { l_widx = 0; l_tile += gridDim.x; }
     };
-    float4 v[PF][4];
+    float4 v[PF][LROWS];
 #pragma unroll
     for (int k = 0; k < PF; ++k)
       if (l_item < n_items) issue_loads(v[k]);
@@ -220,19 +134,14 @@ conv_c32_tc_kernel(const Params p) {
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = rgrp + 32 * j;
-          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
-          const float4 x4 = v[k][j];
-          float4 hi;
-          hi.x = __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u);
-          hi.y = __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u);
-          hi.z = __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u);
-          hi.w = __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u);
-          *reinterpret_cast<float4*>(st + off) = hi;
-          if (p.passes == 3) {
-            const float4 lo = make_float4(x4.x - hi.x, x4.y - hi.y, x4.z - hi.z, x4.w - hi.w);
-            *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+        for (int j = 0; j < LROWS; ++j) {
+          const int r = rgrp + LSTRIDE * j;
+          if (r < 128) {
+            const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+            float4 hi, lo;
+            split_tf32(v[k][j], hi, lo);
+            *reinterpret_cast<float4*>(st + off) = hi;
+            if (p.passes == 3) *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
           }
         }
         fence_async_smem();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -251,7 +160,7 @@ conv_c32_tc_kernel(const Params p) {
         mbar_expect_tx(wbar, (uint32_t)p.nwin * 2 * B_BYTES);
         for (int w = 0; w < p.nwin; ++w)
           bulk_g2s(base + w * STAGE_BYTES + 2 * A_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, wbar);
-        mbar_wait(wbar, 0);
+        mbar_wait_spin(wbar, 0);
       }
       uint32_t stage = 0, phase = 0;
       int it = 0;
@@ -330,7 +239,7 @@ conv_c32_tc_kernel(const Params p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (okr[j]) res[j] = __ldg(reinterpret_cast<const float4*>(
+          if (okr[j]) res[j] = __ldcg(reinterpret_cast<const float4*>(
                                e.residual + (((size_t)slice * p.H + hh[j]) * p.W + ww[j]) * 32 + chunk * 4));
         }
       }
@@ -339,14 +248,17 @@ conv_c32_tc_kernel(const Params p) {
       tc_fence_after();
       const long long tB = prof_clock<PROF>();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 128 + half * 16;
+      {
+        float v0[16], v1[16], v2[16];
+        tmem_ld16x3(taddr, taddr + 32, taddr + 64, v0, v1, v2);
+        float* row = sY + m * 32;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        float v[16];
-        tmem_ld16(taddr + kw * 32, v);
-        float* row = sY + kw * (128 * 32) + m * 32;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(row + (((half * 4 + c) ^ (m & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        for (int c = 0; c < 4; ++c) {
+          const int o = ((half * 4 + c) ^ (m & 7)) << 2;
+          *reinterpret_cast<float4*>(row + o) = make_float4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+          *reinterpret_cast<float4*>(row + 128 * 32 + o) = make_float4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+          *reinterpret_cast<float4*>(row + 2 * 128 * 32 + o) = make_float4(v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -356,24 +268,23 @@ conv_c32_tc_kernel(const Params p) {
       const long long tC = prof_clock<PROF>();
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!okr[j]) continue;
+      for (int j = 0; j < 4; ++j) {       // branch-free: out-of-range rows read clamped smem rows and skip only the store
         const int r = rg + 32 * j;
-        const int r0 = r - p.dil, r2 = r + p.dil;    // kw=0 reads input w-dil: Y0[r-dil]; kw=2: Y2[r+dil]
+        const int r0 = max(r - p.dil, 0), r2 = min(r + p.dil, 127);    // kw=0 reads input w-dil: Y0[r-dil]; kw=2: Y2[r+dil]
         const float4 a = *reinterpret_cast<const float4*>(sY + r0 * 32 + ((chunk ^ (r0 & 7)) << 2));
         const float4 b = *reinterpret_cast<const float4*>(sY + 128 * 32 + r * 32 + ((chunk ^ (r & 7)) << 2));
         const float4 c = *reinterpret_cast<const float4*>(sY + 2 * 128 * 32 + r2 * 32 + ((chunk ^ (r2 & 7)) << 2));
         float4 o;
         o.x = (a.x + b.x) + c.x + bias4.x; o.y = (a.y + b.y) + c.y + bias4.y;
         o.z = (a.z + b.z) + c.z + bias4.z; o.w = (a.w + b.w) + c.w + bias4.w;
-        if (has_stats) {
+        if (has_stats && okr[j]) {
           s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
           s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
         }
         if (e.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
         if (e.lrelu) { o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w); }
         if (has_res) { o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w; }
-        *reinterpret_cast<float4*>(p.y + (((size_t)slice * p.H + hh[j]) * p.W + ww[j]) * 32 + chunk * 4) = o;
+        if (okr[j]) __stcg(reinterpret_cast<float4*>(p.y + (((size_t)slice * p.H + hh[j]) * p.W + ww[j]) * 32 + chunk * 4), o);
       }
       if (has_stats) {
 #pragma unroll

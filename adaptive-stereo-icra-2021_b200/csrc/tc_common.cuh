@@ -1,0 +1,130 @@
+// Shared tcgen05 / TMEM / mbarrier helpers of the tensor-core convolution kernels (sm_100a).
+#pragma once
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int NSTAGE = 3;
+constexpr int A_BYTES = 128 * 128;                       // one 128x32 fp32 operand image (hi or lo)
+constexpr int B_BYTES = 96 * 128;                        // one 96x32 fp32 operand image (hi or lo)
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 56 KB (multiple of 1024)
+constexpr int OUT_BYTES = 3 * 128 * 128;                  // Y0 | Y1 | Y2 staging tiles (128 x 32 fp32 each)
+constexpr int NACC = 4;                                  // TMEM accumulator slots of 128 columns (96 used)
+constexpr int NUM_LOADER_WARPS = 7;                      // 7 + 1 MMA + 8 epilogue = 16 warps = 4 per SMSP -> 128 regs/thread, no spills
+constexpr int LROWS = (128 + NUM_LOADER_WARPS * 4 - 1) / (NUM_LOADER_WARPS * 4);   // tile rows per loader thread (5)
+constexpr int LSTRIDE = NUM_LOADER_WARPS * 4;             // row stride between a loader thread's rows (28)
+constexpr int NUM_EPI_WARPS = 8;                         // two per TMEM lane quadrant (16 of the 32 columns each)
+constexpr int NTHREADS = (NUM_LOADER_WARPS + 1 + NUM_EPI_WARPS) * 32;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + OUT_BYTES + 3072 /*barriers, misc*/ + 1024 /*alignment slack*/;
+constexpr int WIMG_FLOATS_PER_WINDOW = 2 * B_BYTES / 4;  // hi + lo
+
+// instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9 = 10-12 = 2), K-major A and B,
+// N>>3 at bits 17-22, M>>4 at bits 24-28   (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(16 B, unused)<<16 | SBO(1024 B = 8 rows x 128 B)<<32 | version 1<<46 | layout 2<<61
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Bounded mbarrier wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);                                 // back off: spinning warps must not steal issue slots from working ones
+    if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 1.9 GHz
+  }
+}
+// latency-critical variant for the single MMA-issuing thread (no sleep)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// three 16-column TMEM loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x3(uint32_t t0, uint32_t t1, uint32_t t2, float (&a)[16], float (&b)[16], float (&c)[16]) {
+  uint32_t r[48];
+#define SNB_LD16(ARR, OFF, ADDR) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n" \
+      : "=r"(ARR[OFF+0]), "=r"(ARR[OFF+1]), "=r"(ARR[OFF+2]), "=r"(ARR[OFF+3]), "=r"(ARR[OFF+4]), "=r"(ARR[OFF+5]), "=r"(ARR[OFF+6]), "=r"(ARR[OFF+7]), \
+        "=r"(ARR[OFF+8]), "=r"(ARR[OFF+9]), "=r"(ARR[OFF+10]), "=r"(ARR[OFF+11]), "=r"(ARR[OFF+12]), "=r"(ARR[OFF+13]), "=r"(ARR[OFF+14]), "=r"(ARR[OFF+15]) \
+      : "r"(ADDR) : "memory")
+  SNB_LD16(r, 0, t0); SNB_LD16(r, 16, t1); SNB_LD16(r, 32, t2);
+#undef SNB_LD16
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); c[i] = __uint_as_float(r[32 + i]); }
+}
+
+template <bool PROF>
+__device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t parity) {
+  if (!PROF) { mbar_wait(bar, parity); return 0; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  return clock64() - t0;
+}
+template <bool PROF> __device__ __forceinline__ long long prof_clock() { return PROF ? clock64() : 0; }
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b < 0) ? q - 1 : q; }
+
+// hi = top 19 bits (exactly representable in TF32), lo = x - hi (exact in fp32)
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+}  // namespace tc

@@ -128,21 +128,26 @@ def prep_conv_weights_tc(w, mode=0):
   return out
 
 
-def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3):
-  """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32."""
+def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
+                flat=False):
+  """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.
+  2-D inputs use the vertical-walk kernel (snb_conv2d_c32_tc) unless flat=True; 3-D inputs the flat-tiled one."""
   three_d = x.dim() == 5
   _req(x, "x"); _req(wimg, "wimg")
+  lib = _cabi.lib()
+  use2d = (not three_d) and (not flat)
+  fn, fn_tiles = (lib.snb_conv2d_c32_tc, lib.snb_conv2d_c32_tc_num_tiles) if use2d else (lib.snb_conv_c32_tc, lib.snb_conv_c32_tc_num_tiles)
   y = torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
   stats = None
   if want_stats:
-    nt = _cabi.lib().snb_conv_c32_tc_num_tiles(C.byref(g))
+    nt = fn_tiles(C.byref(g))
     stats = torch.empty((nt, 2, 32), device=x.device, dtype=torch.float32)
   if residual is not None:
     _req(residual, "residual")
     if residual.shape != y.shape:
       raise RuntimeError("stereonet_b200: residual shape mismatch")
   e = ConvEpilogue(_p(bias), _p(scale), _p(shift), _p(residual), _p(stats), 1 if lrelu else 0)
-  check(_cabi.lib().snb_conv_c32_tc(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv_c32_tc")
+  check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
   _count()
   return y, stats
 

@@ -88,6 +88,12 @@ SNB_API int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g);
  * MMA wait-tmem, MMA total, epilogue wait-tmem-full, epilogue total, epilogue barrier} (clock64 ticks). */
 SNB_API int snb_conv_c32_tc_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
                             const snb_conv_epilogue* e, int passes, long long* counters, void* stream);
+/* 2-D specialisation with the "vertical walk" schedule (consecutive tiles of a CTA step down a column block by `dil` rows
+ * and share two of their three input-row windows: 3x less loader / L2 traffic).  Same weights image (kd = 1), same
+ * epilogue contract; `stats` has snb_conv2d_c32_tc_num_tiles() rows (one per image row x column block). */
+SNB_API int snb_conv2d_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                      int passes, void* stream);
+SNB_API int snb_conv2d_c32_tc_num_tiles(const snb_conv_geom* g);
 /* Repack [32][32][kd*3*3] weights into the tensor-core B-operand smem image (hi/lo TF32 split, SWIZZLE_128B K-major,
  * one 24 KB block per (kd,kh) window).  kd = 1 (2-D) or 3 (3-D).  mode 0: forward, 1: data gradient. */
 SNB_API int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream);

@@ -11,15 +11,32 @@ pytestmark = pytest.mark.gpu
 TOL = {3: 1e-5, 1: 3e-3}
 
 
+@pytest.mark.parametrize("flat", [False, True])
 @pytest.mark.parametrize("passes", [3, 1])
 @pytest.mark.parametrize("B,H,W,dil", [(1, 19, 45, 1), (2, 23, 37, 2), (1, 40, 50, 4), (1, 33, 41, 8), (1, 8, 128, 1),
-                                       (1, 47, 156, 1), (1, 130, 260, 2)])
-def test_conv_tc_2d(B, H, W, dil, passes):
+                                       (1, 47, 156, 1), (1, 130, 260, 2), (2, 5, 300, 8), (1, 1, 7, 1)])
+def test_conv_tc_2d(B, H, W, dil, passes, flat):
+  """flat=False: vertical-walk 2-D kernel (snb_conv2d_c32_tc); flat=True: the flat-tiled kernel (snb_conv_c32_tc)."""
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
   ref = F.conv2d(x, w, b, padding=dil, dilation=dil)
   g = ops.geom((B, H, W, 32), 3, dil=dil)
-  y, _ = ops.conv_c32_tc(cl(x), ops.prep_conv_weights_tc(w.to(DEV)), g, bias=b.to(DEV), passes=passes)
-  close(uncl(y), ref, TOL[passes], f"tc conv2d dil={dil} passes={passes}")
+  y, _ = ops.conv_c32_tc(cl(x), ops.prep_conv_weights_tc(w.to(DEV)), g, bias=b.to(DEV), passes=passes, flat=flat)
+  close(uncl(y), ref, TOL[passes], f"tc conv2d dil={dil} passes={passes} flat={flat}")
+
+
+@pytest.mark.parametrize("B,H,W,dil", [(2, 23, 37, 2), (1, 47, 156, 1), (1, 64, 300, 4)])
+def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil):
+  x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
+  scale, shift = rnd(32, seed=4).abs() + 0.5, rnd(32, seed=5)
+  z = F.conv2d(x, w, b, padding=dil, dilation=dil)
+  ref = F.leaky_relu(z * scale.view(1, 32, 1, 1) + shift.view(1, 32, 1, 1), 0.2) + x
+  xc = cl(x)
+  y, stats = ops.conv_c32_tc(xc, ops.prep_conv_weights_tc(w.to(DEV)), ops.geom((B, H, W, 32), 3, dil=dil), bias=b.to(DEV),
+                             scale=scale.to(DEV), shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True)
+  close(uncl(y), ref, 1e-5, "conv2d tc epilogue")
+  s = stats.double().sum(0).cpu()
+  close(s[0], z.double().sum((0, 2, 3)), 1e-4, "sum z")
+  close(s[1], (z.double() ** 2).sum((0, 2, 3)), 1e-4, "sum z^2")
 
 
 @pytest.mark.parametrize("passes", [3, 1])
