@@ -65,55 +65,48 @@ conv_c32_taps_kernel(const float* __restrict__ x, const float* __restrict__ w, f
   }
 }
 
-// grid (B*H, ceil(W/32)); block (32, NW). Warp wy handles disparities wy, wy+NW, ... ; lanes = 32 consecutive x.
-__global__ void __launch_bounds__(256)
+// grid (B*H, ceil(W/32)); block (32, D): thread (lane, d) gathers the 27 tap planes of ONE cost value (all 27 loads are
+// independent and coalesced over the 32 x-positions of the warp), the D warps drop their costs into smem and warp 0
+// finishes softmax_d + expectation for the 32 columns.  D <= 32 (maxdisp 192 -> D' <= 24).
+__global__ void __launch_bounds__(1024)
 tapsum_softargmin_kernel(const float* __restrict__ taps, const float* __restrict__ bias, float* __restrict__ cost_out,
                          float* __restrict__ pred, int D, int H, int W) {
-  __shared__ float sM[8][32], sS[8][32], sWS[8][32];
-  const int lane = threadIdx.x, wy = threadIdx.y, NW = blockDim.y;
+  __shared__ float sC[32][33];
+  const int lane = threadIdx.x, d = threadIdx.y;
   const int b = blockIdx.x / H, y = blockIdx.x - b * H;
   const int x = blockIdx.y * 32 + lane;
   const size_t plane = (size_t)H * W;
-  const float bv = bias[0];
-  float m = -INFINITY, s = 0.f, ws = 0.f;
+  float c = bias[0];
   if (x < W) {
-    for (int d = wy; d < D; d += NW) {
-      float c = bv;
 #pragma unroll
-      for (int kd = 0; kd < 3; ++kd) {
-        const int dd = d + kd - 1;
-        if ((unsigned)dd >= (unsigned)D) continue;
-        const float* tp = taps + (((size_t)b * D + dd) * 27 + kd * 9) * plane;
+    for (int kd = 0; kd < 3; ++kd) {
+      const int dd = d + kd - 1;
+      if ((unsigned)dd >= (unsigned)D) continue;
+      const float* tp = taps + (((size_t)b * D + dd) * 27 + kd * 9) * plane;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int yy = y + kh - 1;
-          if ((unsigned)yy >= (unsigned)H) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int yy = y + kh - 1;
+        if ((unsigned)yy >= (unsigned)H) continue;
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int xx = x + kw - 1;
-            if ((unsigned)xx < (unsigned)W) c += tp[(size_t)(kh * 3 + kw) * plane + (size_t)yy * W + xx];
-          }
+        for (int kw = 0; kw < 3; ++kw) {
+          const int xx = x + kw - 1;
+          if ((unsigned)xx < (unsigned)W) c += __ldg(tp + (size_t)(kh * 3 + kw) * plane + (size_t)yy * W + xx);
         }
       }
-      if (cost_out) cost_out[(((size_t)b * D + d) * H + y) * W + x] = c;
-      const float mn = fmaxf(m, c);
-      const float r = __expf(m - mn), ec = __expf(c - mn);     // exp(-inf) = 0 on the first step
-      s = s * r + ec;
-      ws = ws * r + ec * (float)d;
-      m = mn;
     }
+    if (cost_out) cost_out[(((size_t)b * D + d) * H + y) * W + x] = c;
   }
-  sM[wy][lane] = m; sS[wy][lane] = s; sWS[wy][lane] = ws;
+  sC[d][lane] = c;
   __syncthreads();
-  if (wy == 0 && x < W) {
-    float M = sM[0][lane];
-    for (int i = 1; i < NW; ++i) M = fmaxf(M, sM[i][lane]);
-    float S = 0.f, WS = 0.f;
-    for (int i = 0; i < NW; ++i) {
-      const float r = (sM[i][lane] == -INFINITY) ? 0.f : __expf(sM[i][lane] - M);
-      S += sS[i][lane] * r; WS += sWS[i][lane] * r;
+  if (d == 0 && x < W) {
+    float m = -INFINITY;
+    for (int i = 0; i < D; ++i) m = fmaxf(m, sC[i][lane]);
+    float s = 0.f, ws = 0.f;
+    for (int i = 0; i < D; ++i) {
+      const float e = __expf(sC[i][lane] - m);
+      s += e; ws = fmaf(e, (float)i, ws);
     }
-    pred[((size_t)b * H + y) * W + x] = WS / S;
+    pred[((size_t)b * H + y) * W + x] = ws / s;
   }
 }
 
@@ -202,8 +195,8 @@ extern "C" int snb_conv_c32_taps(const float* x, const float* w, float* taps, lo
 extern "C" int snb_tapsum_softargmin(const float* taps, const float* bias, float* cost_out, float* pred,
                                      int B, int D, int H, int W, void* stream) {
   SNB_REQUIRE(taps && bias && pred && B > 0 && D > 0 && H > 0 && W > 0, "snb_tapsum_softargmin: bad args");
-  const int nw = D < 8 ? D : 8;
-  tapsum_softargmin_kernel<<<dim3(B * H, snb_ceil_div(W, 32)), dim3(32, nw), 0, (cudaStream_t)stream>>>(
+  SNB_REQUIRE(D <= 32, "snb_tapsum_softargmin: at most 32 coarse disparity levels (got %d)", D);
+  tapsum_softargmin_kernel<<<dim3(B * H, snb_ceil_div(W, 32)), dim3(32, D), 0, (cudaStream_t)stream>>>(
       taps, bias, cost_out, pred, D, H, W);
   SNB_LAUNCH_CHECK("tapsum_softargmin_kernel");
   return 0;
