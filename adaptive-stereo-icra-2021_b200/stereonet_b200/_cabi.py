@@ -51,6 +51,9 @@ SIGNATURES = {
   "snb_channel_sum": (_I, [_P, _P, _LL, _P]),
   "snb_conv_c32_wgrad": (_I, [_P, _P, _P, _GP, _P]),
   "snb_conv_c32_wgrad_num_partials": (_I, [_GP]),
+  "snb_conv_c32_wgrad_tc": (_I, [_P, _P, _P, _GP, _I, _P]),
+  "snb_conv_c32_wgrad_tc_num_partials": (_I, [_GP]),
+  "snb_conv_c32_wgrad_tc_debug": (_I, [_P, _P, _P, _GP, _I, _P, _P]),
   "snb_conv5x5s2_c3_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
   "snb_conv5x5s2_c3_num_tiles": (_I, [_I, _I, _I]),
   "snb_refine_in_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),

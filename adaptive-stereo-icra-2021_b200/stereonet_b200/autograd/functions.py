@@ -36,7 +36,7 @@ class ConvBnLrelu(torch.autograd.Function):
     dx = None
     if ctx.needs_input_grad[0]:
       dx, _ = fused.conv3x3_c32_dgrad(dz, ctx.conv, g, residual=dy if ctx.residual else None)
-    dw = ops.conv_c32_wgrad(x, dz, g, ctx.wshape)
+    dw = fused.conv3x3_c32_wgrad(x, dz, g, ctx.wshape)
     return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None
 
 
@@ -70,7 +70,10 @@ class ConvC32(torch.autograd.Function):
       else:
         gt = ops.geom_transposed(g)
         dx, _ = ops.conv_c32(dy, fused.wprep(ctx.conv, 2), gt)
-    dw = ops.conv_c32_wgrad(x, dy, g, ctx.wshape)
+    if ctx.ksize == 3 and ctx.stride == 1:
+      dw = fused.conv3x3_c32_wgrad(x, dy, g, ctx.wshape)
+    else:
+      dw = ops.conv_c32_wgrad(x, dy, g, ctx.wshape)
     return dx, dw, ops.channel_sum(dy), None, None, None
 
 

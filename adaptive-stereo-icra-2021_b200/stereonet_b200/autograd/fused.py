@@ -77,6 +77,13 @@ def conv3x3_c32_dgrad(dy, conv, g, residual=None):
   return ops.conv_c32_tc(dy, wprep_tc(conv, 1), g, residual=residual, passes=3 if CONV_BACKEND == "tc3" else 1)
 
 
+def conv3x3_c32_wgrad(x, dz, g, wshape):
+  """Weight gradient of a stride-1 'same' 3x3(x3) conv: tensor-core kernel unless the FFMA backend is selected."""
+  if CONV_BACKEND == "ffma":
+    return ops.conv_c32_wgrad(x, dz, g, wshape)
+  return ops.conv_c32_wgrad_tc(x, dz, g, wshape, passes=3 if CONV_BACKEND == "tc3" else 1)
+
+
 def _needs_grad(*tensors_or_modules):
   if not torch.is_grad_enabled():
     return False

@@ -308,6 +308,20 @@ def conv_c32_wgrad(x, dz, g, wshape):
   return dw.permute(2, 1, 0).reshape(wshape).contiguous()       # layout change only
 
 
+def conv_c32_wgrad_tc(x, dz, g, wshape, passes=3):
+  """Tensor-core weight gradient of a stride-1 'same' 3x3 / 3x3x3 32->32 conv (snb_conv_c32_wgrad_tc)."""
+  _req(x, "x"); _req(dz, "dz")
+  n = _cabi.lib().snb_conv_c32_wgrad_tc_num_partials(C.byref(g))
+  if n <= 0:
+    raise RuntimeError("snb_conv_c32_wgrad_tc_num_partials failed: " + _cabi.lib().snb_last_error().decode())
+  taps = g.KD * g.KH * g.KW
+  part = torch.empty((n, taps * 1024), device=x.device, dtype=torch.float32)
+  check(_cabi.lib().snb_conv_c32_wgrad_tc(_p(x), _p(dz), _p(part), C.byref(g), passes, _stream(x)), "snb_conv_c32_wgrad_tc")
+  _count()
+  dw = reduce_partials(part).view(taps, 32, 32)                  # [tap][cin][cout]
+  return dw.permute(2, 1, 0).reshape(wshape).contiguous()
+
+
 def conv5x5s2_c3_wgrad(img, dy):
   B, _, H, W = img.shape
   n = _cabi.lib().snb_conv5x5s2_c3_num_tiles(B, H, W)

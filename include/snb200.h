@@ -163,6 +163,16 @@ SNB_API int snb_channel_sum(const float* x, float* partial, long long npos, void
 /* Weight gradient of a 32->32 convolution: partial[cta][taps][cin][cout]; sum over cta with snb_reduce_partials. */
 SNB_API int snb_conv_c32_wgrad(const float* x, const float* dz, float* partial, const snb_conv_geom* g, void* stream);
 SNB_API int snb_conv_c32_wgrad_num_partials(const snb_conv_geom* g);
+/* Same result for the stride-1 'same' 3x3 (dilated) / 3x3x3 layers on the tcgen05 tensor cores: the reduction over
+ * positions is the GEMM K dimension, both operands are MN-major SWIZZLE_128B images of the channels-last rows (no
+ * transpose), kw shifts are descriptor offsets into one dz row window, each x row window is fetched once ("walk"
+ * schedules).  passes = 3: 3xTF32 split (fp32-grade); 1: plain TF32.  partial[cta][taps][cin][cout] with
+ * snb_conv_c32_wgrad_tc_num_partials() CTAs. */
+SNB_API int snb_conv_c32_wgrad_tc(const float* x, const float* dz, float* partial, const snb_conv_geom* g, int passes, void* stream);
+SNB_API int snb_conv_c32_wgrad_tc_num_partials(const snb_conv_geom* g);
+/* Diagnostics: same launch plus dbg[cta][64] = {accumulator mask, slots, tiles, any, ..., raw TMEM samples}. */
+SNB_API int snb_conv_c32_wgrad_tc_debug(const float* x, const float* dz, float* partial, const snb_conv_geom* g, int passes,
+                                float* dbg, void* stream);
 /* Weight gradients of the small-Cin layers: partial[tile][k = (ci,kh,kw)][cout]. */
 SNB_API int snb_conv5x5s2_c3_wgrad(const float* img, const float* dy, float* partial, int B, int H, int W, void* stream);
 SNB_API int snb_conv5x5s2_c3_num_tiles(int B, int H, int W);
