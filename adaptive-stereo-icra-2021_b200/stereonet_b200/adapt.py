@@ -7,17 +7,29 @@ import torch.nn as nn
 from .losses import LinearWarping, feature_contrast_mean, khamis_robust_loss, monodepth_single_loss
 
 
-def make_optimizer(feature_net, stereo_net, lr=5e-5):
-  """adapt.py:208-210: two parameter groups, stereo_net first."""
-  return torch.optim.Adam([{"params": stereo_net.parameters()}, {"params": feature_net.parameters()}], lr=lr)
+def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
+  """adapt.py:208-210: two parameter groups, stereo_net first.  capturable=True keeps Adam's step counters on the device
+  (needed by AdaptStepper(use_graph=True))."""
+  return torch.optim.Adam([{"params": stereo_net.parameters()}, {"params": feature_net.parameters()}], lr=lr,
+                          capturable=capturable)
 
 
 class AdaptStepper:
-  def __init__(self, feature_net, stereo_net, optimizer, height, width, clip_grad_norm=True, er_loss_weight=0.05):
+  """use_graph=True captures the WHOLE update (forward, loss, backward, [gradient all-reduce,] clip, Adam) in one CUDA
+  graph per input shape and replays it per frame: at batch 1 the step is ~700 launches of 3-100 us kernels, so eager
+  execution is bound by host launch latency.  Requires an optimizer built with capturable=True and no replay term."""
+
+  def __init__(self, feature_net, stereo_net, optimizer, height, width, clip_grad_norm=True, er_loss_weight=0.05,
+               use_graph=False):
     self.feature_net, self.stereo_net, self.optimizer = feature_net, stereo_net, optimizer
     self.clip, self.er_loss_weight = clip_grad_norm, er_loss_weight
     dev = next(stereo_net.parameters()).device
     self.warper = LinearWarping(height, width, dev)
+    self.use_graph = use_graph
+    self._graphs = {}
+    self.launches_per_step = None
+    if use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
+      raise RuntimeError("AdaptStepper(use_graph=True) needs make_optimizer(..., capturable=True)")
 
   def predict(self, left, right):
     fl, fr = self.feature_net(left), self.feature_net(right)                       # adapt.py:72
@@ -26,10 +38,15 @@ class AdaptStepper:
   def step(self, left, right, replay=None, sync_grads=None):
     """One gradient update (adapt.py:313-314,328-337,381-394).  `replay` = (left, right, gt_disp) adds the
     experience-replay term (adapt.py:339-349).  `sync_grads` is called between backward and clip (DP all-reduce)."""
+    if self.use_graph and replay is None:
+      return self._step_graph(left, right, sync_grads)
+    return self._step_eager(left, right, replay, sync_grads, static_shapes=False)
+
+  def _step_eager(self, left, right, replay, sync_grads, static_shapes):
     s = self.stereo_net.input_scale
     self.feature_net.train(); self.stereo_net.train()
     outputs = self.predict(left, right)
-    loss = monodepth_single_loss(left, right, outputs, self.warper, s)
+    loss = monodepth_single_loss(left, right, outputs, self.warper, s, static_shapes=static_shapes)
     if replay is not None:
       out_er = self.predict(replay[0], replay[1])
       loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
@@ -42,3 +59,57 @@ class AdaptStepper:
       nn.utils.clip_grad_norm_(self.stereo_net.parameters(), 1.0)                 # adapt.py:391-392
     self.optimizer.step()
     return loss.detach(), fcs, outputs
+
+  # ---------------------------------------------------------------------------------------------- CUDA-graph path
+  def _state_tensors(self):
+    ts = [p for net in (self.stereo_net, self.feature_net) for p in net.parameters()]
+    ts += [b for net in (self.stereo_net, self.feature_net) for b in net.buffers()]
+    for st in self.optimizer.state.values():
+      ts += [v for v in st.values() if isinstance(v, torch.Tensor)]
+    return ts
+
+  def _capture(self, left, right, sync_grads):
+    from .autograd import fused
+    self.feature_net.train(); self.stereo_net.train()
+    dev = left.device
+    sl, sr = left.clone(), right.clone()
+    fresh = len(self.optimizer.state) == 0
+    snap = [(t, t.detach().clone()) for t in self._state_tensors()]
+    cur = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+      # One eager warm-up step allocates the lazily-created state (Adam moments and step counters, derived-weight
+      # caches, allocator pools); model and optimizer state are restored afterwards so that capturing does not advance
+      # the adaptation.
+      self._step_eager(sl, sr, None, sync_grads, static_shapes=True)
+      self.optimizer.zero_grad(set_to_none=True)
+      with torch.no_grad():
+        for t, saved in snap:                 # in place: the graph will hold these addresses
+          t.copy_(saved)
+        if fresh:
+          for st in self.optimizer.state.values():
+            for v in st.values():
+              if isinstance(v, torch.Tensor):
+                v.zero_()
+    cur.wait_stream(side)
+    fused.bump_epoch()
+    from . import ops
+    graph = torch.cuda.CUDAGraph()
+    n0 = ops.LAUNCHES
+    with torch.cuda.graph(graph):
+      out = self._step_eager(sl, sr, None, sync_grads, static_shapes=True)
+    self.launches_per_step = ops.LAUNCHES - n0          # library kernels inside one replay
+    return dict(graph=graph, left=sl, right=sr, out=out)
+
+  def _step_graph(self, left, right, sync_grads):
+    from .autograd import fused
+    key = (tuple(left.shape), str(left.device))
+    e = self._graphs.get(key)
+    if e is None:
+      e = self._graphs[key] = self._capture(left, right, sync_grads)
+    e["left"].copy_(left, non_blocking=True)
+    e["right"].copy_(right, non_blocking=True)
+    e["graph"].replay()
+    fused.bump_epoch()                      # the replay rewrote the parameters behind torch's version counters
+    return e["out"]

@@ -7,9 +7,19 @@ from .. import ops
 # Derived read-only tensors (repacked weights, folded BN) live ON the owning nn.Module (attribute `_snb_cache`), keyed
 # on the in-place version counters of the source parameters, so an optimizer step (adapt.py:393) or load_state_dict
 # invalidates them and they die with the module (no process-global state).
+# EPOCH covers updates torch's version counters cannot see: a replayed CUDA graph of the adaptation step rewrites the
+# parameters in place on the device without touching the Python-side counters (adapt.AdaptStepper bumps it per replay).
+EPOCH = 0
+
+
+def bump_epoch():
+  global EPOCH
+  EPOCH += 1
+
+
 def _cached(owner, key, tensors, make):
   cache = owner.__dict__.setdefault("_snb_cache", {})
-  ver = tuple((t.data_ptr(), t._version) for t in tensors)
+  ver = (EPOCH,) + tuple((t.data_ptr(), t._version) for t in tensors)
   hit = cache.get(key)
   if hit is not None and hit[0] == ver:
     return hit[1]

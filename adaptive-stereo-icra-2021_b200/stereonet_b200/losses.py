@@ -61,10 +61,16 @@ def monodepth_loss(pred_disp, true_img, warped_img, smoothness_weight=0.001):
   return l_photo + smoothness_weight * l_smooth, photo_l1, photo_ssim, l_smooth
 
 
-def monodepth_single_loss(left_img, right_img, outputs, warper, scale):
+def monodepth_single_loss(left_img, right_img, outputs, warper, scale, static_shapes=False):
+  """adapt.py:78-86.  static_shapes=True computes the same masked mean as sum(loss*mask)/sum(mask) instead of boolean
+  indexing, so the step has no data-dependent shapes / host syncs and can be captured in a CUDA graph."""
   key = "pred_disp_l/{}".format(scale)
   left_warped, mask = warper(right_img, outputs[key], right_to_left=True)
-  return monodepth_loss(outputs[key], left_img, left_warped, smoothness_weight=1e-3)[0][mask].mean()
+  loss = monodepth_loss(outputs[key], left_img, left_warped, smoothness_weight=1e-3)[0]
+  if static_shapes:
+    m = mask.to(loss.dtype)
+    return (loss * m).sum() / m.sum()
+  return loss[mask].mean()
 
 
 def khamis_robust_loss(pred_disp, gt_disp):

@@ -234,7 +234,8 @@ def gpu_arm(args):
     from stereonet_b200.adapt import AdaptStepper, make_optimizer
     from stereonet_b200 import parallel
     fnet.train(); snet.train()
-    stepper = AdaptStepper(fnet, snet, make_optimizer(fnet, snet, lr=5e-5), H, W, clip_grad_norm=True)
+    stepper = AdaptStepper(fnet, snet, make_optimizer(fnet, snet, lr=5e-5, capturable=not args.no_graph), H, W,
+                           clip_grad_norm=True, use_graph=not args.no_graph)
     dl, dr = left.to(dev), right.to(dev)
     used = parallel.used_parameters(snet, fnet)
     sync = (lambda: parallel.allreduce_gradients(used)) if world > 1 else None
@@ -250,7 +251,7 @@ def gpu_arm(args):
     ev5.record(stream)
     barrier()
     ms_adapt = ev4.elapsed_time(ev5)
-    adapt_launches = (ops.LAUNCHES - n0) // adapt_steps
+    adapt_launches = stepper.launches_per_step if stepper.launches_per_step else (ops.LAUNCHES - n0) // adapt_steps
     fnet.eval(); snet.eval()
 
   t = torch.tensor([ms_dev, ms_e2e, ms_adapt], device=dev, dtype=torch.float64)
@@ -320,6 +321,7 @@ def gpu_arm(args):
       result["adapt"] = {"metric": "online adaptation steps/s @KITTI 376x1248 (train-mode fwd + Monodepth loss + bwd + clip + Adam lr 5e-5)",
                          "value": world * adapt_steps / (ms_adapt / 1e3), "unit": "steps/s", "ms_per_step": ms_adapt / adapt_steps,
                          "steps": adapt_steps, "library_launches_per_step": adapt_launches,
+                         "cuda_graph": not args.no_graph,
                          "parallelism": "single stream" if world == 1 else f"shared-model DP x{world}, one NCCL all-reduce of 288066 grads per step",
                          "note": "loss / Adam / clip are the caller's plain PyTorch ops as in adapt.py; model fwd+bwd are libsnb200 kernels"}
     if cpu is not None:

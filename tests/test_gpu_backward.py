@@ -282,3 +282,38 @@ def test_refine_tail_backward():
   close(uncl(xg.grad), x.grad, 1e-4, "dx")
   close(gconv.weight.grad.cpu(), conv.weight.grad, 1e-4, "dw")
   close(gconv.bias.grad.cpu(), conv.bias.grad, 1e-4, "db")
+
+
+def test_adapt_step_cuda_graph_matches_eager():
+  """AdaptStepper(use_graph=True) replays the whole update (fwd, loss, bwd, clip, Adam) as one CUDA graph: three steps
+  on changing frames must leave the same weights / BN statistics / Adam state as three eager steps, and capturing must
+  not advance the adaptation."""
+  from stereonet_b200.adapt import AdaptStepper, make_optimizer
+  k, Hh, Ww = 3, 96, 256
+  fsd, ssd = O.make_feature_state(k, 11), O.make_stereo_state(22, sharpen=10.0)
+  frames = [O.make_stereo_pair(1, Hh, Ww, seed=1000 + i, max_disp_px=40.0)[:2] for i in range(3)]
+  results = []
+  for use_graph in (False, True):
+    f = S.FeatureExtractorNetwork(k).to(DEV); s = S.StereoNet(k, 1, 0).to(DEV)
+    f.load_state_dict(fsd); s.load_state_dict(ssd)
+    opt = make_optimizer(f, s, lr=5e-5, capturable=True)
+    st = AdaptStepper(f, s, opt, Hh, Ww, clip_grad_norm=True, use_graph=use_graph)
+    losses = []
+    for l, r in frames:
+      loss, fcs, out = st.step(l.to(DEV), r.to(DEV))
+      losses.append(loss.item())
+    torch.cuda.synchronize()
+    # an eval-mode forward after the replays must see the updated weights (derived-weight caches invalidated)
+    f.eval(); s.eval()
+    with torch.no_grad():
+      l, r = frames[0][0].to(DEV), frames[0][1].to(DEV)
+      disp = s(l, f(l), f(r), "l")["pred_disp_l/0"].cpu()
+    results.append((losses, {n: v.detach().cpu().clone() for n, v in list(s.state_dict().items()) + list(f.state_dict().items())}, disp))
+  (le, we, de), (lg, wg, dg) = results
+  assert max(abs(a - b) for a, b in zip(le, lg)) < 1e-5, (le, lg)
+  for n in we:
+    if "num_batches_tracked" in n:
+      assert torch.equal(we[n], wg[n]), n
+    else:
+      assert (we[n] - wg[n]).abs().max().item() <= 2e-6 + 1e-5 * we[n].abs().max().item(), n
+  assert (de - dg).abs().max().item() < 1e-2
