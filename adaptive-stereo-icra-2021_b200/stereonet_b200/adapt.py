@@ -35,14 +35,24 @@ class AdaptStepper:
     fl, fr = self.feature_net(left), self.feature_net(right)                       # adapt.py:72
     return self.stereo_net(left, fl, fr, "l", output_cost_volume=True)             # adapt.py:73
 
-  def step(self, left, right, replay=None, sync_grads=None):
+  def step(self, left, right, replay=None, sync_grads=None, dp_params=None, dp_group=None):
     """One gradient update (adapt.py:313-314,328-337,381-394).  `replay` = (left, right, gt_disp) adds the
-    experience-replay term (adapt.py:339-349).  `sync_grads` is called between backward and clip (DP all-reduce)."""
-    if self.use_graph and replay is None:
-      return self._step_graph(left, right, sync_grads)
-    return self._step_eager(left, right, replay, sync_grads, static_shapes=False)
+    experience-replay term (adapt.py:339-349).  Shared-model data parallelism: either `sync_grads` (a callable run
+    between backward and clip, eager path only) or `dp_params` (+ `dp_group`): the gradients of those parameters are
+    packed into one flat bucket, SUM-all-reduced over NCCL and averaged.  With use_graph=True the step then becomes
+    graph(fwd + loss + bwd + pack) -> eager all-reduce -> graph(unpack + clip + Adam): the collective is not captured."""
+    if self.use_graph and replay is None and sync_grads is None:
+      return self._step_graph(left, right, dp_params, dp_group)
+    if dp_params is not None and sync_grads is None:
+      from . import parallel
+      sync_grads = lambda: parallel.allreduce_gradients(dp_params, dp_group)
+    out = self._fwd_bwd(left, right, replay, static_shapes=False)
+    if sync_grads is not None:
+      sync_grads()
+    self._update()
+    return out
 
-  def _step_eager(self, left, right, replay, sync_grads, static_shapes):
+  def _fwd_bwd(self, left, right, replay, static_shapes):
     s = self.stereo_net.input_scale
     self.feature_net.train(); self.stereo_net.train()
     outputs = self.predict(left, right)
@@ -53,12 +63,12 @@ class AdaptStepper:
     fcs = feature_contrast_mean(outputs["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
     self.optimizer.zero_grad()
     loss.backward()
-    if sync_grads is not None:
-      sync_grads()
+    return loss.detach(), fcs, outputs
+
+  def _update(self):
     if self.clip:
       nn.utils.clip_grad_norm_(self.stereo_net.parameters(), 1.0)                 # adapt.py:391-392
     self.optimizer.step()
-    return loss.detach(), fcs, outputs
 
   # ---------------------------------------------------------------------------------------------- CUDA-graph path
   def _state_tensors(self):
@@ -68,11 +78,14 @@ class AdaptStepper:
       ts += [v for v in st.values() if isinstance(v, torch.Tensor)]
     return ts
 
-  def _capture(self, left, right, sync_grads):
+  def _capture(self, left, right, dp_params, dp_group):
+    import torch.distributed as dist
+    from . import ops, parallel
     from .autograd import fused
     self.feature_net.train(); self.stereo_net.train()
     dev = left.device
     sl, sr = left.clone(), right.clone()
+    world = dist.get_world_size(dp_group) if dp_params is not None else 1
     fresh = len(self.optimizer.state) == 0
     snap = [(t, t.detach().clone()) for t in self._state_tensors()]
     cur = torch.cuda.current_stream(dev)
@@ -82,10 +95,13 @@ class AdaptStepper:
       # One eager warm-up step allocates the lazily-created state (Adam moments and step counters, derived-weight
       # caches, allocator pools); model and optimizer state are restored afterwards so that capturing does not advance
       # the adaptation.
-      self._step_eager(sl, sr, None, sync_grads, static_shapes=True)
+      self._fwd_bwd(sl, sr, None, static_shapes=True)
+      if dp_params is not None:
+        parallel.allreduce_gradients(dp_params, dp_group)
+      self._update()
       self.optimizer.zero_grad(set_to_none=True)
       with torch.no_grad():
-        for t, saved in snap:                 # in place: the graph will hold these addresses
+        for t, saved in snap:                 # in place: the graphs will hold these addresses
           t.copy_(saved)
         if fresh:
           for st in self.optimizer.state.values():
@@ -94,22 +110,37 @@ class AdaptStepper:
                 v.zero_()
     cur.wait_stream(side)
     fused.bump_epoch()
-    from . import ops
-    graph = torch.cuda.CUDAGraph()
     n0 = ops.LAUNCHES
-    with torch.cuda.graph(graph):
-      out = self._step_eager(sl, sr, None, sync_grads, static_shapes=True)
+    g1 = torch.cuda.CUDAGraph()
+    flat = None
+    with torch.cuda.graph(g1):
+      out = self._fwd_bwd(sl, sr, None, static_shapes=True)
+      if dp_params is not None:
+        flat = parallel.pack_gradients(dp_params)
+      else:
+        self._update()
+    g2 = None
+    if dp_params is not None:
+      g2 = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g2, pool=g1.pool()):
+        with torch.no_grad():
+          parallel.unpack_gradients(dp_params, flat, world)
+        self._update()
     self.launches_per_step = ops.LAUNCHES - n0          # library kernels inside one replay
-    return dict(graph=graph, left=sl, right=sr, out=out)
+    return dict(g1=g1, g2=g2, flat=flat, left=sl, right=sr, out=out)
 
-  def _step_graph(self, left, right, sync_grads):
+  def _step_graph(self, left, right, dp_params, dp_group):
+    import torch.distributed as dist
     from .autograd import fused
-    key = (tuple(left.shape), str(left.device))
+    key = (tuple(left.shape), str(left.device), None if dp_params is None else len(dp_params))
     e = self._graphs.get(key)
     if e is None:
-      e = self._graphs[key] = self._capture(left, right, sync_grads)
+      e = self._graphs[key] = self._capture(left, right, dp_params, dp_group)
     e["left"].copy_(left, non_blocking=True)
     e["right"].copy_(right, non_blocking=True)
-    e["graph"].replay()
+    e["g1"].replay()
+    if e["g2"] is not None:
+      dist.all_reduce(e["flat"], op=dist.ReduceOp.SUM, group=dp_group)      # eager, between the two graphs
+      e["g2"].replay()
     fused.bump_epoch()                      # the replay rewrote the parameters behind torch's version counters
     return e["out"]

@@ -25,13 +25,18 @@ def used_parameters(stereo_net, feature_net):
   return out
 
 
-def allreduce_gradients(params, group=None):
-  """One flat-bucket SUM all-reduce then divide by world size (classic DP; 288 066 floats = 1.15 MB for k=3).
-  A rank whose frame went to the validation set contributes zeros so the collective stays matched (adapt.py:385)."""
-  world = dist.get_world_size(group)
+def pack_gradients(params, out=None):
+  """Flat fp32 bucket of the gradients of `params` (zeros where a parameter has no gradient).  `out` reuses a buffer."""
   flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
-  dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-  flat.div_(world)
+  if out is not None:
+    out.copy_(flat)
+    return out
+  return flat
+
+
+def unpack_gradients(params, flat, world):
+  """p.grad <- flat / world, parameter by parameter (creates the gradient where a rank had none)."""
+  flat = flat / world
   off = 0
   for p in params:
     n = p.numel()
@@ -41,4 +46,13 @@ def allreduce_gradients(params, group=None):
     else:
       p.grad.copy_(g)
     off += n
+
+
+def allreduce_gradients(params, group=None):
+  """One flat-bucket SUM all-reduce then divide by world size (classic DP; 288 066 floats = 1.15 MB for k=3).
+  A rank whose frame went to the validation set contributes zeros so the collective stays matched (adapt.py:385)."""
+  world = dist.get_world_size(group)
+  flat = pack_gradients(params)
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+  unpack_gradients(params, flat, world)
   return flat.numel()

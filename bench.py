@@ -238,16 +238,16 @@ def gpu_arm(args):
                            clip_grad_norm=True, use_graph=not args.no_graph)
     dl, dr = left.to(dev), right.to(dev)
     used = parallel.used_parameters(snet, fnet)
-    sync = (lambda: parallel.allreduce_gradients(used)) if world > 1 else None
+    dp = used if world > 1 else None
     adapt_steps = max(3, args.steps // 5)
     for _ in range(3):
-      stepper.step(dl, dr, sync_grads=sync)
+      stepper.step(dl, dr, dp_params=dp)
     barrier()
     n0 = ops.LAUNCHES
     ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev4.record(stream)
     for _ in range(adapt_steps):
-      stepper.step(dl, dr, sync_grads=sync)
+      stepper.step(dl, dr, dp_params=dp)
     ev5.record(stream)
     barrier()
     ms_adapt = ev4.elapsed_time(ev5)
@@ -335,6 +335,9 @@ def gpu_arm(args):
 
 
 def main():
+  if os.environ.get("SNB_BENCH_DUMP_AFTER"):        # debugging aid: dump all Python stacks and exit if the run stalls
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ["SNB_BENCH_DUMP_AFTER"]), exit=True)
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=50)
