@@ -31,6 +31,7 @@ struct Params2 {
   int nstrips;              // B * ncb * dil * nseg strip slots (some are empty)
   int passes;
   snb_conv_epilogue e;
+  long long* dbg;           // optional [grid][16] cycle counters (diagnostics, PROF kernels only), or NULL
 };
 
 struct Strip { int b, cb, row0, ntiles; };   // first output row, tiles (rows row0, row0+dil, ...)
@@ -47,8 +48,16 @@ __device__ __forceinline__ Strip decode_strip(const Params2& p, int sid) {
   return s;
 }
 
+// TA = true: the A window is copied ONCE from its smem image into TMEM (tcgen05.cp, 8 x 128x256b) and the 36 MMAs of the
+// window read A from TMEM — the per-MMA shared-memory operand fetch drops from 7 KB (A 4 KB + B 3 KB) to 3 KB; with A in
+// smem the kernel is bound by exactly that fetch (~110 cycles per M128 N96 K8 MMA instead of ~48).
+// TMEM columns: TA: 4 accumulators x 96 | 2 A slots x 64 (hi 32 | lo 32);  !TA: 4 accumulators x 128.
+template <bool TA, bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv2d_c32_tc_kernel(const Params2 p) {
+  constexpr int ACC_STRIDE = TA ? 96 : 128;
+  constexpr int TA_BASE = NACC * 96;
+  constexpr int TA_LOADERS = 3;              // TA: warps 0-2 load, warps 3-6 convert (one per TMEM lane quadrant)
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -60,14 +69,17 @@ conv2d_c32_tc_kernel(const Params2 p) {
   uint64_t* tfull = bars + 2 * NA;       // [NACC] MMA commit -> epilogue
   uint64_t* tempty = tfull + NACC;       // [NACC] epilogue -> MMA
   uint64_t* wbar = tempty + NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  uint64_t* rfull = wbar + 1;            // [NA]   TA: loaders -> converters (raw fp32 window in smem)
+  uint64_t* rempty = rfull + NA;         // [NA]   TA: converters -> loaders
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + NA);
   float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == NUM_LOADER_WARPS) {
     if (lane == 0) {
-      for (int i = 0; i < NA; ++i) { mbar_init(&full[i], NUM_LOADER_WARPS); mbar_init(&empty[i], 1); }
+      for (int i = 0; i < NA; ++i) { mbar_init(&full[i], TA ? 4 : NUM_LOADER_WARPS); mbar_init(&empty[i], 1); }
+      for (int i = 0; i < NA; ++i) { mbar_init(&rfull[i], TA_LOADERS); mbar_init(&rempty[i], 4); }
       for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
       mbar_init(wbar, 1);
       mbar_fence_init();
@@ -81,7 +93,116 @@ conv2d_c32_tc_kernel(const Params2 p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < NUM_LOADER_WARPS) {
+  if (TA && warp < TA_LOADERS) {
+    // =============================================================== TA loaders (warps 0-2): coalesced LDG.128 -> raw fp32 window in
+    // the smem ring (row = pixel, 16-B chunks XOR-swizzled by row & 7).  No hi/lo split here.
+    constexpr int PF = 2;
+    constexpr int LT_ROWS = TA_LOADERS * 4;                // rows covered by one pass of the loader threads (12)
+    constexpr int LT_N = (128 + LT_ROWS - 1) / LT_ROWS;    // rows per thread (11)
+    const int chunk = tid & 7, rgrp = tid >> 3;
+    int l_sid = blockIdx.x, l_u = 0;
+    Strip ls = decode_strip(p, l_sid < p.nstrips ? l_sid : 0);
+    auto l_skip_empty = [&]() {
+      while (l_sid < p.nstrips && ls.ntiles == 0) { l_sid += gridDim.x; if (l_sid < p.nstrips) ls = decode_strip(p, l_sid); }
+    };
+    l_skip_empty();
+    auto issue_loads = [&](float4 (&v)[LT_N]) {
+      const int r = ls.row0 + (l_u - 1) * p.dil;
+      const int x0 = ls.cb * p.step - p.dil;
+      const bool row_ok = (unsigned)r < (unsigned)p.H;
+      const float* rowp = p.x + ((size_t)ls.b * p.H + (row_ok ? r : 0)) * p.W * 32 + chunk * 4;
+#pragma unroll
+      for (int j = 0; j < LT_N; ++j) {
+        const int xx = x0 + rgrp + LT_ROWS * j;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && rgrp + LT_ROWS * j < 128 && (unsigned)xx < (unsigned)p.W) v[j] = __ldcg(reinterpret_cast<const float4*>(rowp + (size_t)xx * 32));
+      }
+      if (++l_u == ls.ntiles + 2) {
+        l_u = 0; l_sid += gridDim.x;
+        if (l_sid < p.nstrips) { ls = decode_strip(p, l_sid); l_skip_empty(); }
+      }
+    };
+    float4 v[PF][LT_N];
+#pragma unroll
+    for (int k = 0; k < PF; ++k)
+      if (l_sid < p.nstrips) issue_loads(v[k]);
+    long long n_items = 0;
+    for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+      const Strip s = decode_strip(p, sid);
+      if (s.ntiles > 0) n_items += s.ntiles + 2;
+    }
+    uint32_t buf = 0, phase = 0;
+    long long t_lwait = 0; const long long t_lbegin = prof_clock<PROF>();
+    for (long long item0 = 0; item0 < n_items; item0 += PF) {
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        if (item0 + k >= n_items) break;
+        unsigned char* st = base + buf * A_BYTES;
+        t_lwait += mbar_wait_timed<PROF>(&rempty[buf], phase ^ 1);
+#pragma unroll
+        for (int j = 0; j < LT_N; ++j) {
+          const int r = rgrp + LT_ROWS * j;
+          if (r < 128) *reinterpret_cast<float4*>(st + r * 128 + ((chunk ^ (r & 7)) << 4)) = v[k][j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rfull[buf]);
+        if (++buf == NA) { buf = 0; phase ^= 1; }
+        if (l_sid < p.nstrips) issue_loads(v[k]);
+      }
+    }
+    if (PROF && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_lwait; p.dbg[blockIdx.x * 16 + 1] = prof_clock<PROF>() - t_lbegin; }
+  } else if (TA && warp < NUM_LOADER_WARPS) {
+    // =============================================================== TA converters (warps 3-6, TMEM lane quadrant = warp % 4):
+    // thread = pixel row: 8 conflict-free LDS.128 -> hi/lo split in registers -> tcgen05.st into the A slot in TMEM.  The
+    // MMAs then read A from TMEM: no per-MMA shared-memory fetch of the A operand.
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;                        // window row = TMEM lane
+    long long n_items = 0;
+    for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+      const Strip s = decode_strip(p, sid);
+      if (s.ntiles > 0) n_items += s.ntiles + 2;
+    }
+    uint32_t buf = 0, phase = 0;
+    for (long long it = 0; it < n_items; ++it) {
+      const uint32_t slot = (uint32_t)it & 1;
+      tc::mbar_wait(&rfull[buf], phase);
+      const unsigned char* st = base + buf * A_BYTES + m * 128;
+      float4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(st + ((c ^ (m & 7)) << 4));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rempty[buf]);            // raw window consumed (values are in registers)
+      if (++buf == NA) { buf = 0; phase ^= 1; }
+      tc::mbar_wait(&empty[slot], (((uint32_t)it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + slot * 64;
+      {
+        uint32_t h[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          h[4 * c] = __float_as_uint(v[c].x) & 0xffffe000u; h[4 * c + 1] = __float_as_uint(v[c].y) & 0xffffe000u;
+          h[4 * c + 2] = __float_as_uint(v[c].z) & 0xffffe000u; h[4 * c + 3] = __float_as_uint(v[c].w) & 0xffffe000u;
+        }
+        tmem_st32(ta, h);
+      }
+      if (p.passes == 3) {
+        uint32_t l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x4 = v[c];
+          l[4 * c] = __float_as_uint(x4.x - __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u));
+          l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u));
+          l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u));
+          l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u));
+        }
+        tmem_st32(ta + 32, l);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[slot]);
+    }
+  } else if (warp < NUM_LOADER_WARPS) {
     // =============================================================== loaders (window items, register prefetch PF deep)
     constexpr int PF = 3;
     const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes = one 128-B pixel; rows rgrp + LSTRIDE*j (< 128)
@@ -120,12 +241,13 @@ conv2d_c32_tc_kernel(const Params2 p) {
       if (s.ntiles > 0) n_items += s.ntiles + 2;
     }
     uint32_t buf = 0, phase = 0;
+    long long t_lwait = 0; const long long t_lbegin = prof_clock<PROF>();
     for (long long item0 = 0; item0 < n_items; item0 += PF) {
 #pragma unroll
       for (int k = 0; k < PF; ++k) {
         if (item0 + k >= n_items) break;
         unsigned char* st = base + buf * AWIN_BYTES;
-        tc::mbar_wait(&empty[buf], phase ^ 1);
+        t_lwait += mbar_wait_timed<PROF>(&empty[buf], phase ^ 1);
 #pragma unroll
         for (int j = 0; j < LROWS; ++j) {
           const int r = rgrp + LSTRIDE * j;
@@ -144,23 +266,33 @@ conv2d_c32_tc_kernel(const Params2 p) {
         if (l_sid < p.nstrips) issue_loads(v[k]);
       }
     }
+    if (PROF && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_lwait; p.dbg[blockIdx.x * 16 + 1] = prof_clock<PROF>() - t_lbegin; }
   } else if (warp == NUM_LOADER_WARPS) {
-    // =============================================================== MMA issuer (one thread), window-major
-    if (lane == 0) {
-      mbar_expect_tx(wbar, 3 * BWIN_BYTES);
-      for (int w = 0; w < 3; ++w)
-        bulk_g2s(sB + w * BWIN_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, BWIN_BYTES, wbar);
+    // =============================================================== MMA issuer (converged warp, elected lane), window-major
+    {
+      if (lane == 0) {
+        mbar_expect_tx(wbar, 3 * BWIN_BYTES);
+        for (int w = 0; w < 3; ++w)
+          bulk_g2s(sB + w * BWIN_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, BWIN_BYTES, wbar);
+      }
+      __syncwarp();
       tc::mbar_wait_spin(wbar, 0);
       const uint32_t sb_u32 = base_u32 + NA * AWIN_BYTES;
       uint32_t buf = 0, phase = 0;
       long long tile_base = 0;                 // tiles issued so far by this CTA (TMEM slot = counter % NACC)
+      uint32_t win_count = 0;                  // windows consumed so far (TMEM A slot = counter & 1)
+      long long t_full = 0, t_tempty = 0; const long long t_mbegin = prof_clock<PROF>();
       for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
         const Strip s = decode_strip(p, sid);
         if (s.ntiles == 0) continue;
         for (int u = 0; u < s.ntiles + 2; ++u) {
-          tc::mbar_wait_spin(&full[buf], phase);
+          const uint32_t aslot = win_count & 1;
+          uint64_t* fbar = TA ? &full[aslot] : &full[buf];
+          const uint32_t fphase = TA ? ((win_count >> 1) & 1) : phase;
+          if (PROF) t_full += mbar_wait_timed<PROF>(fbar, fphase); else tc::mbar_wait_spin(fbar, fphase);
           tc_fence_after();
           const uint32_t sa = base_u32 + buf * AWIN_BYTES;
+          const uint32_t ta = tmem_base + TA_BASE + aslot * 64;
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk) {
             const int kh = 2 - kk;             // finish the oldest tile first so the epilogue can start on it
@@ -169,27 +301,39 @@ conv2d_c32_tc_kernel(const Params2 p) {
             const long long tcount = tile_base + j;
             const int slot = (int)(tcount & (NACC - 1));
             if (kh == 0) {                     // first touch of this tile's accumulator: the epilogue must have drained it
-              tc::mbar_wait_spin(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
+              if (PROF) t_tempty += mbar_wait_timed<PROF>(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
+              else tc::mbar_wait_spin(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
               tc_fence_after();
             }
-            const uint32_t tmem_d = tmem_base + slot * 128;
+            const uint32_t tmem_d = tmem_base + slot * ACC_STRIDE;
             const uint32_t sbw = sb_u32 + kh * BWIN_BYTES;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sbw + ks * 32);
-              mma_tf32(tmem_d, ah, bh, (kh | ks) != 0);
-              if (p.passes == 3) {
-                mma_tf32(tmem_d, make_desc(sa + A_BYTES + ks * 32), bh, 1);
-                mma_tf32(tmem_d, ah, make_desc(sbw + B_BYTES + ks * 32), 1);
+              const uint64_t bh = make_desc(sbw + ks * 32);
+              if (TA) {
+                mma_tf32_ts(tmem_d, ta + ks * 8, bh, (kh | ks) != 0);
+                if (p.passes == 3) {
+                  mma_tf32_ts(tmem_d, ta + 32 + ks * 8, bh, 1);
+                  mma_tf32_ts(tmem_d, ta + ks * 8, make_desc(sbw + B_BYTES + ks * 32), 1);
+                }
+              } else {
+                const uint64_t ah = make_desc(sa + ks * 32);
+                mma_tf32(tmem_d, ah, bh, (kh | ks) != 0);
+                if (p.passes == 3) {
+                  mma_tf32(tmem_d, make_desc(sa + A_BYTES + ks * 32), bh, 1);
+                  mma_tf32(tmem_d, ah, make_desc(sbw + B_BYTES + ks * 32), 1);
+                }
               }
             }
             if (kh == 2) mma_commit(&tfull[slot]);      // tile j = u-2 has received all three kh contributions
           }
-          mma_commit(&empty[buf]);                      // window u fully consumed
+          ++win_count;
+          mma_commit(TA ? &empty[aslot] : &empty[buf]);   // window u fully consumed (TA: its TMEM slot, else its smem buffer)
           if (++buf == NA) { buf = 0; phase ^= 1; }
         }
         tile_base += s.ntiles;
       }
+      if (PROF && p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 2] = t_full; p.dbg[blockIdx.x * 16 + 3] = t_tempty; p.dbg[blockIdx.x * 16 + 4] = prof_clock<PROF>() - t_mbegin; }
     }
     __syncwarp();
   } else {
@@ -207,10 +351,12 @@ conv2d_c32_tc_kernel(const Params2 p) {
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
     long long tcount = 0;
+    long long t_tfull = 0, t_pre = 0, t_tmem = 0, t_out = 0, t_bar = 0; const long long t_ebegin = prof_clock<PROF>();
     for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
       const Strip s = decode_strip(p, sid);
       const int x0 = s.cb * p.step - p.dil;
       for (int j = 0; j < s.ntiles; ++j, ++tcount) {
+        const long long tA = prof_clock<PROF>();
         const int slot = (int)(tcount & (NACC - 1));
         const uint32_t accphase = (uint32_t)((tcount / NACC) & 1);
         const int h = s.row0 + j * p.dil;
@@ -230,9 +376,11 @@ conv2d_c32_tc_kernel(const Params2 p) {
             if (okr[jj]) res[jj] = __ldcg(reinterpret_cast<const float4*>(e.residual + (rowbase + xs[jj]) * 32 + chunk * 4));
           }
         }
-        tc::mbar_wait(&tfull[slot], accphase);
+        t_pre += prof_clock<PROF>() - tA;
+        t_tfull += mbar_wait_timed<PROF>(&tfull[slot], accphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 128 + half * 16;
+        const long long tB = prof_clock<PROF>();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * ACC_STRIDE + half * 16;
         {
           float v0[16], v1[16], v2[16];
           tmem_ld16x3(taddr, taddr + 32, taddr + 64, v0, v1, v2);
@@ -248,7 +396,9 @@ conv2d_c32_tc_kernel(const Params2 p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[slot]);
-        epi_bar();
+        t_tmem += prof_clock<PROF>() - tB;
+        { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }
+        const long long tC = prof_clock<PROF>();
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {       // branch-free: out-of-range rows read clamped smem rows and skip only the store
@@ -287,9 +437,11 @@ conv2d_c32_tc_kernel(const Params2 p) {
             e.stats[(((size_t)s.b * p.H + h) * p.ncb + s.cb) * 64 + et] = a;
           }
         }
-        epi_bar();
+        t_out += prof_clock<PROF>() - tC;
+        { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }
       }
     }
+    if (PROF && p.dbg && et == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = prof_clock<PROF>() - t_ebegin; d[7] = t_bar; d[8] = t_pre; d[9] = t_tmem; d[10] = t_out; }
   }
 
   tc_fence_before();
@@ -330,20 +482,42 @@ extern "C" int snb_conv2d_c32_tc_num_tiles(const snb_conv_geom* g) {
   return p.B * p.H * p.ncb;          // one stats row per (image row, column block)
 }
 
+static int conv2d_tc_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                            int passes, long long* dbg, void* stream);
+
 extern "C" int snb_conv2d_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                                  int passes, void* stream) {
+  return conv2d_tc_launch(x, wimg, y, g, e, passes, nullptr, stream);
+}
+
+extern "C" int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
+                                         const snb_conv_epilogue* e, int passes, long long* counters, void* stream) {
+  SNB_REQUIRE(counters != nullptr, "snb_conv2d_c32_tc_profile: null counters");
+  return conv2d_tc_launch(x, wimg, y, g, e, passes, counters, stream);
+}
+
+template <bool TA, bool PROF>
+static int conv2d_tc_go(const tc2d::Params2& p, int grid, void* stream) {
+  SNB_CUDA(cudaFuncSetAttribute(tc2d::conv2d_c32_tc_kernel<TA, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2d::SMEM_BYTES2));
+  tc2d::conv2d_c32_tc_kernel<TA, PROF><<<grid, tc::NTHREADS, tc2d::SMEM_BYTES2, (cudaStream_t)stream>>>(p);
+  SNB_LAUNCH_CHECK("conv2d_c32_tc_kernel");
+  return 0;
+}
+
+static int conv2d_tc_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                            int passes, long long* dbg, void* stream) {
   tc2d::Params2 p;
   if (int rc = tc2d_setup(g, p, "snb_conv2d_c32_tc")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv2d_c32_tc: null pointer");
+  const bool legacy = (passes & 0x100) != 0;      // diagnostics: A operand from shared memory instead of TMEM
+  passes &= 0xff;
   SNB_REQUIRE(passes == 1 || passes == 3, "snb_conv2d_c32_tc: passes must be 1 or 3");
   SNB_REQUIRE(!e->scale || e->shift, "snb_conv2d_c32_tc: scale without shift");
-  p.x = x; p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e;
+  p.x = x; p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e; p.dbg = dbg;
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nstrips < sms ? p.nstrips : sms;
-  SNB_CUDA(cudaFuncSetAttribute(tc2d::conv2d_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2d::SMEM_BYTES2));
-  tc2d::conv2d_c32_tc_kernel<<<grid, tc::NTHREADS, tc2d::SMEM_BYTES2, (cudaStream_t)stream>>>(p);
-  SNB_LAUNCH_CHECK("conv2d_c32_tc_kernel");
-  return 0;
+  if (dbg) return legacy ? conv2d_tc_go<false, true>(p, grid, stream) : conv2d_tc_go<true, true>(p, grid, stream);
+  return legacy ? conv2d_tc_go<false, false>(p, grid, stream) : conv2d_tc_go<true, false>(p, grid, stream);
 }

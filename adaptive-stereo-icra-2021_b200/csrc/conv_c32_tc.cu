@@ -154,12 +154,15 @@ conv_c32_tc_kernel(const Params p) {
     }
     if (PROF && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_wait; p.dbg[blockIdx.x * 16 + 1] = prof_clock<PROF>() - t_begin; }
   } else if (warp == NUM_LOADER_WARPS) {
-    // =============================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // =============================================================== MMA issuer (converged warp, elected lane)
+    {
       if (!stream_b) {       // 2-D: window kh always lands in stage kh -> keep its B image resident there
-        mbar_expect_tx(wbar, (uint32_t)p.nwin * 2 * B_BYTES);
-        for (int w = 0; w < p.nwin; ++w)
-          bulk_g2s(base + w * STAGE_BYTES + 2 * A_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, wbar);
+        if (lane == 0) {
+          mbar_expect_tx(wbar, (uint32_t)p.nwin * 2 * B_BYTES);
+          for (int w = 0; w < p.nwin; ++w)
+            bulk_g2s(base + w * STAGE_BYTES + 2 * A_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, wbar);
+        }
+        __syncwarp();
         mbar_wait_spin(wbar, 0);
       }
       uint32_t stage = 0, phase = 0;
@@ -190,7 +193,7 @@ conv_c32_tc_kernel(const Params p) {
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
-      if (PROF && p.dbg) { p.dbg[blockIdx.x * 16 + 2] = t_full; p.dbg[blockIdx.x * 16 + 3] = t_tempty; p.dbg[blockIdx.x * 16 + 4] = prof_clock<PROF>() - t_begin; }
+      if (PROF && p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 2] = t_full; p.dbg[blockIdx.x * 16 + 3] = t_tempty; p.dbg[blockIdx.x * 16 + 4] = prof_clock<PROF>() - t_begin; }
     }
     __syncwarp();
   } else {

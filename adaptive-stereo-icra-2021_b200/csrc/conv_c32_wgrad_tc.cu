@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t mn_off(int rr, int chunk) {
 }
 
 __device__ __forceinline__ void mma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if (elect_one())
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -225,8 +226,8 @@ conv_c32_wgrad_tc_kernel(const WParams p) {
       }
     }
   } else {
-    // =============================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // =============================================================== MMA issuer (converged warp, elected lane)
+    {
       uint32_t xc = 0, zc = 0, used = 0;
       bool any = false;
       const uint32_t zb_u32 = base_u32 + ring_bytes;
@@ -282,9 +283,9 @@ conv_c32_wgrad_tc_kernel(const WParams p) {
         mma_commit(&xempty[(xc + s.nt + 1) % R]);
         xc += s.nt + 2;
       }
-      *used_slot = used;
-      if (p.dbg) { float* d = p.dbg + blockIdx.x * 64; d[0] = (float)used; d[1] = (float)xc; d[2] = (float)zc; d[3] = any ? 1.f : 0.f; }
-      if (any) mma_commit(done); else mbar_arrive(done);
+      if (lane == 0) *used_slot = used;
+      if (p.dbg && lane == 0) { float* d = p.dbg + blockIdx.x * 64; d[0] = (float)used; d[1] = (float)xc; d[2] = (float)zc; d[3] = any ? 1.f : 0.f; }
+      if (any) mma_commit(done); else if (lane == 0) mbar_arrive(done);
     }
     __syncwarp();
   }

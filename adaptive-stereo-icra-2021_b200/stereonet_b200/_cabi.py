@@ -31,6 +31,7 @@ SIGNATURES = {
   "snb_conv_c32_tc_num_tiles": (_I, [_GP]),
   "snb_conv2d_c32_tc": (_I, [_P, _P, _P, _GP, _EP, _I, _P]),
   "snb_conv2d_c32_tc_num_tiles": (_I, [_GP]),
+  "snb_conv2d_c32_tc_profile": (_I, [_P, _P, _P, _GP, _EP, _I, _P, _P]),
   "snb_conv_c32_tc_profile": (_I, [_P, _P, _P, _GP, _EP, _I, _P, _P]),
   "snb_prep_conv_weights_tc": (_I, [_P, _P, _I, _I, _P]),
   "snb_conv_weights_tc_floats": (_I, [_I]),

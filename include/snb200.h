@@ -94,6 +94,10 @@ SNB_API int snb_conv_c32_tc_profile(const float* x, const float* wimg, float* y,
 SNB_API int snb_conv2d_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                       int passes, void* stream);
 SNB_API int snb_conv2d_c32_tc_num_tiles(const snb_conv_geom* g);
+/* Diagnostics: same launch plus per-CTA cycle counters (layout of snb_conv_c32_tc_profile).  passes | 0x100 selects the
+ * legacy path that feeds the A operand from shared memory instead of TMEM (for A/B measurements). */
+SNB_API int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
+                              const snb_conv_epilogue* e, int passes, long long* counters, void* stream);
 /* Repack [32][32][kd*3*3] weights into the tensor-core B-operand smem image (hi/lo TF32 split, SWIZZLE_128B K-major,
  * one 24 KB block per (kd,kh) window).  kd = 1 (2-D) or 3 (3-D).  mode 0: forward, 1: data gradient. */
 SNB_API int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream);

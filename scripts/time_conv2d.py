@@ -1,0 +1,25 @@
+"""2-D tensor-core conv: TMEM-A vs smem-A operand path, parity against the FFMA kernel and timing at KITTI size."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "adaptive-stereo-icra-2021_b200")); sys.path.insert(0, ROOT)
+import torch
+from stereonet_b200 import ops
+from bench import time_kernel
+dev = "cuda:0"
+torch.manual_seed(0)
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+stream = torch.cuda.current_stream()
+for shape, dil in [((1, 47, 156, 32), 1), ((1, 376, 1248, 32), 1), ((1, 376, 1248, 32), 2), ((1, 376, 1248, 32), 4), ((1, 376, 1248, 32), 8), ((2, 47, 156, 32), 1)]:
+  x = torch.randn(shape, device=dev)
+  w = torch.randn(32, 32, 3, 3, device=dev) * 0.1
+  b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
+  g = ops.geom(shape, 3, dil=dil)
+  wimg = ops.prep_conv_weights_tc(w); wp = ops.prep_conv_weights(w)
+  ref, _ = ops.conv_c32(x, wp, g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True)
+  flops = 2 * 9 * 32 * 32 * x.numel() / 32
+  for passes in (3, 1):
+    for a_smem in (False, True):
+      y, _ = ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True, passes=passes, a_smem=a_smem)
+      err = (y - ref).abs().max().item() / ref.abs().max().item()
+      ms, med = time_kernel(lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True, passes=passes, a_smem=a_smem), 10, flush, stream)
+      print(f"{shape} dil{dil} passes{passes} {'smemA' if a_smem else 'tmemA'}: {ms*1e3:7.1f} us  {flops/ms/1e9:6.1f} TFLOP/s  rel err {err:.2e}", flush=True)

@@ -14,6 +14,6 @@ for shape, dil in [((1, 376, 1248, 32), 1), ((1, 376, 1248, 32), 2), ((1, 376, 1
   ws = (32, 32, 3, 3, 3) if len(shape) == 5 else (32, 32, 3, 3)
   taps = 27 if len(shape) == 5 else 9
   flops = 2 * taps * 32 * 32 * x.numel() / 32
-  for name, fn in [("tc3", lambda: ops.conv_c32_wgrad_tc(x, dz, g, ws, 3)), ("tc1", lambda: ops.conv_c32_wgrad_tc(x, dz, g, ws, 1)), ("ffma", lambda: ops.conv_c32_wgrad(x, dz, g, ws))]:
+  for name, fn in [("tc3", lambda: ops.conv_c32_wgrad_tc(x, dz, g, ws, 3)), ("tc1", lambda: ops.conv_c32_wgrad_tc(x, dz, g, ws, 1))] + ([("ffma", lambda: ops.conv_c32_wgrad(x, dz, g, ws))] if os.environ.get("WITH_FFMA") else []):
     ms, med = time_kernel(fn, 10, flush, stream)
     print(f"{shape} dil{dil} {name}: {ms*1e3:.1f} us (median {med*1e3:.1f})  {flops/ms/1e9:.1f} TFLOP/s  [incl. reduce_partials + layout permute]")
