@@ -35,6 +35,8 @@ SIGNATURES = {
   "snb_conv_c32_tc_profile": (_I, [_P, _P, _P, _GP, _EP, _I, _P, _P]),
   "snb_prep_conv_weights_tc": (_I, [_P, _P, _I, _I, _P]),
   "snb_conv_weights_tc_floats": (_I, [_I]),
+  "snb_phase_split": (_I, [_P, _P, _I, _I, _I, _P]),
+  "snb_phase_merge": (_I, [_P, _P, _I, _I, _I, _P]),
   "snb_conv5x5s2_c3": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
   "snb_refine_in_conv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _EP, _P]),
   "snb_refine_in_conv_num_tiles": (_I, [_I, _I, _I]),

@@ -52,6 +52,8 @@ class ConvC32(torch.autograd.Function):
     g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
     if ksize == 3 and stride == 1:
       y, _ = fused.conv3x3_c32(x, conv, g, bias=b.detach())
+    elif ksize == 5 and stride == 2:
+      y = fused.conv5x5s2_c32(x, conv, b.detach())
     else:
       y, _ = ops.conv_c32(x, fused.wprep(conv), g, bias=b.detach())
     ctx.save_for_backward(x)
@@ -67,6 +69,8 @@ class ConvC32(torch.autograd.Function):
     if ctx.needs_input_grad[0]:
       if ctx.ksize == 3 and ctx.stride == 1:
         dx, _ = fused.conv3x3_c32_dgrad(dy, ctx.conv, g)
+      elif ctx.ksize == 5 and ctx.stride == 2:
+        dx = fused.conv5x5s2_c32_dgrad(dy, ctx.conv, x.shape[1], x.shape[2])
       else:
         gt = ops.geom_transposed(g)
         dx, _ = ops.conv_c32(dy, fused.wprep(ctx.conv, 2), gt)

@@ -120,6 +120,49 @@ def conv5x5s2_first(img, conv):
   return ops.conv5x5s2_c3(img, conv.weight, conv.bias)
 
 
+def wprep_tc_phases(conv, mode):
+  """Tensor-core weight images of the four polyphase 3x3 sub-kernels of a 5x5 stride-2 conv (csrc/phase.cu)."""
+  def make():
+    w = conv.weight.detach()
+    imgs = []
+    for a in (0, 1):
+      for b in (0, 1):
+        sub = w[:, :, a::2, b::2]                                  # [32,32,3|2,3|2]  (layout ops only)
+        sub = torch.nn.functional.pad(sub, (0, 3 - sub.shape[3], 0, 3 - sub.shape[2])).contiguous()
+        imgs.append(ops.prep_conv_weights_tc(sub, mode))
+    return imgs
+  return _cached(conv, ("wtc_phase", mode), [conv.weight], make)
+
+
+def conv5x5s2_c32(x, conv, bias):
+  """5x5 stride-2 pad-2 32->32 convolution: FFMA kernel, or four chained tensor-core 3x3 convs over the phase images."""
+  if CONV_BACKEND == "ffma":
+    g = ops.geom(x.shape, 5, stride=2, dil=1, pad=2)
+    y, _ = ops.conv_c32(x, wprep(conv), g, bias=bias)
+    return y
+  ph = ops.phase_split(x)
+  g3 = ops.geom(ph[0].shape, 3, stride=1, dil=1)
+  passes = 3 if CONV_BACKEND == "tc3" else 1
+  y = None
+  for i, wimg in enumerate(wprep_tc_phases(conv, 0)):
+    y, _ = ops.conv_c32_tc(ph[i], wimg, g3, bias=bias if i == 0 else None, residual=y, passes=passes)
+  return y
+
+
+def conv5x5s2_c32_dgrad(dy, conv, H, W):
+  """Data gradient of the above: dx[2i+a][2j+b] = conv3x3_same(dy, flipped/transposed W_ab)[i][j]."""
+  if CONV_BACKEND == "ffma":
+    g = ops.geom((dy.shape[0], H, W, 32), 5, stride=2, dil=1, pad=2)
+    dx, _ = ops.conv_c32(dy, wprep(conv, 2), ops.geom_transposed(g))
+    return dx
+  g3 = ops.geom(dy.shape, 3, stride=1, dil=1)
+  passes = 3 if CONV_BACKEND == "tc3" else 1
+  ph = torch.empty((4,) + tuple(dy.shape), device=dy.device, dtype=torch.float32)
+  for i, wimg in enumerate(wprep_tc_phases(conv, 1)):
+    ops.conv_c32_tc(dy, wimg, g3, passes=passes, out=ph[i])
+  return ops.phase_merge(ph, H, W)
+
+
 def conv_plain(x, conv, ksize, stride):
   """Conv2d 32->32 with bias only (downsample[1:], conv_alone)."""
   g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
@@ -128,6 +171,8 @@ def conv_plain(x, conv, ksize, stride):
     return functions.ConvC32.apply(x, conv.weight, conv.bias, conv, ksize, stride)
   if ksize == 3 and stride == 1:
     y, _ = conv3x3_c32(x, conv, g, bias=conv.bias.detach())
+  elif ksize == 5 and stride == 2:
+    y = conv5x5s2_c32(x, conv, conv.bias.detach())
   else:
     y, _ = ops.conv_c32(x, wprep(conv), g, bias=conv.bias.detach())
   return y

@@ -129,7 +129,7 @@ def prep_conv_weights_tc(w, mode=0):
 
 
 def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
-                flat=False, a_smem=False):
+                flat=False, a_smem=False, out=None):
   """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.
   2-D inputs use the vertical-walk kernel (snb_conv2d_c32_tc) unless flat=True; 3-D inputs the flat-tiled one."""
   three_d = x.dim() == 5
@@ -137,7 +137,11 @@ def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lr
   lib = _cabi.lib()
   use2d = (not three_d) and (not flat)
   fn, fn_tiles = (lib.snb_conv2d_c32_tc, lib.snb_conv2d_c32_tc_num_tiles) if use2d else (lib.snb_conv_c32_tc, lib.snb_conv_c32_tc_num_tiles)
-  y = torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
+  y = out if out is not None else torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
+  if out is not None:
+    _req(out, "out")
+    if tuple(out.shape) != tuple(out_shape(g, three_d)):
+      raise RuntimeError("stereonet_b200: `out` shape mismatch")
   stats = None
   if want_stats:
     nt = fn_tiles(C.byref(g))
@@ -152,6 +156,26 @@ def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lr
   check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
   _count()
   return y, stats
+
+
+def phase_split(x):
+  """[B,H,W,32] -> [4,B,ceil(H/2),ceil(W/2),32]: phase a*2+b holds x[:, a::2, b::2] (zero padded to the common size)."""
+  _req(x, "x", 4)
+  B, H, W, _ = x.shape
+  out = torch.empty((4, B, (H + 1) // 2, (W + 1) // 2, 32), device=x.device, dtype=torch.float32)
+  check(_cabi.lib().snb_phase_split(_p(x), _p(out), B, H, W, _stream(x)), "snb_phase_split")
+  _count()
+  return out
+
+
+def phase_merge(ph, H, W):
+  """Inverse of phase_split: [4,B,ceil(H/2),ceil(W/2),32] -> [B,H,W,32]."""
+  _req(ph, "phases", 5)
+  B = ph.shape[1]
+  dx = torch.empty((B, H, W, 32), device=ph.device, dtype=torch.float32)
+  check(_cabi.lib().snb_phase_merge(_p(ph), _p(dx), B, H, W, _stream(ph)), "snb_phase_merge")
+  _count()
+  return dx
 
 
 def conv5x5s2_c3(img, w, bias):

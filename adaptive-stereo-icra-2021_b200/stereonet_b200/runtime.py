@@ -88,3 +88,60 @@ class StereoEngine:
       key = "pred_disp_l/{}".format(self.stereo_net.input_scale)
     out_host.copy_(out[key], non_blocking=True)
     return out_host
+
+  # ------------------------------------------------------------------------------------------------ streaming API
+  def _pipe(self, e, dev):
+    p = e.get("pipe")
+    if p is None:
+      B2 = e["pair"].shape[0]
+      key = "pred_disp_l/{}".format(self.stereo_net.input_scale)
+      p = dict(i=0, key=key, s_in=torch.cuda.Stream(device=dev), s_out=torch.cuda.Stream(device=dev),
+               stage_in=[torch.empty_like(e["pair"]) for _ in range(2)],
+               stage_out=[torch.empty_like(e["out"][key]) for _ in range(2)],
+               ev_in=[torch.cuda.Event() for _ in range(2)], ev_free=[torch.cuda.Event() for _ in range(2)],
+               ev_out=[torch.cuda.Event() for _ in range(2)], ev_outfree=[torch.cuda.Event() for _ in range(2)])
+      cur = torch.cuda.current_stream(dev)
+      for k in range(2):
+        p["ev_free"][k].record(cur); p["ev_outfree"][k].record(cur)
+      e["pipe"] = p
+    return p
+
+  @torch.no_grad()
+  def infer_host_async(self, left_host, right_host, out_host):
+    """Streaming variant of infer_host for frame sequences: the H2D copy of frame i+1 (copy-in stream), the forward of
+    frame i (current stream, CUDA graph) and the D2H copy of frame i-1 (copy-out stream) overlap through double-buffered
+    device staging.  `out_host` is valid after `synchronize()`; the caller must not overwrite `left_host`/`right_host`
+    of a frame before the next-but-one call returns (or before `synchronize()`)."""
+    dev = next(self.stereo_net.parameters()).device
+    e = self._entry(left_host.shape, dev)
+    p = self._pipe(e, dev)
+    k = p["i"] & 1
+    B = left_host.shape[0]
+    cur = torch.cuda.current_stream(dev)
+    p["s_in"].wait_event(p["ev_free"][k])                 # staging k was consumed by the forward two frames ago
+    with torch.cuda.stream(p["s_in"]):
+      p["stage_in"][k][:B].copy_(left_host, non_blocking=True)
+      p["stage_in"][k][B:].copy_(right_host, non_blocking=True)
+      p["ev_in"][k].record(p["s_in"])
+    cur.wait_event(p["ev_in"][k])
+    e["pair"].copy_(p["stage_in"][k], non_blocking=True)  # device-to-device into the graph's static input
+    p["ev_free"][k].record(cur)
+    out, _ = self.run_static(left_host.shape, dev)
+    cur.wait_event(p["ev_outfree"][k])                    # the D2H of two frames ago has drained staging k
+    p["stage_out"][k].copy_(out[p["key"]], non_blocking=True)
+    p["ev_out"][k].record(cur)
+    p["s_out"].wait_event(p["ev_out"][k])
+    with torch.cuda.stream(p["s_out"]):
+      out_host.copy_(p["stage_out"][k], non_blocking=True)
+      p["ev_outfree"][k].record(p["s_out"])
+    p["i"] += 1
+    return out_host
+
+  def synchronize(self):
+    """Make the current stream wait for every copy issued by infer_host_async (then synchronize it on the host)."""
+    for e in self._graphs.values():
+      p = e.get("pipe")
+      if p is not None:
+        dev = e["pair"].device
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_stream(p["s_in"]); cur.wait_stream(p["s_out"])

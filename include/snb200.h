@@ -103,6 +103,13 @@ SNB_API int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, float* 
 SNB_API int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream);
 SNB_API int snb_conv_weights_tc_floats(int kd);
 
+/* Polyphase helpers for the stride-2 5x5 32->32 layers (stereo_net.py:64-70): the convolution is the sum of four stride-1
+ * 'same' 3x3 convolutions over the phase images P_ab[i][j] = x[2i+a][2j+b], so forward and data gradient run on
+ * snb_conv2d_c32_tc.  snb_phase_split: x [B,H,W,32] -> out [4][B,ceil(H/2),ceil(W/2),32] (phase a*2+b, zero padded);
+ * snb_phase_merge: the inverse interleave, in [4][B,ceil(H/2),ceil(W/2),32] -> dx [B,H,W,32]. */
+SNB_API int snb_phase_split(const float* x, float* out, int B, int H, int W, void* stream);
+SNB_API int snb_phase_merge(const float* in, float* dx, int B, int H, int W, void* stream);
+
 /* Small-Cin first layers.
  * snb_conv5x5s2_c3: FeatureExtractorNetwork.downsample[0] (stereo_net.py:64-70,81): NCHW image [B,3,H,W] -> [B,OH,OW,32]. */
 SNB_API int snb_conv5x5s2_c3(const float* img, const float* w /*[32][3][5][5]*/, const float* bias, float* y,

@@ -157,6 +157,29 @@ def test_engine_graph_replay_matches_module_calls(kitti):
     assert torch.equal(host, ref["pred_disp_l/0"].cpu())
 
 
+def test_engine_streaming_api_matches_blocking_api(kitti):
+  """infer_host_async (copy-in / forward / copy-out overlapped on three streams, double-buffered staging) must return,
+  frame by frame, exactly what the blocking infer_host returns — over more frames than staging buffers."""
+  from stereonet_b200.runtime import StereoEngine
+  cfg, fsd, ssd, left, right, gt, f, s = kitti
+  eng = StereoEngine(f, s, output_cost_volume=True)
+  frames = [(left, right)] + [O.make_stereo_pair(1, 376, 1248, seed=2000 + i, max_disp_px=30.0 + 5 * i)[:2] for i in range(4)]
+  pins = [(l.pin_memory(), r.pin_memory()) for l, r in frames]
+  ref = []
+  for l, r in pins:
+    host = torch.empty((1, 1, 376, 1248)).pin_memory()
+    eng.infer_host(l, r, host)
+    torch.cuda.synchronize()
+    ref.append(host.clone())
+  outs = [torch.empty((1, 1, 376, 1248)).pin_memory() for _ in pins]
+  for (l, r), o in zip(pins, outs):
+    eng.infer_host_async(l, r, o)
+  eng.synchronize()
+  torch.cuda.synchronize()
+  for i, (a, b) in enumerate(zip(outs, ref)):
+    assert torch.equal(a, b), f"frame {i}"
+
+
 @pytest.mark.parametrize("backend,tol", [("ffma", 1e-2), ("tc3", 1e-2), ("tc1", None)])
 def test_conv_backends_agree(kitti, backend, tol):
   """All three convolution back ends are this library's kernels; fp32-grade ones must meet the north-star tolerance."""
