@@ -17,7 +17,8 @@ struct TileDims {
   static constexpr int ROW = (S == 2) ? 2 * IWP : IWP;
   static constexpr int IN_FLOATS = (CIN * IH * ROW + 3) & ~3;   // keep the weight block 16-B aligned
   static constexpr int W_FLOATS = CIN * KS * KS * 32;
-  static constexpr int SMEM_BYTES = (IN_FLOATS + W_FLOATS + 64 * 8) * 4;
+  static constexpr int MAIN_FLOATS = (IN_FLOATS + W_FLOATS) > 8 * 1024 ? (IN_FLOATS + W_FLOATS) : 8 * 1024;   // >= output staging (8 warps x 4 KB)
+  static constexpr int SMEM_BYTES = (MAIN_FLOATS + 64 * 8) * 4;
 };
 
 template <int S, int IWP>
@@ -48,7 +49,7 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
   extern __shared__ __align__(16) float smem[];
   float* sIn = smem;
   float* sW = smem + T::IN_FLOATS;             // [k][32], k = (ci*KS + kh)*KS + kw
-  float* sRed = sW + T::W_FLOATS;              // [8 warps][64]
+  float* sRed = smem + T::MAIN_FLOATS;         // [8 warps][64]
   const int t = threadIdx.x;
   const int tiles_x = (OW + TW - 1) / TW, tiles_y = (OH + TH - 1) / TH;
   const int tile = blockIdx.x;
@@ -134,15 +135,27 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
     if (e.scale) { const float sc = e.scale[j], sh = e.shift[j]; acc0[j] = fmaf(acc0[j], sc, sh); acc1[j] = fmaf(acc1[j], sc, sh); }
     if (e.lrelu) { acc0[j] = lrelu(acc0[j]); acc1[j] = lrelu(acc1[j]); }
   }
-  if (oka) {
-    float4* yp = reinterpret_cast<float4*>(y + (((size_t)b * OH + oy) * OW + oxa) * 32);
+  // Coalesced output: a thread holds whole pixels (32 channels = 128 B); writing them directly would touch 32 different
+  // lines per STG.  Each warp transposes its 32-pixel run through a private 4 KB smem tile (16-B chunks XOR-swizzled by
+  // pixel) and stores 4 KB of consecutive channels-last memory with fully coalesced STG.128.
+  __syncthreads();                             // every warp is done with the input tile / weights: reuse as staging
+  float* stg = smem + ty * 1024;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) yp[j] = make_float4(acc0[4 * j], acc0[4 * j + 1], acc0[4 * j + 2], acc0[4 * j + 3]);
-  }
-  if (okb) {
-    float4* yp = reinterpret_cast<float4*>(y + (((size_t)b * OH + oy) * OW + oxb) * 32);
+  for (int half = 0; half < 2; ++half) {
+    const float* acc = half ? acc1 : acc0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) yp[j] = make_float4(acc1[4 * j], acc1[4 * j + 1], acc1[4 * j + 2], acc1[4 * j + 3]);
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stg + tx * 32 + ((j ^ (tx & 7)) << 2)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    __syncwarp();
+    const int oxs = ox0 + half * 32;
+    float* yrow = y + (((size_t)b * OH + oy) * OW + oxs) * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = i * 32 + tx, pp = idx >> 3, c = idx & 7;
+      const float4 v = *reinterpret_cast<const float4*>(stg + pp * 32 + ((c ^ (pp & 7)) << 2));
+      if (oy < OH && oxs + pp < OW) *reinterpret_cast<float4*>(yrow + (size_t)pp * 32 + c * 4) = v;
+    }
+    __syncwarp();
   }
 }
 

@@ -80,7 +80,9 @@ SNB_API int snb_conv_c32(const float* x, const float* wprep, float* y, const snb
 /* Same contract as snb_conv_c32 for stride-1 "same" 3x3 (dilated) / 3x3x3 convolutions, on the tcgen05 tensor cores
  * (TF32 operands from shared memory, fp32 accumulators in TMEM; kw folded into N = 96).  passes = 3: error-compensated
  * 3xTF32 split (fp32-grade results); passes = 1: plain single-pass TF32.  wimg from snb_prep_conv_weights_tc.
- * `stats` rows are indexed by this kernel's own tiles: snb_conv_c32_tc_num_tiles(). */
+ * `stats` rows are indexed by this kernel's own tiles: snb_conv_c32_tc_num_tiles().
+ * Diagnostics: passes | 0x200 feeds the A operand from TMEM (loader -> raw smem -> converter warps -> tcgen05.st) instead
+ * of shared memory; slower for this flat-tiled kernel (9 windows per tile), default for the 2-D walk kernel. */
 SNB_API int snb_conv_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                     int passes, void* stream);
 SNB_API int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g);
