@@ -1,0 +1,374 @@
+// 3-D 32->32 3x3x3 'same' convolution (cost filtering, stereo_net.py:155-160,185-186) on the tcgen05 tensor cores with a TMA
+// producer and the A operand in TMEM.  Same GEMM formulation as conv_c32_tc.cu (M = 128 positions, N = 96 = 3 kw x 32 cout,
+// K = 9 (kd,kh) windows x 32 cin, 3xTF32 split, epilogue out[m] = Y0[m-1] + Y1[m] + Y2[m+1]) but:
+//   * tiles are 128 consecutive positions of the UNPADDED flat index q = h*W + w of one (b,d) slice, so a (kd,kh) window is
+//     16 KB of contiguous channels-last memory: one 4-D TMA tile load (box 32 ch x 128 positions, SWIZZLE_128B, zero fill
+//     for q < 0, q >= H*W and d' outside [0,D)) — no loader warps, no per-element address arithmetic.  The wrap of the +-1
+//     kw shift across image rows is undone in the epilogue (Y0 is dropped at w = 0, Y2 at w = W-1);
+//   * 4 converter warps (one per TMEM lane quadrant, thread = position) read the raw fp32 window (conflict-free LDS.128),
+//     split hi/lo in registers and tcgen05.st it into one of two A slots in TMEM; the MMAs read A from TMEM, so the
+//     per-MMA shared-memory fetch is the 3 KB B operand only (the smem-operand kernel is bound by its 7 KB A+B fetch);
+//   * windows of slices outside the volume (d' = -1, D) are skipped instead of multiplied as zeros.
+// Warps: 0 producer (TMA A + bulk B), 1 MMA issuer, 2-9 converters (two per TMEM lane quadrant, alternating windows),
+// 10-17 epilogue (two per quadrant).  smem: 4 x 16 KB raw A ring | 4 x 24 KB B ring (hi|lo) | 48 KB epilogue tiles.
+// TMEM: 2 accumulators x 96 | 4 A slots x 64 (a tile is 9 windows long, so two accumulators keep the epilogue off the critical path).
+#include <cuda.h>
+#include "tc_common.cuh"
+
+namespace tc3 {
+
+using namespace tc;
+
+constexpr int NR = 4;                                    // ring depth (raw A and B)
+constexpr int NTHREADS3 = 18 * 32;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;                // 8 converter warps: two per quadrant, alternating windows
+constexpr int NACC3 = 2, NA = 4;                           // TMEM: 2 accumulators x 96 columns | 4 A slots x 64 columns
+constexpr int ACC_STRIDE = 96, TA_BASE = NACC3 * 96;
+constexpr int SMEM_BYTES3 = NR * A_BYTES + NR * 2 * B_BYTES + OUT_BYTES + 3072 /*barriers, stats scratch*/ + 1024 /*alignment slack*/;
+
+struct Params3 {
+  const float* wimg; float* y;
+  int B, D, H, W;
+  int tiles_per_slice, ntiles, step;       // step = 126 output positions per tile
+  int passes;
+  snb_conv_epilogue e;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void epi_bar3() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(NTHREADS3, 1)
+conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
+  unsigned char* sBring = base + NR * A_BYTES;
+  unsigned char* sOutB = sBring + NR * 2 * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOutB + OUT_BYTES);
+  uint64_t* rfull = bars;                // [NR]   TMA (A window) -> converters
+  uint64_t* rempty = rfull + NR;         // [NR]   converters -> producer
+  uint64_t* bfull = rempty + NR;         // [NR]   bulk copy (B window) -> MMA
+  uint64_t* bempty = bfull + NR;         // [NR]   MMA commit -> producer
+  uint64_t* afull = bempty + NR;         // [NA]    converters -> MMA (A slot in TMEM)
+  uint64_t* aempty = afull + NA;         // [NA]    MMA commit -> converters
+  uint64_t* tfull = aempty + NA;         // [NACC3] MMA commit -> epilogue
+  uint64_t* tempty = tfull + NACC3;      // [NACC3] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC3);
+  float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+      for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+      for (int i = 0; i < NACC3; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int HW = p.H * p.W;
+
+  if (warp == 0) {
+    // =============================================================== producer: one TMA tile load (A) + one bulk copy (B) per window
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
+        const int b = slice / p.D, d = slice - b * p.D;
+        const int q0 = tt * p.step - 1;
+        for (int widx = 0; widx < 9; ++widx) {
+          const int kd = widx / 3, kh = widx - kd * 3;
+          const int dd = d + kd - 1;
+          if ((unsigned)dd >= (unsigned)p.D) continue;
+          const uint32_t s = cnt % NR, ph = ((cnt / NR) & 1) ^ 1;
+          tc::mbar_wait(&rempty[s], ph);
+          mbar_expect_tx(&rfull[s], A_BYTES);
+          tma_load_4d(base + s * A_BYTES, &tmap, &rfull[s], 0, q0 + (kh - 1) * p.W, dd, b);
+          tc::mbar_wait(&bempty[s], ph);
+          mbar_expect_tx(&bfull[s], 2 * B_BYTES);
+          bulk_g2s(sBring + s * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[s]);
+          ++cnt;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (converged warp, elected lane)
+    uint32_t cnt = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int slice = tile / p.tiles_per_slice;
+      const int d = slice % p.D;
+      const int acc = it & (NACC3 - 1);
+      tc::mbar_wait_spin(&tempty[acc], (uint32_t)(((it / NACC3) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+      bool first = true;
+      for (int widx = 0; widx < 9; ++widx) {
+        const int dd = d + widx / 3 - 1;
+        if ((unsigned)dd >= (unsigned)p.D) continue;
+        const uint32_t s = cnt % NR, aslot = cnt % NA;
+        tc::mbar_wait_spin(&afull[aslot], (cnt / NA) & 1);
+        tc::mbar_wait_spin(&bfull[s], (cnt / NR) & 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + TA_BASE + aslot * 64;
+        const uint32_t sb = base_u32 + NR * A_BYTES + s * 2 * B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bh = make_desc(sb + ks * 32);
+          mma_tf32_ts(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
+          if (p.passes == 3) {
+            mma_tf32_ts(tmem_d, ta + 32 + ks * 8, bh, 1);
+            mma_tf32_ts(tmem_d, ta + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
+          }
+        }
+        first = false;
+        mma_commit(&aempty[aslot]);
+        mma_commit(&bempty[s]);
+        ++cnt;
+      }
+      mma_commit(&tfull[acc]);
+    }
+  } else if (warp < EPI_WARP0) {
+    // =============================================================== converters (TMEM lane quadrant = warp % 4, thread = position)
+    const int quad = warp & 3;
+    const uint32_t mine = (uint32_t)(warp - CONV_WARP0) >> 2;      // this warp converts the windows with cnt % 2 == mine
+    const int m = quad * 32 + lane;
+    uint32_t cnt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int d = (tile / p.tiles_per_slice) % p.D;
+      for (int widx = 0; widx < 9; ++widx) {
+        const int dd = d + widx / 3 - 1;
+        if ((unsigned)dd >= (unsigned)p.D) continue;
+        if ((cnt & 1) != mine) { ++cnt; continue; }
+        const uint32_t s = cnt % NR, aslot = cnt % NA;
+        tc::mbar_wait(&rfull[s], (cnt / NR) & 1);
+        const unsigned char* st = base + s * A_BYTES + m * 128;
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(st + ((c ^ (m & 7)) << 4));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rempty[s]);            // raw window consumed (values are in registers)
+        tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * 64;
+        {
+          uint32_t h[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            h[4 * c] = __float_as_uint(v[c].x) & 0xffffe000u; h[4 * c + 1] = __float_as_uint(v[c].y) & 0xffffe000u;
+            h[4 * c + 2] = __float_as_uint(v[c].z) & 0xffffe000u; h[4 * c + 3] = __float_as_uint(v[c].w) & 0xffffe000u;
+          }
+          tmem_st32(ta, h);
+        }
+        if (p.passes == 3) {
+          uint32_t l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x4 = v[c];
+            l[4 * c] = __float_as_uint(x4.x - __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u));
+            l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u));
+            l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u));
+            l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u));
+          }
+          tmem_st32(ta + 32, l);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[aslot]);
+        ++cnt;
+      }
+    }
+  } else {
+    // =============================================================== epilogue (8 warps, two per TMEM lane quadrant)
+    // Step 1: TMEM -> smem (Y0|Y1|Y2 tiles, rows XOR-swizzled).  Step 2: out[r] = Y0[r-1] + Y1[r] + Y2[r+1] (+bias, stats, BN
+    // scale/shift, LeakyReLU, residual) with 8 lanes per 128-B position -> fully coalesced stores.
+    const int ew = warp - EPI_WARP0;                 // 0..7
+    const int quad = warp & 3;
+    const int half = ew >> 2;                        // which 16 of the 32 output channels this warp moves out of TMEM
+    const int m = quad * 32 + lane;
+    const int et = tid - EPI_WARP0 * 32;
+    const int chunk = et & 7, rg = et >> 3;          // rows rg + 32*j, 16-B chunk `chunk`
+    float* sY = reinterpret_cast<float*>(sOutB);
+    const snb_conv_epilogue& e = p.e;
+    const bool has_res = e.residual != nullptr, has_stats = e.stats != nullptr;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bias4;
+    if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
+    if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & (NACC3 - 1);
+      const uint32_t accphase = (it / NACC3) & 1;
+      const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
+      const int q0 = tt * p.step - 1;
+      int ww[4]; bool okr[4]; size_t goff[4];
+      {
+        const int q = q0 + rg;
+        int h = (q >= 0) ? q / p.W : -1, w = (q >= 0) ? q - h * p.W : p.W - 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rg + 32 * j, qq = q + 32 * j;
+          ww[j] = w;
+          okr[j] = r >= 1 && r < 127 && qq >= 0 && qq < HW;
+          goff[j] = ((size_t)slice * HW + (size_t)(qq < 0 ? 0 : qq)) * 32 + chunk * 4;
+          w += 32;
+          while (w >= p.W) { w -= p.W; ++h; }
+        }
+      }
+      float4 res[4];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (okr[j]) res[j] = __ldcg(reinterpret_cast<const float4*>(e.residual + goff[j]));
+        }
+      }
+      tc::mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_STRIDE + half * 16;
+      {
+        float v0[16], v1[16], v2[16];
+        tmem_ld16x3(taddr, taddr + 32, taddr + 64, v0, v1, v2);
+        float* row = sY + m * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int o = ((half * 4 + c) ^ (m & 7)) << 2;
+          *reinterpret_cast<float4*>(row + o) = make_float4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+          *reinterpret_cast<float4*>(row + 128 * 32 + o) = make_float4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+          *reinterpret_cast<float4*>(row + 2 * 128 * 32 + o) = make_float4(v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      epi_bar3();
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rg + 32 * j;
+        const int r0 = max(r - 1, 0), r2 = min(r + 1, 127);
+        float4 a = *reinterpret_cast<const float4*>(sY + r0 * 32 + ((chunk ^ (r0 & 7)) << 2));
+        const float4 bb = *reinterpret_cast<const float4*>(sY + 128 * 32 + r * 32 + ((chunk ^ (r & 7)) << 2));
+        float4 c = *reinterpret_cast<const float4*>(sY + 2 * 128 * 32 + r2 * 32 + ((chunk ^ (r2 & 7)) << 2));
+        // un-padded flat index: the kw = 0 / kw = 2 taps of the first / last column wrapped into the neighbouring image row
+        if (ww[j] == 0) a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ww[j] == p.W - 1) c = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = (a.x + bb.x) + c.x + bias4.x; o.y = (a.y + bb.y) + c.y + bias4.y;
+        o.z = (a.z + bb.z) + c.z + bias4.z; o.w = (a.w + bb.w) + c.w + bias4.w;
+        if (has_stats && okr[j]) {
+          s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+          s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+        }
+        if (e.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
+        if (e.lrelu) { o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w); }
+        if (has_res) { o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w; }
+        if (okr[j]) __stcg(reinterpret_cast<float4*>(p.y + goff[j]), o);
+      }
+      if (has_stats) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 8); s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 16);
+          s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], 8); s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { sRed[ew * 64 + lane * 4 + c] = s1[c]; sRed[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
+        }
+        epi_bar3();
+        if (et < 64) {
+          float a = 0.f;
+#pragma unroll
+          for (int wq = 0; wq < NUM_EPI_WARPS; ++wq) a += sRed[wq * 64 + et];
+          e.stats[(size_t)tile * 64 + et] = a;
+        }
+      }
+      epi_bar3();                                    // sY / sRed are rewritten by the next tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace tc3
+
+// ---- host side
+typedef CUresult (*snb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static snb_encode_tiled_fn snb_get_encode_tiled() {
+  static snb_encode_tiled_fn fn = []() -> snb_encode_tiled_fn {       // thread-safe one-time lookup of a driver entry point
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<snb_encode_tiled_fn>(p);
+  }();
+  return fn;
+}
+
+int snb_conv3d_tma_setup(const snb_conv_geom* g, tc3::Params3& p, const char* who) {
+  SNB_REQUIRE(g != nullptr, "%s: null geometry", who);
+  SNB_REQUIRE(g->transposed == 0 && g->stride == 1 && g->KD == 3 && g->KH == 3 && g->KW == 3 && g->dil == 1, "%s: needs a stride-1 3x3x3 conv", who);
+  SNB_REQUIRE(g->OD == g->D && g->OH == g->H && g->OW == g->W && g->ph == 1 && g->pw == 1 && g->pd == 1, "%s: needs 'same' padding", who);
+  p.B = g->B; p.D = g->D; p.H = g->H; p.W = g->W;
+  p.step = 126;
+  p.tiles_per_slice = snb_ceil_div((long long)g->H * g->W, p.step);
+  const long long nt = (long long)g->B * g->D * p.tiles_per_slice;
+  SNB_REQUIRE(nt < (1ll << 30), "%s: too many tiles", who);
+  p.ntiles = (int)nt;
+  return 0;
+}
+
+int snb_conv3d_tma_num_tiles(const snb_conv_geom* g) {
+  tc3::Params3 p;
+  if (snb_conv3d_tma_setup(g, p, "snb_conv_c32_tc_num_tiles")) return -1;
+  return p.ntiles;
+}
+
+int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                          int passes, void* stream) {
+  tc3::Params3 p;
+  if (int rc = snb_conv3d_tma_setup(g, p, "snb_conv_c32_tc")) return rc;
+  SNB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "snb_conv_c32_tc: x must be 16-byte aligned");
+  p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e;
+  snb_encode_tiled_fn enc = snb_get_encode_tiled();
+  SNB_REQUIRE(enc != nullptr, "snb_conv_c32_tc: cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap tmap;
+  const cuuint64_t HW = (cuuint64_t)g->H * g->W;
+  const cuuint64_t dims[4] = {32, HW, (cuuint64_t)g->D, (cuuint64_t)g->B};
+  const cuuint64_t strides[3] = {128, HW * 128, HW * 128 * (cuuint64_t)g->D};      // bytes, dims 1..3
+  const cuuint32_t box[4] = {32, 128, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv_c32_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  int dev = 0, sms = 148;
+  SNB_CUDA(cudaGetDevice(&dev));
+  SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
+  tc3::conv3d_c32_tma_kernel<<<grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, (cudaStream_t)stream>>>(tmap, p);
+  SNB_LAUNCH_CHECK("conv3d_c32_tma_kernel");
+  return 0;
+}

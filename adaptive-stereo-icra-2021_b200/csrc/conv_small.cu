@@ -58,11 +58,28 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
   const int oy0 = (trem / tiles_x) * TH, ox0 = (trem % tiles_x) * TW;
   const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
 
-  for (int i = t; i < CIN * T::IH * T::IW; i += 256) {
-    const int c = i % T::IW;
-    const int r = (i / T::IW) % T::IH;
-    const int ci = i / (T::IW * T::IH);
-    sIn[(ci * T::IH + r) * T::ROW + col_index<S, T::IWP>(c)] = ld(b, ci, iy0 + r, ix0 + c);
+  {  // input halo tile: U global loads in flight per thread before the dependent smem stores (a load->store chain per
+     // element exposed one full memory latency per iteration: 20 % of all stall samples in the ncu source view)
+    constexpr int NIN = CIN * T::IH * T::IW, U = 8;
+    for (int i0 = t; i0 < NIN; i0 += 256 * U) {
+      float vals[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        const int c = i % T::IW;
+        const int r = (i / T::IW) % T::IH;
+        const int ci = i / (T::IW * T::IH);
+        vals[u] = i < NIN ? ld(b, ci, iy0 + r, ix0 + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        const int c = i % T::IW;
+        const int r = (i / T::IW) % T::IH;
+        const int ci = i / (T::IW * T::IH);
+        if (i < NIN) sIn[(ci * T::IH + r) * T::ROW + col_index<S, T::IWP>(c)] = vals[u];
+      }
+    }
   }
   for (int i = t; i < T::W_FLOATS; i += 256) {   // w is [32][CIN][KS][KS]
     const int co = i / (CIN * KS * KS);
@@ -189,11 +206,27 @@ conv_small_wgrad_kernel(Loader ld, const float* __restrict__ dy, float* __restri
     }
     cp_async_commit();
   }
-  for (int i = t; i < CIN * T::IH * T::IW; i += 256) {
-    const int c = i % T::IW;
-    const int r = (i / T::IW) % T::IH;
-    const int ci = i / (T::IW * T::IH);
-    sIn[(ci * T::IH + r) * T::ROW + col_index<S, T::IWP>(c)] = ld(b, ci, iy0 + r, ix0 + c);
+  {  // input halo tile, U loads in flight per thread (see conv_small_kernel)
+    constexpr int NIN = CIN * T::IH * T::IW, U = 8;
+    for (int i0 = t; i0 < NIN; i0 += 256 * U) {
+      float vals[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        const int c = i % T::IW;
+        const int r = (i / T::IW) % T::IH;
+        const int ci = i / (T::IW * T::IH);
+        vals[u] = i < NIN ? ld(b, ci, iy0 + r, ix0 + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        const int c = i % T::IW;
+        const int r = (i / T::IW) % T::IH;
+        const int ci = i / (T::IW * T::IH);
+        if (i < NIN) sIn[(ci * T::IH + r) * T::ROW + col_index<S, T::IWP>(c)] = vals[u];
+      }
+    }
   }
   cp_async_wait<0>();
   __syncthreads();

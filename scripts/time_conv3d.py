@@ -9,7 +9,7 @@ dev = "cuda:0"
 torch.manual_seed(0)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 stream = torch.cuda.current_stream()
-for shape in [(1, 6, 9, 21, 32), (1, 24, 47, 156, 32), (2, 24, 47, 156, 32), (1, 24, 68, 120, 32)]:
+for shape in [(1, 3, 3, 8, 32), (1, 6, 9, 21, 32), (1, 24, 47, 156, 32), (2, 24, 47, 156, 32), (1, 24, 68, 120, 32)]:
   x = torch.randn(shape, device=dev)
   w = torch.randn(32, 32, 3, 3, 3, device=dev) * 0.05
   b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
@@ -19,7 +19,7 @@ for shape in [(1, 6, 9, 21, 32), (1, 24, 47, 156, 32), (2, 24, 47, 156, 32), (1,
   flops = 2 * 27 * 32 * 32 * x.numel() / 32
   for passes in (3, 1):
     for a_smem in (False, True):
-      y, st = ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, lrelu=True, passes=passes, a_smem=a_smem)
+      y, st = ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, lrelu=True, passes=passes, legacy3d=a_smem)
       err = (y - ref).abs().max().item() / ref.abs().max().item()
-      ms, med = time_kernel(lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, lrelu=True, passes=passes, a_smem=a_smem), 10, flush, stream)
-      print(f"{shape} passes{passes} {'smemA' if a_smem else 'tmemA'}: {ms*1e3:7.1f} us  {flops/ms/1e9:6.1f} TFLOP/s  rel err {err:.2e}", flush=True)
+      ms, med = time_kernel(lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, lrelu=True, passes=passes, legacy3d=a_smem), 10, flush, stream)
+      print(f"{shape} passes{passes} {'legacy' if a_smem else 'tma   '}: {ms*1e3:7.1f} us  {flops/ms/1e9:6.1f} TFLOP/s  rel err {err:.2e}", flush=True)
