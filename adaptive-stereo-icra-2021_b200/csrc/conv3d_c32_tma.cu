@@ -10,8 +10,11 @@
 //     per-MMA shared-memory fetch is the 3 KB B operand only (the smem-operand kernel is bound by its 7 KB A+B fetch);
 //   * windows of slices outside the volume (d' = -1, D) are skipped instead of multiplied as zeros.
 // Warps: 0 producer (TMA A + bulk B), 1 MMA issuer, 2-9 converters (two per TMEM lane quadrant, alternating windows),
-// 10-17 epilogue (two per quadrant).  smem: 4 x 16 KB raw A ring | 4 x 24 KB B ring (hi|lo) | 48 KB epilogue tiles.
-// TMEM: 2 accumulators x 96 | 4 A slots x 64 (a tile is 9 windows long, so two accumulators keep the epilogue off the critical path).
+// 10-17 epilogue (two per quadrant).  smem: 6 x 16 KB raw A ring | 3 x 24 KB B ring (hi|lo) | 48 KB epilogue tiles.
+// TMEM: 4 accumulators x 96 (two tiles in flight + two draining) | 2 A slots x 64.
+// A CTA works on SUPER-TILES of two consecutive tiles of one slice: every (kd,kh) weight image is fetched once per pair, which
+// halves the dominant L2->smem stream (24 KB of weights against 16 KB of activations per window) and doubles the MMA work
+// behind each in-flight weight stage (the single-tile version was bound by exactly that stream / its latency).
 #include <cuda.h>
 #include "tc_common.cuh"
 
@@ -19,20 +22,25 @@ namespace tc3 {
 
 using namespace tc;
 
-constexpr int NR = 4;                                    // ring depth (raw A and B)
+constexpr int NR = 6;                                    // raw A ring depth (TMA latency / NR bounds the window rate)
+constexpr int NB = 3;                                    // B ring depth (one weight image serves both tiles of a pair)
 constexpr int NTHREADS3 = 18 * 32;
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;                // 8 converter warps: two per quadrant, alternating windows
-constexpr int NACC3 = 2, NA = 4;                           // TMEM: 2 accumulators x 96 columns | 4 A slots x 64 columns
+constexpr int NACC3 = 4, NA = 2;                           // TMEM: 4 accumulators x 96 columns | 2 A slots x 64 columns
 constexpr int ACC_STRIDE = 96, TA_BASE = NACC3 * 96;
-constexpr int SMEM_BYTES3 = NR * A_BYTES + NR * 2 * B_BYTES + OUT_BYTES + 3072 /*barriers, stats scratch*/ + 1024 /*alignment slack*/;
+constexpr int SMEM_BYTES3 = NR * A_BYTES + NB * 2 * B_BYTES + OUT_BYTES + 3072 /*barriers, stats scratch*/ + 1024 /*alignment slack*/;
 
 struct Params3 {
   const float* wimg; float* y;
   int B, D, H, W;
   int tiles_per_slice, ntiles, step;       // step = 126 output positions per tile
+  int spt, nsuper;                         // super-tiles (pairs of tiles) per slice, in total
   int passes;
   snb_conv_epilogue e;
+  long long* dbg;                          // optional [grid][16] cycle counters (diagnostics), or NULL
 };
+
+#define T3WAIT(acc, call) do { const long long _t0 = p.dbg ? clock64() : 0; call; if (p.dbg) acc += clock64() - _t0; } while (0)
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -49,13 +57,13 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
   unsigned char* sBring = base + NR * A_BYTES;
-  unsigned char* sOutB = sBring + NR * 2 * B_BYTES;
+  unsigned char* sOutB = sBring + NB * 2 * B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOutB + OUT_BYTES);
   uint64_t* rfull = bars;                // [NR]   TMA (A window) -> converters
   uint64_t* rempty = rfull + NR;         // [NR]   converters -> producer
-  uint64_t* bfull = rempty + NR;         // [NR]   bulk copy (B window) -> MMA
-  uint64_t* bempty = bfull + NR;         // [NR]   MMA commit -> producer
-  uint64_t* afull = bempty + NR;         // [NA]    converters -> MMA (A slot in TMEM)
+  uint64_t* bfull = rempty + NR;         // [NB]   bulk copy (B window) -> MMA
+  uint64_t* bempty = bfull + NB;         // [NB]   MMA commit -> producer
+  uint64_t* afull = bempty + NB;         // [NA]    converters -> MMA (A slot in TMEM)
   uint64_t* aempty = afull + NA;         // [NA]    MMA commit -> converters
   uint64_t* tfull = aempty + NA;         // [NACC3] MMA commit -> epilogue
   uint64_t* tempty = tfull + NACC3;      // [NACC3] epilogue -> MMA
@@ -66,7 +74,8 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
 
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+      for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); }
+      for (int i = 0; i < NB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
       for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
       for (int i = 0; i < NACC3; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
       mbar_fence_init();
@@ -84,85 +93,107 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
   if (warp == 0) {
     // =============================================================== producer: one TMA tile load (A) + one bulk copy (B) per window
     if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
+      uint32_t ac = 0, bc = 0;
+      long long w_r = 0, w_b = 0; const long long t0 = clock64();
+      for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x) {
+        const int slice = st / p.spt, sst = st - slice * p.spt;
         const int b = slice / p.D, d = slice - b * p.D;
-        const int q0 = tt * p.step - 1;
+        const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
         for (int widx = 0; widx < 9; ++widx) {
           const int kd = widx / 3, kh = widx - kd * 3;
           const int dd = d + kd - 1;
           if ((unsigned)dd >= (unsigned)p.D) continue;
-          const uint32_t s = cnt % NR, ph = ((cnt / NR) & 1) ^ 1;
-          tc::mbar_wait(&rempty[s], ph);
-          mbar_expect_tx(&rfull[s], A_BYTES);
-          tma_load_4d(base + s * A_BYTES, &tmap, &rfull[s], 0, q0 + (kh - 1) * p.W, dd, b);
-          tc::mbar_wait(&bempty[s], ph);
-          mbar_expect_tx(&bfull[s], 2 * B_BYTES);
-          bulk_g2s(sBring + s * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[s]);
-          ++cnt;
+          const uint32_t sb = bc % NB;
+          T3WAIT(w_b, tc::mbar_wait(&bempty[sb], ((bc / NB) & 1) ^ 1));
+          mbar_expect_tx(&bfull[sb], 2 * B_BYTES);
+          bulk_g2s(sBring + sb * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[sb]);
+          ++bc;
+          for (int h = 0; h < nh; ++h) {
+            const uint32_t sa = ac % NR;
+            T3WAIT(w_r, tc::mbar_wait(&rempty[sa], ((ac / NR) & 1) ^ 1));
+            mbar_expect_tx(&rfull[sa], A_BYTES);
+            tma_load_4d(base + sa * A_BYTES, &tmap, &rfull[sa], 0, (2 * sst + h) * p.step - 1 + (kh - 1) * p.W, dd, b);
+            ++ac;
+          }
         }
       }
+      if (p.dbg) { long long* dd = p.dbg + blockIdx.x * 16; dd[0] = w_r; dd[1] = w_b; dd[2] = clock64() - t0; }
     }
     __syncwarp();
   } else if (warp == 1) {
     // =============================================================== MMA issuer (converged warp, elected lane)
-    uint32_t cnt = 0;
+    // warp-uniform copies (a shuffle from lane 0 tells nvcc the value is uniform: addresses then stay in uniform registers)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), smem_u = __shfl_sync(0xffffffffu, base_u32, 0);
+    uint32_t ac = 0, bc = 0, accpar = 0;         // accpar bit a = (number of earlier uses of accumulator a) & 1
+    long long w_a = 0, w_bf = 0, w_t = 0; const long long t0 = clock64();
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int slice = tile / p.tiles_per_slice;
+    for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x, ++it) {
+      const int slice = st / p.spt, sst = st - slice * p.spt;
       const int d = slice % p.D;
-      const int acc = it & (NACC3 - 1);
-      tc::mbar_wait_spin(&tempty[acc], (uint32_t)(((it / NACC3) & 1) ^ 1));
+      const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
+      const int acc0 = (it & 1) * 2;
+      for (int h = 0; h < nh; ++h) T3WAIT(w_t, mbar_wait_warp(&tempty[acc0 + h], ((accpar >> (acc0 + h)) & 1) ^ 1));
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
       bool first = true;
       for (int widx = 0; widx < 9; ++widx) {
         const int dd = d + widx / 3 - 1;
         if ((unsigned)dd >= (unsigned)p.D) continue;
-        const uint32_t s = cnt % NR, aslot = cnt % NA;
-        tc::mbar_wait_spin(&afull[aslot], (cnt / NA) & 1);
-        tc::mbar_wait_spin(&bfull[s], (cnt / NR) & 1);
-        tc_fence_after();
-        const uint32_t ta = tmem_base + TA_BASE + aslot * 64;
-        const uint32_t sb = base_u32 + NR * A_BYTES + s * 2 * B_BYTES;
+        const uint32_t sbi = bc % NB;
+        T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
+        const uint32_t sb = smem_u + NR * A_BYTES + sbi * 2 * B_BYTES;
+        for (int h = 0; h < nh; ++h) {
+          const uint32_t aslot = ac % NA;
+          T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
+          tc_fence_after();
+          const uint32_t ta = tmem_u + TA_BASE + aslot * 64;
+          const uint32_t tmem_d = tmem_u + (acc0 + h) * ACC_STRIDE;
+          if (elect_one()) {                     // one election per 12 MMAs + commit (see tc_common.cuh)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t bh = make_desc(sb + ks * 32);
-          mma_tf32_ts(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
-          if (p.passes == 3) {
-            mma_tf32_ts(tmem_d, ta + 32 + ks * 8, bh, 1);
-            mma_tf32_ts(tmem_d, ta + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bh = make_desc(sb + ks * 32);
+              mma_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
+              if (p.passes == 3) {
+                mma_tf32_ts_raw(tmem_d, ta + 32 + ks * 8, bh, 1);
+                mma_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
+              }
+            }
+            mma_commit_raw(&aempty[aslot]);
           }
+          __syncwarp();
+          ++ac;
         }
         first = false;
-        mma_commit(&aempty[aslot]);
-        mma_commit(&bempty[s]);
-        ++cnt;
+        mma_commit(&bempty[sbi]);
+        ++bc;
       }
-      mma_commit(&tfull[acc]);
+      for (int h = 0; h < nh; ++h) { mma_commit(&tfull[acc0 + h]); accpar ^= 1u << (acc0 + h); }
     }
+    if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[3] = w_a; dd[4] = w_bf; dd[5] = w_t; dd[6] = clock64() - t0; }
   } else if (warp < EPI_WARP0) {
     // =============================================================== converters (TMEM lane quadrant = warp % 4, thread = position)
     const int quad = warp & 3;
     const uint32_t mine = (uint32_t)(warp - CONV_WARP0) >> 2;      // this warp converts the windows with cnt % 2 == mine
     const int m = quad * 32 + lane;
-    uint32_t cnt = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const int d = (tile / p.tiles_per_slice) % p.D;
-      for (int widx = 0; widx < 9; ++widx) {
+    uint32_t cnt = 0;                                              // A items: (window, tile of the pair)
+    long long w_rf = 0, w_ae = 0, w_st = 0; const long long t0 = clock64();
+    for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x) {
+      const int slice = st / p.spt, sst = st - slice * p.spt;
+      const int d = slice % p.D;
+      const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
+      for (int item = 0; item < 9 * nh; ++item) {
+        const int widx = item / nh;
         const int dd = d + widx / 3 - 1;
         if ((unsigned)dd >= (unsigned)p.D) continue;
         if ((cnt & 1) != mine) { ++cnt; continue; }
         const uint32_t s = cnt % NR, aslot = cnt % NA;
-        tc::mbar_wait(&rfull[s], (cnt / NR) & 1);
-        const unsigned char* st = base + s * A_BYTES + m * 128;
+        T3WAIT(w_rf, tc::mbar_wait(&rfull[s], (cnt / NR) & 1));
+        const unsigned char* rowp = base + s * A_BYTES + m * 128;
         float4 v[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(st + ((c ^ (m & 7)) << 4));
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (m & 7)) << 4));
         __syncwarp();
         if (lane == 0) mbar_arrive(&rempty[s]);            // raw window consumed (values are in registers)
-        tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1);
+        T3WAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * 64;
         {
@@ -186,13 +217,14 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
           }
           tmem_st32(ta + 32, l);
         }
-        tmem_wait_st();
+        T3WAIT(w_st, tmem_wait_st());
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&afull[aslot]);
         ++cnt;
       }
     }
+    if (p.dbg && warp == CONV_WARP0 && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[7] = w_rf; dd[8] = w_ae; dd[9] = w_st; dd[10] = clock64() - t0; }
   } else {
     // =============================================================== epilogue (8 warps, two per TMEM lane quadrant)
     // Step 1: TMEM -> smem (Y0|Y1|Y2 tiles, rows XOR-swizzled).  Step 2: out[r] = Y0[r-1] + Y1[r] + Y2[r+1] (+bias, stats, BN
@@ -210,10 +242,17 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int acc = it & (NACC3 - 1);
-      const uint32_t accphase = (it / NACC3) & 1;
-      const int slice = tile / p.tiles_per_slice, tt = tile - slice * p.tiles_per_slice;
+    long long w_tf = 0; const long long t0 = clock64();
+    uint32_t accpar = 0;                             // same bookkeeping as the MMA warp (a single-tile pair skips one accumulator)
+    for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x, ++it) {
+     const int slice = st / p.spt, sst = st - slice * p.spt;
+     const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
+     for (int hh2 = 0; hh2 < nh; ++hh2) {
+      const int acc = (it & 1) * 2 + hh2;
+      const uint32_t accphase = (accpar >> acc) & 1;
+      accpar ^= 1u << acc;
+      const int tt = 2 * sst + hh2;
+      const int tile = slice * p.tiles_per_slice + tt;
       const int q0 = tt * p.step - 1;
       int ww[4]; bool okr[4]; size_t goff[4];
       {
@@ -237,7 +276,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
           if (okr[j]) res[j] = __ldcg(reinterpret_cast<const float4*>(e.residual + goff[j]));
         }
       }
-      tc::mbar_wait(&tfull[acc], accphase);
+      T3WAIT(w_tf, tc::mbar_wait(&tfull[acc], accphase));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_STRIDE + half * 16;
       {
@@ -298,7 +337,9 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         }
       }
       epi_bar3();                                    // sY / sRed are rewritten by the next tile
+     }
     }
+    if (p.dbg && et == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[11] = w_tf; dd[12] = clock64() - t0; }
   }
 
   tc_fence_before();
@@ -336,6 +377,8 @@ int snb_conv3d_tma_setup(const snb_conv_geom* g, tc3::Params3& p, const char* wh
   const long long nt = (long long)g->B * g->D * p.tiles_per_slice;
   SNB_REQUIRE(nt < (1ll << 30), "%s: too many tiles", who);
   p.ntiles = (int)nt;
+  p.spt = (p.tiles_per_slice + 1) / 2;
+  p.nsuper = g->B * g->D * p.spt;
   return 0;
 }
 
@@ -346,11 +389,11 @@ int snb_conv3d_tma_num_tiles(const snb_conv_geom* g) {
 }
 
 int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
-                          int passes, void* stream) {
+                          int passes, long long* dbg, void* stream) {
   tc3::Params3 p;
   if (int rc = snb_conv3d_tma_setup(g, p, "snb_conv_c32_tc")) return rc;
   SNB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "snb_conv_c32_tc: x must be 16-byte aligned");
-  p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e;
+  p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e; p.dbg = dbg;
   snb_encode_tiled_fn enc = snb_get_encode_tiled();
   SNB_REQUIRE(enc != nullptr, "snb_conv_c32_tc: cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap tmap;
@@ -366,7 +409,7 @@ int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  const int grid = p.nsuper < sms ? p.nsuper : sms;
   SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
   tc3::conv3d_c32_tma_kernel<<<grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, (cudaStream_t)stream>>>(tmap, p);
   SNB_LAUNCH_CHECK("conv3d_c32_tma_kernel");

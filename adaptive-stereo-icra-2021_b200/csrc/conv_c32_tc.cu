@@ -467,7 +467,7 @@ static int tc_setup(const snb_conv_geom* g, tc::Params& p, const char* who) {
 // 3-D default path: TMA producer + A operand in TMEM (conv3d_c32_tma.cu)
 int snb_conv3d_tma_num_tiles(const snb_conv_geom* g);
 int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
-                          int passes, void* stream);
+                          int passes, long long* dbg, void* stream);
 
 extern "C" int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g) {
   if (g && g->KD == 3) return snb_conv3d_tma_num_tiles(g);
@@ -505,10 +505,10 @@ static int conv_c32_tc_launch(const float* x, const float* wimg, float* y, const
   tc::Params p;
   if (int rc = tc_setup(g, p, "snb_conv_c32_tc")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv_c32_tc: null pointer");
-  if (g->KD == 3 && (passes & 0x400) == 0 && dbg == nullptr) {        // 3-D product path
+  if (g->KD == 3 && (passes & 0x400) == 0) {                            // 3-D product path (dbg: per-role wait counters)
     SNB_REQUIRE((passes & 0xff) == 1 || (passes & 0xff) == 3, "snb_conv_c32_tc: passes must be 1 or 3");
     SNB_REQUIRE(!e->scale || e->shift, "snb_conv_c32_tc: scale without shift");
-    return snb_conv3d_tma_launch(x, wimg, y, g, e, passes & 0xff, stream);
+    return snb_conv3d_tma_launch(x, wimg, y, g, e, passes & 0xff, dbg, stream);
   }
   SNB_REQUIRE(g->KD != 3 || e->stats == nullptr, "snb_conv_c32_tc: the legacy 3-D kernels (diagnostics) do not emit BN statistics");
   // The flat-tiled kernel loads 9 windows per tile; with the A operand in TMEM only 3 warps are left to load them and the

@@ -131,6 +131,39 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// Un-predicated variants for use INSIDE one `if (elect_one()) { ... }` block that issues a whole batch of MMAs + commits: one
+// ELECT / divergence check per batch instead of one per instruction.
+__device__ __forceinline__ void mma_tf32_ts_raw(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_raw(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_raw(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-uniform wait for the CONVERGED MMA-issuing warp: every lane polls and the loop exits on a warp vote, so the loop
+// is provably non-divergent and nvcc keeps the loop-carried state (stage counters, smem/TMEM addresses, descriptors) in
+// the uniform datapath — with a per-lane exit condition they live in vector registers and every tcgen05.mma pays
+// R2UR / VOTEU / ELECT round trips (~13 SASS instructions, ~80 cycles per MMA on the issuing warp, measured).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  const long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
 // three 16-column TMEM loads in flight, one wait
 __device__ __forceinline__ void tmem_ld16x3(uint32_t t0, uint32_t t1, uint32_t t2, float (&a)[16], float (&b)[16], float (&c)[16]) {
   uint32_t r[48];
