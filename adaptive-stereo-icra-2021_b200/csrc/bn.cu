@@ -12,9 +12,14 @@ bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, co
                    float* scale, float* shift, float* mean_out, float* invstd_out) {
   __shared__ double red[16][64];
   const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
-  double a = 0.0;
-  for (int i = part; i < ntiles; i += 16) a += (double)stats[(size_t)i * 64 + c];
-  red[part][c] = a;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;          // 4 independent chains: the loop is bound by the fp64 add latency
+  int i = part;
+  for (; i + 48 < ntiles; i += 64) {
+    a0 += (double)stats[(size_t)i * 64 + c];        a1 += (double)stats[(size_t)(i + 16) * 64 + c];
+    a2 += (double)stats[(size_t)(i + 32) * 64 + c]; a3 += (double)stats[(size_t)(i + 48) * 64 + c];
+  }
+  for (; i < ntiles; i += 16) a0 += (double)stats[(size_t)i * 64 + c];
+  red[part][c] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (threadIdx.x < 32) {
     double s1 = 0.0, s2 = 0.0;
