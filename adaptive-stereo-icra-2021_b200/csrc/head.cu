@@ -179,7 +179,33 @@ upsample_bilinear_bwd_kernel(const float* __restrict__ dout, float* __restrict__
   din[((size_t)b * h + i) * w + j] = mul * acc;
 }
 
+// Feature-contrast score (adaptive_stereo/utils/feature_contrast.py:12-23):
+//   fcs[b,y,x] = max_d cost - mean of all but the two largest costs  ( = sorted_desc[0] - mean(sorted_desc[2:]) )
+// One pass over D with a running top-2 and sum instead of a torch.sort over [B,D,H,W].
+__global__ void __launch_bounds__(256)
+feature_contrast_kernel(const float* __restrict__ cost, float* __restrict__ out, int D, long long plane, long long total) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / plane, q = i - b * plane;
+  const float* c = cost + b * D * plane + q;
+  float m1 = -INFINITY, m2 = -INFINITY, s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float v = c[(size_t)d * plane];
+    s += v;
+    if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+  }
+  out[i] = m1 - (s - m1 - m2) / (float)(D - 2);
+}
+
 }  // namespace
+
+extern "C" int snb_feature_contrast(const float* cost, float* out, int B, int D, int H, int W, void* stream) {
+  SNB_REQUIRE(cost && out && B > 0 && D > 2 && H > 0 && W > 0, "snb_feature_contrast: bad args (needs D > 2)");
+  const long long plane = (long long)H * W, total = plane * B;
+  feature_contrast_kernel<<<snb_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(cost, out, D, plane, total);
+  SNB_LAUNCH_CHECK("feature_contrast_kernel");
+  return 0;
+}
 
 extern "C" int snb_conv_c32_taps(const float* x, const float* w, float* taps, long long nslices, int plane, int ntaps, void* stream) {
   SNB_REQUIRE(x && w && taps && nslices > 0 && plane > 0, "snb_conv_c32_taps: bad args");

@@ -62,6 +62,9 @@ SIGNATURES = {
   "snb_refine_in_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_softargmin_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
   "snb_relu_bwd": (_I, [_P, _P, _P, _LL, _P]),
+  "snb_feature_contrast": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+  "snb_photo_loss": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+  "snb_photo_loss_workspace_floats": (_I, [_I, _I, _I]),
   "snb_conv_c32_taps_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -4,7 +4,8 @@ parameters only, Adam step.  The state machine / OVS / logging of adapt.py stay 
 import torch
 import torch.nn as nn
 
-from .losses import LinearWarping, feature_contrast_mean, khamis_robust_loss, monodepth_single_loss
+from .losses import (LinearWarping, feature_contrast_mean, khamis_robust_loss, monodepth_single_loss,
+                     monodepth_single_loss_fused)
 
 
 def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
@@ -20,12 +21,13 @@ class AdaptStepper:
   execution is bound by host launch latency.  Requires an optimizer built with capturable=True and no replay term."""
 
   def __init__(self, feature_net, stereo_net, optimizer, height, width, clip_grad_norm=True, er_loss_weight=0.05,
-               use_graph=False):
+               use_graph=False, fused_loss=False):
     self.feature_net, self.stereo_net, self.optimizer = feature_net, stereo_net, optimizer
     self.clip, self.er_loss_weight = clip_grad_norm, er_loss_weight
     dev = next(stereo_net.parameters()).device
     self.warper = LinearWarping(height, width, dev)
     self.use_graph = use_graph
+    self.fused_loss = fused_loss            # photometric loss + its gradient from snb_photo_loss instead of ~150 torch kernels
     self._graphs = {}
     self.launches_per_step = None
     if use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
@@ -56,7 +58,10 @@ class AdaptStepper:
     s = self.stereo_net.input_scale
     self.feature_net.train(); self.stereo_net.train()
     outputs = self.predict(left, right)
-    loss = monodepth_single_loss(left, right, outputs, self.warper, s, static_shapes=static_shapes)
+    if self.fused_loss:
+      loss = monodepth_single_loss_fused(left, right, outputs, s)
+    else:
+      loss = monodepth_single_loss(left, right, outputs, self.warper, s, static_shapes=static_shapes)
     if replay is not None:
       out_er = self.predict(replay[0], replay[1])
       loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])

@@ -73,6 +73,28 @@ def monodepth_single_loss(left_img, right_img, outputs, warper, scale, static_sh
   return loss[mask].mean()
 
 
+class _FusedPhotoLoss(torch.autograd.Function):
+  """snb_photo_loss: value and d loss / d disp from one fused pass."""
+
+  @staticmethod
+  def forward(ctx, disp, left, right, smooth_w):
+    from . import ops
+    loss, ddisp = ops.photo_loss(left.contiguous(), right.contiguous(), disp.contiguous(), smooth_w)
+    ctx.save_for_backward(ddisp)
+    return loss[0]
+
+  @staticmethod
+  def backward(ctx, gout):
+    (ddisp,) = ctx.saved_tensors
+    return ddisp * gout, None, None, None
+
+
+def monodepth_single_loss_fused(left_img, right_img, outputs, scale):
+  """Same value and gradient as monodepth_single_loss, computed by the library's fused CUDA kernels."""
+  pred = outputs["pred_disp_l/{}".format(scale)]
+  return _FusedPhotoLoss.apply(pred.squeeze(1), left_img, right_img, 1e-3)
+
+
 def khamis_robust_loss(pred_disp, gt_disp):
   mask = (gt_disp > 0).detach()
   num_valid = max(mask.sum(), 1)
@@ -80,6 +102,12 @@ def khamis_robust_loss(pred_disp, gt_disp):
 
 
 def feature_contrast_mean(cost_volume):
+  """feature_contrast.py:12-23.  CUDA tensors use the library's single-pass kernel (no sort); the torch expression below is
+  the reference formulation (kept for CPU tensors in tests)."""
+  if cost_volume.is_cuda:
+    from . import ops
+    with torch.no_grad():
+      return ops.feature_contrast(cost_volume.detach().contiguous())
   with torch.no_grad():
     s = torch.sort(cost_volume, dim=1, descending=True)[0]
     return s[:, 0] - s[:, 2:].mean(dim=1)

@@ -406,3 +406,29 @@ def conv_c32_taps_bwd(x, w, g, ntaps):
   red = reduce_partials(part)
   dw = red[:ntaps * 32].view(ntaps, 32).t().reshape(w.shape).contiguous()
   return dx, dw, red[ntaps * 32:].clone()
+
+
+def photo_loss(left, right, disp, smooth_w=1e-3):
+  """Fused Monodepth photometric loss (adapt.py:78-86): returns (loss [1], dloss/ddisp [B,H,W])."""
+  _req(left, "left_img", 4); _req(right, "right_img", 4); _req(disp, "disp", 3)
+  B, Cc, H, W = left.shape
+  if Cc != 3 or right.shape != left.shape or tuple(disp.shape) != (B, H, W):
+    raise RuntimeError(f"stereonet_b200: photo_loss expects [B,3,H,W] images and a [B,H,W] disparity, got "
+                       f"{tuple(left.shape)} {tuple(right.shape)} {tuple(disp.shape)}")
+  loss = torch.empty((1,), device=left.device, dtype=torch.float32)
+  ddisp = torch.empty((B, H, W), device=left.device, dtype=torch.float32)
+  ws = torch.empty((_cabi.lib().snb_photo_loss_workspace_floats(B, H, W),), device=left.device, dtype=torch.float32)
+  check(_cabi.lib().snb_photo_loss(_p(left), _p(right), _p(disp), _p(loss), _p(ddisp), _p(ws), B, H, W, float(smooth_w),
+                                   _stream(left)), "snb_photo_loss")
+  _count(3)
+  return loss, ddisp
+
+
+def feature_contrast(cost):
+  """Feature-contrast score map [B,H,W] of a cost volume [B,D,H,W] (feature_contrast.py:12-23)."""
+  _req(cost, "cost_volume", 4)
+  B, D, H, W = cost.shape
+  out = torch.empty((B, H, W), device=cost.device, dtype=torch.float32)
+  check(_cabi.lib().snb_feature_contrast(_p(cost), _p(out), B, D, H, W, _stream(cost)), "snb_feature_contrast")
+  _count()
+  return out

@@ -203,6 +203,19 @@ SNB_API int snb_relu_bwd(const float* out, const float* dout, float* dres, long 
 SNB_API int snb_conv_c32_taps_bwd(const float* x, const float* w, const float* g, float* dx, float* partial,
                           int B, int D, int H, int W, int ntaps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * fused photometric loss of the adaptation step (adapt.py:78-86; LinearWarping
+ * linear_warping.py:18-57; SSIM / L1 / edge-aware smoothness loss_functions.py:41-138), forward value AND gradient
+ * w.r.t. the predicted disparity in three launches.  left/right [B,3,H,W] NCHW, disp [B,H,W] (full resolution),
+ * loss_out [1], ddisp [B,H,W] = d loss / d disp, workspace of snb_photo_loss_workspace_floats(B,H,W) floats.
+ * smooth_w = 1e-3 in adapt.py:81-83. */
+SNB_API int snb_photo_loss(const float* left, const float* right, const float* disp, float* loss_out, float* ddisp,
+                   float* workspace, int B, int H, int W, float smooth_w, void* stream);
+SNB_API int snb_photo_loss_workspace_floats(int B, int H, int W);
+/* Row f2: feature-contrast score of a cost volume [B,D,H,W] -> [B,H,W] (feature_contrast.py:12-23, adapt.py:352-353):
+ * max_d cost - mean of all but the two largest costs, without sorting. */
+SNB_API int snb_feature_contrast(const float* cost, float* out, int B, int D, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

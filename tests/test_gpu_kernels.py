@@ -184,3 +184,13 @@ def test_bn_train_pieces():
   close(bn_gpu.running_var.cpu(), bn.running_var, 1e-6, "running_var")
   close(mean.cpu(), z.mean((0, 2, 3)), 1e-5, "batch mean")
   assert int(bn_gpu.num_batches_tracked) == 1
+
+
+def test_feature_contrast_matches_sort():
+  """snb_feature_contrast vs the reference formulation sorted_desc[0] - mean(sorted_desc[2:])."""
+  cost = rnd(2, 24, 13, 37, seed=3) * 5
+  cost[0, 3, 2, 5] = cost[0, 7, 2, 5] = cost[0].max() + 1.0        # a tie for the maximum
+  s = torch.sort(cost, dim=1, descending=True)[0]
+  ref = s[:, 0] - s[:, 2:].mean(dim=1)
+  got = ops.feature_contrast(cost.to(DEV)).cpu()
+  close(got, ref, 1e-5, "feature contrast")
