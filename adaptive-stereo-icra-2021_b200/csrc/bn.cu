@@ -42,6 +42,21 @@ bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, co
   }
 }
 
+// Stage 1 of the two-stage statistics reduction: block b sums rows [b*chunk, (b+1)*chunk) of stats [ntiles][64] into
+// scratch[b][64] (fp64 accumulation, fixed order).  A single CTA walking ~1 MB of partials (one row per image row x column
+// block at full resolution) is bound by one SM's load bandwidth: 12-23 us per layer, 23 layers per adaptation step.
+__global__ void __launch_bounds__(256)
+bn_stats_prereduce_kernel(const float* __restrict__ stats, int ntiles, int chunk, float* __restrict__ scratch) {
+  __shared__ double red[4][64];
+  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int lo = blockIdx.x * chunk, hi = min(lo + chunk, ntiles);
+  double a = 0.0;
+  for (int i = lo + part; i < hi; i += 4) a += (double)stats[(size_t)i * 64 + c];
+  red[part][c] = a;
+  __syncthreads();
+  if (part == 0) scratch[(size_t)blockIdx.x * 64 + c] = (float)((red[0][c] + red[1][c]) + (red[2][c] + red[3][c]));
+}
+
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                 const float4* __restrict__ residual, float4* __restrict__ y, long long n4, int do_lrelu) {
@@ -72,6 +87,19 @@ extern "C" int snb_bn_finalize(const float* stats, int ntiles, long long count, 
                                                            momentum, eps, scale, shift, mean, invstd);
   SNB_LAUNCH_CHECK("bn_finalize_kernel");
   return 0;
+}
+
+extern "C" int snb_bn_finalize_ws(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps,
+                                  float* scale, float* shift, float* mean, float* invstd, float* scratch, void* stream) {
+  SNB_REQUIRE(scratch != nullptr, "snb_bn_finalize_ws: null scratch");
+  if (ntiles <= 256)
+    return snb_bn_finalize(stats, ntiles, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, stream);
+  SNB_REQUIRE(stats && gamma && beta && scale && shift && count > 0, "snb_bn_finalize_ws: bad args");
+  const int nblk = 64, chunk = (ntiles + nblk - 1) / nblk;
+  bn_stats_prereduce_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(stats, ntiles, chunk, scratch);
+  SNB_LAUNCH_CHECK("bn_stats_prereduce_kernel");
+  return snb_bn_finalize(scratch, nblk, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, stream);
 }
 
 extern "C" int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,

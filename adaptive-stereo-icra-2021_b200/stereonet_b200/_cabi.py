@@ -46,6 +46,7 @@ SIGNATURES = {
   "snb_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_upsample_bilinear_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_bn_finalize": (_I, [_P, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+  "snb_bn_finalize_ws": (_I, [_P, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
   "snb_bn_apply": (_I, [_P, _P, _P, _P, _P, _LL, _I, _P]),
   "snb_bwd_num_blocks": (_I, [_LL]),
   "snb_bn_lrelu_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P]),

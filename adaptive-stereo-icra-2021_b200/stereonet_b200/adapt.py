@@ -11,8 +11,10 @@ from .losses import (LinearWarping, feature_contrast_mean, khamis_robust_loss, m
 def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
   """adapt.py:208-210: two parameter groups, stereo_net first.  capturable=True keeps Adam's step counters on the device
   (needed by AdaptStepper(use_graph=True))."""
+  # capturable: step counters live on the device; fused: one multi-tensor kernel per group instead of ~220 tiny
+  # per-parameter bias-correction kernels (same update rule, torch.optim.Adam defaults)
   return torch.optim.Adam([{"params": stereo_net.parameters()}, {"params": feature_net.parameters()}], lr=lr,
-                          capturable=capturable)
+                          capturable=capturable, fused=True if capturable else None)
 
 
 class AdaptStepper:

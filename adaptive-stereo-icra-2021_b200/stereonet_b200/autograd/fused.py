@@ -17,6 +17,20 @@ def bump_epoch():
   EPOCH += 1
 
 
+# Fused optimizers (torch.optim.Adam(fused=True), torch._fused_adam_) update parameters in place WITHOUT bumping their
+# version counters, so every optimizer step also advances the epoch (global post-step hook; costs one integer add).
+def _after_optimizer_step(optimizer, args, kwargs):
+  bump_epoch()
+
+
+try:
+  from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook
+  _register_step_hook(_after_optimizer_step)
+except Exception as exc:  # pragma: no cover
+  raise RuntimeError("stereonet_b200 needs torch.optim.optimizer.register_optimizer_step_post_hook "
+                     "(PyTorch >= 2.1) to keep its derived-weight caches coherent") from exc
+
+
 def _cached(owner, key, tensors, make):
   cache = owner.__dict__.setdefault("_snb_cache", {})
   ver = (EPOCH,) + tuple((t.data_ptr(), t._version) for t in tensors)

@@ -269,10 +269,11 @@ def bn_finalize(stats, count, bn, update_running=True):
   out = torch.empty((4, 32), device=dev, dtype=torch.float32)
   rm = bn.running_mean if update_running else None
   rv = bn.running_var if update_running else None
-  check(_cabi.lib().snb_bn_finalize(_p(stats), stats.shape[0], int(count), _p(bn.weight.detach()), _p(bn.bias.detach()),
-                                    _p(rm), _p(rv), BN_MOMENTUM, BN_EPS, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
-                                    _stream(stats)), "snb_bn_finalize")
-  _count()
+  scratch = torch.empty((64, 64), device=dev, dtype=torch.float32)
+  check(_cabi.lib().snb_bn_finalize_ws(_p(stats), stats.shape[0], int(count), _p(bn.weight.detach()), _p(bn.bias.detach()),
+                                       _p(rm), _p(rv), BN_MOMENTUM, BN_EPS, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                       _p(scratch), _stream(stats)), "snb_bn_finalize_ws")
+  _count(2 if stats.shape[0] > 256 else 1)
   if update_running and bn.num_batches_tracked is not None:
     bn.num_batches_tracked += 1
   return out[0], out[1], out[2], out[3]

@@ -66,7 +66,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                    "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
     except Exception:
@@ -236,7 +236,6 @@ def gpu_arm(args):
   ev7.record(stream)
   barrier()
   ms_e2e_seq = ev6.elapsed_time(ev7)
-  clocks = sampler.stop() if rank == 0 else None
 
   # ---- online-adaptation step (BASELINE.json configs[2]/[4]): train-mode fwd + photometric loss + bwd + clip + Adam.
   # N > 1: shared-model data parallel, one stream per rank, ONE flat-bucket NCCL all-reduce of the used gradients.
@@ -265,6 +264,7 @@ def gpu_arm(args):
     adapt_launches = stepper.launches_per_step if stepper.launches_per_step else (ops.LAUNCHES - n0) // adapt_steps
     fnet.eval(); snet.eval()
 
+  clocks = sampler.stop() if rank == 0 else None          # sampled across all three timed regions (device, e2e, adapt)
   t = torch.tensor([ms_dev, ms_e2e, ms_adapt], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)              # max over ranks

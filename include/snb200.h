@@ -152,6 +152,11 @@ SNB_API int snb_upsample_bilinear_bwd(const float* dout, float* din, int B, int 
 SNB_API int snb_bn_finalize(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps,
                     float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* Same, with a caller-provided scratch of 64 x 64 floats: more than 256 partial rows are first reduced by 64 CTAs (a single
+ * CTA walking ~1 MB of partials is bound by one SM's load bandwidth). */
+SNB_API int snb_bn_finalize_ws(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps,
+                       float* scale, float* shift, float* mean, float* invstd, float* scratch, void* stream);
 /* y = [residual +] LeakyReLU(z*scale + shift) over n positions x 32 channels. */
 SNB_API int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,
                  long long npos, int lrelu, void* stream);

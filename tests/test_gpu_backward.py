@@ -164,8 +164,9 @@ def test_refinement_backward(training):
     close(prm.grad.cpu(), sd[p + n].grad, 2e-2 if training else 5e-3, n)
 
 
+@pytest.mark.parametrize("fused_loss", [False, True])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["train"]])
-def test_adapt_step_vs_reference_golden(name):
+def test_adapt_step_vs_reference_golden(name, fused_loss):
   """One full adaptation step (adapt.py:313-337,381-394) on the GPU vs the reference's own step (golden vectors).
 
   Tolerances: the reference gradient itself is ill-conditioned at this size — perturbing the input images by 1e-7
@@ -174,7 +175,7 @@ def test_adapt_step_vs_reference_golden(name):
   BN; measured with the oracle on the CPU).  The bounds below sit just outside that band; the
   layer-level tests in this file, which use exactly representable data, pin every backward kernel to 2e-5."""
   from stereonet_b200.adapt import AdaptStepper, make_optimizer
-  from stereonet_b200.losses import monodepth_single_loss
+  from stereonet_b200.losses import monodepth_single_loss, monodepth_single_loss_fused
   cfg = CASES[name]
   g = np.load(os.path.join(GOLD, name + ".npz"))
   fsd, _, left, right, _ = build(cfg)
@@ -186,7 +187,10 @@ def test_adapt_step_vs_reference_golden(name):
   f.train(); s.train()
   l, r = left.to(DEV), right.to(DEV)
   outputs = stepper.predict(l, r)
-  loss = monodepth_single_loss(l, r, outputs, stepper.warper, cfg["s"])
+  if fused_loss:     # snb_photo_loss (row f1) against the reference's own loss value and gradients
+    loss = monodepth_single_loss_fused(l, r, outputs, cfg["s"])
+  else:
+    loss = monodepth_single_loss(l, r, outputs, stepper.warper, cfg["s"])
   opt.zero_grad()
   loss.backward()
   print(f"[parity] {name} loss {loss.item():.7f} vs reference {float(g['train/loss']):.7f}")

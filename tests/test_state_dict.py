@@ -58,3 +58,21 @@ def test_cpu_tensors_fail_loudly():
   f = S.FeatureExtractorNetwork(3)
   with pytest.raises(RuntimeError, match="no CPU path"):
     f(torch.zeros(1, 3, 64, 64))
+
+
+def test_optimizer_step_invalidates_derived_weight_caches():
+  """Fused optimizers update parameters without bumping tensor version counters; the derived-weight caches must still be
+  invalidated (global optimizer post-step hook -> cache epoch)."""
+  import torch
+  from stereonet_b200.autograd import fused
+  p = torch.nn.Parameter(torch.randn(4, 4))
+  p.grad = torch.randn(4, 4)
+  opt = torch.optim.Adam([p], lr=1e-3, fused=True)
+  calls = []
+  owner = torch.nn.Module()
+  fused._cached(owner, "k", [p], lambda: calls.append(1) or len(calls))
+  fused._cached(owner, "k", [p], lambda: calls.append(1) or len(calls))
+  assert len(calls) == 1
+  opt.step()
+  fused._cached(owner, "k", [p], lambda: calls.append(1) or len(calls))
+  assert len(calls) == 2
