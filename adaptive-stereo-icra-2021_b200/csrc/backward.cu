@@ -228,26 +228,30 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
         cp_async_wait<0>();
       }
       __syncthreads();
-      float acc[4][8];
+      unsigned long long pacc[4][4];           // 4 ci x 8 co as packed pairs (FFMA2)
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) pacc[i][j] = 0ull;
 #pragma unroll 4
       for (int pp = 0; pp < 16; ++pp) {
         const int r = grp * 16 + pp;
         const float4 xv = *reinterpret_cast<const float4*>(&s.x[buf][r][(cig ^ (r & 7)) * 4]);
-        const float4 d0 = *reinterpret_cast<const float4*>(&s.dz[r][((cog * 2) ^ (r & 7)) * 4]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&s.dz[r][((cog * 2 + 1) ^ (r & 7)) * 4]);
+        const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(&s.dz[r][((cog * 2) ^ (r & 7)) * 4]);
+        const ulonglong2 d1 = *reinterpret_cast<const ulonglong2*>(&s.dz[r][((cog * 2 + 1) ^ (r & 7)) * 4]);
         const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          acc[i][0] = fmaf(xx[i], d0.x, acc[i][0]); acc[i][1] = fmaf(xx[i], d0.y, acc[i][1]);
-          acc[i][2] = fmaf(xx[i], d0.z, acc[i][2]); acc[i][3] = fmaf(xx[i], d0.w, acc[i][3]);
-          acc[i][4] = fmaf(xx[i], d1.x, acc[i][4]); acc[i][5] = fmaf(xx[i], d1.y, acc[i][5]);
-          acc[i][6] = fmaf(xx[i], d1.z, acc[i][6]); acc[i][7] = fmaf(xx[i], d1.w, acc[i][7]);
+          const unsigned long long xp = pack2(xx[i], xx[i]);
+          ffma2(pacc[i][0], xp, d0.x); ffma2(pacc[i][1], xp, d0.y);
+          ffma2(pacc[i][2], xp, d1.x); ffma2(pacc[i][3], xp, d1.y);
         }
       }
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][2 * j] = lo2(pacc[i][j]); acc[i][2 * j + 1] = hi2(pacc[i][j]); }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -349,19 +353,22 @@ conv_c32_taps_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   cp_async_wait<0>();
   __syncthreads();
   if (u < npos) {       // dx row of this position
-    float acc[32];
+    unsigned long long pacc[16];             // 32 channels as packed pairs (FFMA2)
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int c = 0; c < 16; ++c) pacc[c] = 0ull;
 #pragma unroll 3
     for (int tap = 0; tap < NT; ++tap) {
       const float gv = sG[t][tap];
+      const unsigned long long gp = pack2(gv, gv);
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 wv = *reinterpret_cast<const float4*>(&sW[tap][c4 * 4]);
-        acc[c4 * 4 + 0] = fmaf(gv, wv.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(gv, wv.y, acc[c4 * 4 + 1]);
-        acc[c4 * 4 + 2] = fmaf(gv, wv.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(gv, wv.w, acc[c4 * 4 + 3]);
+        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(&sW[tap][c4 * 4]);
+        ffma2(pacc[2 * c4], gp, wv.x); ffma2(pacc[2 * c4 + 1], gp, wv.y);
       }
     }
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { acc[2 * c] = lo2(pacc[c]); acc[2 * c + 1] = hi2(pacc[c]); }
     float4* o = reinterpret_cast<float4*>(dx + u * 32);
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) o[c4] = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);

@@ -89,9 +89,10 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
   __syncthreads();
 
   const int ty = t >> 5, tx = t & 31;
-  float acc0[32], acc1[32];
+  // 2 pixels x 32 couts per thread as 32 packed accumulators: FFMA2 (fma.rn.f32x2) halves the FMA instruction count
+  unsigned long long pa0[16], pa1[16];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  for (int j = 0; j < 16; ++j) { pa0[j] = 0ull; pa1[j] = 0ull; }
 
   for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
@@ -101,17 +102,22 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
       for (int kw = 0; kw < KS; ++kw) {
         const float x0 = rowp[col_index<S, T::IWP>(tx * S + kw)];
         const float x1 = rowp[col_index<S, T::IWP>((tx + 32) * S + kw)];
-        const float4* wp = reinterpret_cast<const float4*>(sW + ((ci * KS + kh) * KS + kw) * 32);
+        const unsigned long long x0p = pack2(x0, x0), x1p = pack2(x1, x1);
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(sW + ((ci * KS + kh) * KS + kw) * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 wv = wp[j];
-          acc0[4 * j + 0] = fmaf(x0, wv.x, acc0[4 * j + 0]); acc1[4 * j + 0] = fmaf(x1, wv.x, acc1[4 * j + 0]);
-          acc0[4 * j + 1] = fmaf(x0, wv.y, acc0[4 * j + 1]); acc1[4 * j + 1] = fmaf(x1, wv.y, acc1[4 * j + 1]);
-          acc0[4 * j + 2] = fmaf(x0, wv.z, acc0[4 * j + 2]); acc1[4 * j + 2] = fmaf(x1, wv.z, acc1[4 * j + 2]);
-          acc0[4 * j + 3] = fmaf(x0, wv.w, acc0[4 * j + 3]); acc1[4 * j + 3] = fmaf(x1, wv.w, acc1[4 * j + 3]);
+          const ulonglong2 wv = wp[j];                     // (w[4j], w[4j+1]) | (w[4j+2], w[4j+3])
+          ffma2(pa0[2 * j], x0p, wv.x); ffma2(pa1[2 * j], x1p, wv.x);
+          ffma2(pa0[2 * j + 1], x0p, wv.y); ffma2(pa1[2 * j + 1], x1p, wv.y);
         }
       }
     }
+  }
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    acc0[2 * j] = lo2(pa0[j]); acc0[2 * j + 1] = hi2(pa0[j]);
+    acc1[2 * j] = lo2(pa1[j]); acc1[2 * j + 1] = hi2(pa1[j]);
   }
 
   const int oy = oy0 + ty;

@@ -37,24 +37,27 @@ conv_c32_taps_kernel(const float* __restrict__ x, const float* __restrict__ w, f
   cp_async_wait<0>();
   __syncthreads();
 
-  float acc[NTP];
+  unsigned long long pacc[NTP / 2];              // packed pairs of taps: FFMA2 halves the FMA instruction count
 #pragma unroll
-  for (int j = 0; j < NTP; ++j) acc[j] = 0.f;
+  for (int j = 0; j < NTP / 2; ++j) pacc[j] = 0ull;
 #pragma unroll 1
   for (int c = 0; c < 8; ++c) {     // not unrolled: a full unroll hoists all 32xNT weights into registers and spills
     const float4 xa = *reinterpret_cast<const float4*>(&sA[t][(c ^ (t & 7)) * 4]);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float xv = kk == 0 ? xa.x : kk == 1 ? xa.y : kk == 2 ? xa.z : xa.w;
-      const float4* wp = reinterpret_cast<const float4*>(&sW[c * 4 + kk][0]);
+      const unsigned long long xp = pack2(xv, xv);
+      const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(&sW[c * 4 + kk][0]);
 #pragma unroll
       for (int j = 0; j < NTP / 4; ++j) {
-        const float4 wv = wp[j];
-        acc[4 * j + 0] = fmaf(xv, wv.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(xv, wv.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(xv, wv.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(xv, wv.w, acc[4 * j + 3]);
+        const ulonglong2 wv = wp[j];
+        ffma2(pacc[2 * j], xp, wv.x); ffma2(pacc[2 * j + 1], xp, wv.y);
       }
     }
   }
+  float acc[NTP];
+#pragma unroll
+  for (int j = 0; j < NTP / 2; ++j) { acc[2 * j] = lo2(pacc[j]); acc[2 * j + 1] = hi2(pacc[j]); }
   const long long p = pos0 + t;
   if (p < npos) {
     const long long slice = p / plane;

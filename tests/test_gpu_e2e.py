@@ -203,3 +203,23 @@ def test_conv_backends_agree(kitti, backend, tol):
     assert depe <= 0.1 and d.median().item() <= 0.5
   else:
     assert err <= tol and depe <= EPE_TOL
+
+
+def test_sceneflow_batch_vs_oracle():
+  """BASELINE.json configs[3] shape (540x960: 540 -> 270 -> 135 -> 68, a non-divisible height), batch 2 of different pairs:
+  every sample must match the oracle run on that sample alone (eval mode never mixes samples)."""
+  cfg = dict(B=2, H=540, W=960, k=3, s=0, sharpen=40.0)
+  fsd, ssd = O.make_feature_state(3, 11), O.make_stereo_state(22, sharpen=40.0)
+  pairs = [O.make_stereo_pair(1, 540, 960, seed=3000 + i, max_disp_px=50.0 + 10 * i) for i in range(2)]
+  left = torch.cat([p[0] for p in pairs]); right = torch.cat([p[1] for p in pairs])
+  f, s = make_nets(cfg, fsd, ssd)
+  f.eval(); s.eval()
+  with torch.no_grad():
+    l, r = left.to(DEV), right.to(DEV)
+    out = s(l, f(l), f(r), "l", output_cost_volume=True)
+    for i, (pl, pr, gt) in enumerate(pairs):
+      ref = O.predict_disparity_left(fsd, ssd, pl, pr, 3)
+      for key, v in ref.items():
+        err = report(f"sceneflow[{i}] " + key, out[key][i:i + 1].cpu().numpy(), v.numpy())
+        assert err <= (MAX_DISP_TOL if key.startswith("pred_disp") else 2e-3), (i, key)
+      assert abs(O.epe(out["pred_disp_l/0"][i:i + 1].cpu(), gt).item() - O.epe(ref["pred_disp_l/0"], gt).item()) <= EPE_TOL
