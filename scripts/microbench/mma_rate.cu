@@ -1,0 +1,87 @@
+// Microbenchmark: issue rate of tcgen05.mma kind::tf32 M128 x N x K8 for several N, A operand from smem or TMEM.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu && ./mma_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t a) {
+  return (uint64_t)((a & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int N, bool TA, int NACC>
+__global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;\n"); }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tslot;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  long long t0 = 0, t1 = 0;
+  if (threadIdx.x < 32) {
+    const uint32_t sa = base, sb = base + 16384;
+    const uint32_t ta = tmem + 448;                       // A operand columns (garbage values are fine)
+    t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) {
+            const uint32_t td = tmem + a * (N <= 96 ? 96 : (N <= 128 ? 128 : 256)) % 448;
+            const uint64_t bd = make_desc(sb + ks * 32);
+            if (TA) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                                 :: "r"(td), "r"(ta + ks * 8), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
+            else    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                                 :: "r"(td), "l"(make_desc(sa + ks * 32)), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(&bar)) : "memory");
+    }
+    __syncwarp();
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    t1 = clock64();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
+}
+
+template <int N, bool TA, int NACC>
+void run(const char* tag) {
+  long long* d; cudaMalloc(&d, 148 * sizeof(long long));
+  const int iters = 200, smem = 16384 + 32768 + 2048;
+  cudaFuncSetAttribute(rate_kernel<N, TA, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC><<<148, 128, smem>>>(d, iters);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  double s = 0; for (int i = 0; i < 148; ++i) s += h[i];
+  const double cyc = s / 148 / (iters * 4 * NACC);
+  printf("%-28s N=%3d acc=%d: %7.1f cycles/MMA  %7.1f MAC/clk/SM  (%s)\n", tag, N, NACC, cyc, 128.0 * N * 8 / cyc, cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+int main() {
+  run<32, false, 1>("A smem"); run<64, false, 1>("A smem"); run<96, false, 1>("A smem"); run<128, false, 1>("A smem"); run<192, false, 1>("A smem"); run<256, false, 1>("A smem");
+  run<96, true, 1>("A tmem"); run<128, true, 1>("A tmem"); run<192, true, 1>("A tmem"); run<256, true, 1>("A tmem");
+  run<96, false, 3>("A smem, 3 accumulators"); run<96, true, 3>("A tmem, 3 accumulators");
+  return 0;
+}
