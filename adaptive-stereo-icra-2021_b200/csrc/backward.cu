@@ -86,8 +86,9 @@ bn_lrelu_bwd_apply_kernel(const float4* __restrict__ z, const float4* __restrict
 }
 
 // out[j] = mul * sum_i partial[i][j]: block = 32 columns x 8 row groups, double accumulation, fixed order -> deterministic
+// taps > 0: the row is a [taps][32 ci][32 co] weight-gradient block and is written in PyTorch's [co][ci][taps] layout.
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ partial, int n, int len, float* __restrict__ out, float mul) {
+reduce_partials_kernel(const float* __restrict__ partial, int n, int len, float* __restrict__ out, float mul, int taps) {
   __shared__ double red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -98,7 +99,9 @@ reduce_partials_kernel(const float* __restrict__ partial, int n, int len, float*
   __syncthreads();
   if (ty == 0 && j < len) {
     double a = ((red[0][tx] + red[1][tx]) + (red[2][tx] + red[3][tx])) + ((red[4][tx] + red[5][tx]) + (red[6][tx] + red[7][tx]));
-    out[j] = (float)(a * (double)mul);
+    int o = j;
+    if (taps > 0) { const int co = j & 31, ci = (j >> 5) & 31, tap = j >> 10; o = (co * 32 + ci) * taps + tap; }
+    out[o] = (float)(a * (double)mul);
   }
 }
 
@@ -427,7 +430,14 @@ extern "C" int snb_reduce_partials(const float* partial, int n, int len, float* 
   if (len <= 512 && n >= 64)
     reduce_partials_narrow_kernel<<<snb_ceil_div(len, 4), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul);
   else
-    reduce_partials_kernel<<<snb_ceil_div(len, 32), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul);
+    reduce_partials_kernel<<<snb_ceil_div(len, 32), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul, 0);
+  SNB_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+extern "C" int snb_reduce_wgrad_partials(const float* partial, int n, int taps, float* out, void* stream) {
+  SNB_REQUIRE(partial && out && n > 0 && taps > 0, "snb_reduce_wgrad_partials: bad args");
+  reduce_partials_kernel<<<taps * 32, 256, 0, (cudaStream_t)stream>>>(partial, n, taps * 1024, out, 1.0f, taps);
   SNB_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }

@@ -44,7 +44,7 @@ struct RefineLoader {       // channel 0 = scale * bilinear(coarse), channels 1.
 template <int CIN, int KS, int S, class Loader>
 __global__ void __launch_bounds__(256)
 conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y, float* __restrict__ up_out,
-                  int OH, int OW, int pad, snb_conv_epilogue e) {
+                  int OH, int OW, int pad, snb_conv_epilogue e, int phaseB) {
   using T = TileDims<CIN, KS, S>;
   extern __shared__ __align__(16) float smem[];
   float* sIn = smem;
@@ -176,7 +176,14 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
     for (int i = 0; i < 8; ++i) {
       const int idx = i * 32 + tx, pp = idx >> 3, c = idx & 7;
       const float4 v = *reinterpret_cast<const float4*>(stg + pp * 32 + ((c ^ (pp & 7)) << 2));
-      if (oy < OH && oxs + pp < OW) *reinterpret_cast<float4*>(yrow + (size_t)pp * 32 + c * 4) = v;
+      if (oy < OH && oxs + pp < OW) {
+        if (phaseB > 0) {      // polyphase output [4][B][OH/2][OW/2][32] for the stride-2 layer that follows (csrc/phase.cu)
+          const int ox = oxs + pp, ph = (oy & 1) * 2 + (ox & 1);
+          *reinterpret_cast<float4*>(y + ((((size_t)ph * phaseB + b) * (OH >> 1) + (oy >> 1)) * (OW >> 1) + (ox >> 1)) * 32 + c * 4) = v;
+        } else {
+          *reinterpret_cast<float4*>(yrow + (size_t)pp * 32 + c * 4) = v;
+        }
+      }
     }
     __syncwarp();
   }
@@ -272,8 +279,23 @@ extern "C" int snb_conv5x5s2_c3(const float* img, const float* w, const float* b
   auto kern = conv_small_kernel<3, 5, 2, ImgLoader>;
   SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   const int tiles = B * ((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
-  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, y, nullptr, OH, OW, 2, e);
+  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, y, nullptr, OH, OW, 2, e, 0);
   SNB_LAUNCH_CHECK("conv5x5s2_c3");
+  return 0;
+}
+
+extern "C" int snb_conv5x5s2_c3_phases(const float* img, const float* w, const float* bias, float* yph, int B, int H, int W, void* stream) {
+  SNB_REQUIRE(img && w && yph && B > 0 && H > 0 && W > 0, "snb_conv5x5s2_c3_phases: bad args");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  SNB_REQUIRE((OH % 2) == 0 && (OW % 2) == 0, "snb_conv5x5s2_c3_phases: output %dx%d must be even (use snb_conv5x5s2_c3 + snb_phase_split)", OH, OW);
+  using T = TileDims<3, 5, 2>;
+  ImgLoader ld{img, 3, H, W};
+  snb_conv_epilogue e{bias, nullptr, nullptr, nullptr, nullptr, 0};
+  auto kern = conv_small_kernel<3, 5, 2, ImgLoader>;
+  SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  const int tiles = B * ((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
+  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, yph, nullptr, OH, OW, 2, e, B);
+  SNB_LAUNCH_CHECK("conv5x5s2_c3_phases");
   return 0;
 }
 
@@ -289,7 +311,7 @@ extern "C" int snb_refine_in_conv(const float* coarse, const float* rgb, const f
   auto kern = conv_small_kernel<4, 3, 1, RefineLoader>;
   SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
   const int tiles = snb_refine_in_conv_num_tiles(B, H, W);
-  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, z, up, H, W, 1, *e);
+  kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, z, up, H, W, 1, *e, 0);
   SNB_LAUNCH_CHECK("refine_in_conv");
   return 0;
 }

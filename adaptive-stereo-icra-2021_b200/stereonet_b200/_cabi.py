@@ -38,6 +38,7 @@ SIGNATURES = {
   "snb_phase_split": (_I, [_P, _P, _I, _I, _I, _P]),
   "snb_phase_merge": (_I, [_P, _P, _I, _I, _I, _P]),
   "snb_conv5x5s2_c3": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+  "snb_conv5x5s2_c3_phases": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
   "snb_refine_in_conv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _EP, _P]),
   "snb_refine_in_conv_num_tiles": (_I, [_I, _I, _I]),
   "snb_conv_c32_taps": (_I, [_P, _P, _P, _LL, _I, _I, _P]),
@@ -52,6 +53,7 @@ SIGNATURES = {
   "snb_bn_lrelu_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P]),
   "snb_bn_lrelu_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _P, _P]),
   "snb_reduce_partials": (_I, [_P, _I, _I, _P, _F, _P]),
+  "snb_reduce_wgrad_partials": (_I, [_P, _I, _I, _P, _P]),
   "snb_channel_sum": (_I, [_P, _P, _LL, _P]),
   "snb_conv_c32_wgrad": (_I, [_P, _P, _P, _GP, _P]),
   "snb_conv_c32_wgrad_num_partials": (_I, [_GP]),

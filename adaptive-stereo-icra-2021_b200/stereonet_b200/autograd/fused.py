@@ -148,13 +148,14 @@ def wprep_tc_phases(conv, mode):
   return _cached(conv, ("wtc_phase", mode), [conv.weight], make)
 
 
-def conv5x5s2_c32(x, conv, bias):
-  """5x5 stride-2 pad-2 32->32 convolution: FFMA kernel, or four chained tensor-core 3x3 convs over the phase images."""
+def conv5x5s2_c32(x, conv, bias, phases=None):
+  """5x5 stride-2 pad-2 32->32 convolution: FFMA kernel, or four chained tensor-core 3x3 convs over the phase images
+  (`phases`: the input already in polyphase form)."""
   if CONV_BACKEND == "ffma":
     g = ops.geom(x.shape, 5, stride=2, dil=1, pad=2)
     y, _ = ops.conv_c32(x, wprep(conv), g, bias=bias)
     return y
-  ph = ops.phase_split(x)
+  ph = phases if phases is not None else ops.phase_split(x)
   g3 = ops.geom(ph[0].shape, 3, stride=1, dil=1)
   passes = 3 if CONV_BACKEND == "tc3" else 1
   y = None
@@ -175,6 +176,17 @@ def conv5x5s2_c32_dgrad(dy, conv, H, W):
   for i, wimg in enumerate(wprep_tc_phases(conv, 1)):
     ops.conv_c32_tc(dy, wimg, g3, passes=passes, out=ph[i])
   return ops.phase_merge(ph, H, W)
+
+
+def downsample_pair(img, conv0, conv1):
+  """downsample[0] (3->32) followed by downsample[1] (32->32), both 5x5 stride 2.  Inference with even intermediate size:
+  the first layer writes the polyphase images the second one consumes (no separate split pass)."""
+  H, W = img.shape[-2:]
+  OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+  if CONV_BACKEND != "ffma" and not _needs_grad(conv0, conv1) and OH % 2 == 0 and OW % 2 == 0:
+    ph = ops.conv5x5s2_c3_phases(img, conv0.weight, conv0.bias)
+    return conv5x5s2_c32(None, conv1, conv1.bias.detach(), phases=ph)
+  return conv_plain(conv5x5s2_first(img, conv0), conv1, ksize=5, stride=2)
 
 
 def conv_plain(x, conv, ksize, stride):

@@ -74,8 +74,11 @@ class FeatureExtractorNetwork(nn.Module):
   def forward(self, rgb_img):
     if not (isinstance(rgb_img, torch.Tensor) and rgb_img.is_cuda and rgb_img.dtype == torch.float32):
       raise RuntimeError("stereonet_b200: rgb_img must be an fp32 CUDA tensor; this build has no CPU path")
-    x = fused.conv5x5s2_first(rgb_img.contiguous(), self.downsample[0])
-    for i in range(1, self.k):
+    if self.k >= 2:
+      x = fused.downsample_pair(rgb_img.contiguous(), self.downsample[0], self.downsample[1])
+    else:
+      x = fused.conv5x5s2_first(rgb_img.contiguous(), self.downsample[0])
+    for i in range(2, self.k):
       x = fused.conv_plain(x, self.downsample[i], ksize=5, stride=2)
     for block in self.residual_blocks:
       x = block.forward_cl(x)

@@ -195,6 +195,18 @@ def conv5x5s2_c3(img, w, bias):
   return y
 
 
+def conv5x5s2_c3_phases(img, w, bias):
+  """downsample[0] written as the polyphase images [4,B,OH/2,OW/2,32] of its output (OH, OW even)."""
+  _req(img, "rgb_img", 4)
+  B, Cc, H, W = img.shape
+  OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+  y = torch.empty((4, B, OH // 2, OW // 2, 32), device=img.device, dtype=torch.float32)
+  check(_cabi.lib().snb_conv5x5s2_c3_phases(_p(img), _p(_req(w.detach(), "w")), _p(bias.detach()), _p(y), B, H, W, _stream(img)),
+        "snb_conv5x5s2_c3_phases")
+  _count()
+  return y
+
+
 def refine_in_conv(coarse, rgb, w, bias, scale=None, shift=None, lrelu=False, want_stats=False):
   """Fused upsample + scale + concat + Conv2d(4->32).  Returns (up [B,H,W], z [B,H,W,32], stats)."""
   _req(coarse, "coarse_disparity", 3); _req(rgb, "guidance_rgb", 4)
@@ -298,6 +310,14 @@ def reduce_partials(partial, mul=1.0):
   return out
 
 
+def reduce_wgrad_partials(part, taps, wshape):
+  """[n, taps*1024] per-CTA partials -> weight gradient in PyTorch layout `wshape` = [32,32,*k] (one launch)."""
+  out = torch.empty(wshape, device=part.device, dtype=torch.float32)
+  check(_cabi.lib().snb_reduce_wgrad_partials(_p(part), part.shape[0], taps, _p(out), _stream(part)), "snb_reduce_wgrad_partials")
+  _count()
+  return out
+
+
 def bn_lrelu_bwd(z, dy, scale, shift, mean, invstd, train, lrelu=True):
   """Backward of y = LeakyReLU(z*scale + shift) with (train) batch-stat BatchNorm.  Returns dz, dgamma, dbeta, dbias."""
   _req(z, "z"); _req(dy, "dy")
@@ -335,8 +355,7 @@ def conv_c32_wgrad(x, dz, g, wshape):
   part = torch.empty((n, taps * 1024), device=x.device, dtype=torch.float32)
   check(_cabi.lib().snb_conv_c32_wgrad(_p(x), _p(dz), _p(part), C.byref(g), _stream(x)), "snb_conv_c32_wgrad")
   _count()
-  dw = reduce_partials(part).view(taps, 32, 32)                  # [tap][cin][cout]
-  return dw.permute(2, 1, 0).reshape(wshape).contiguous()       # layout change only
+  return reduce_wgrad_partials(part, taps, wshape)
 
 
 def conv_c32_wgrad_tc(x, dz, g, wshape, passes=3):
@@ -349,8 +368,7 @@ def conv_c32_wgrad_tc(x, dz, g, wshape, passes=3):
   part = torch.empty((n, taps * 1024), device=x.device, dtype=torch.float32)
   check(_cabi.lib().snb_conv_c32_wgrad_tc(_p(x), _p(dz), _p(part), C.byref(g), passes, _stream(x)), "snb_conv_c32_wgrad_tc")
   _count()
-  dw = reduce_partials(part).view(taps, 32, 32)                  # [tap][cin][cout]
-  return dw.permute(2, 1, 0).reshape(wshape).contiguous()
+  return reduce_wgrad_partials(part, taps, wshape)
 
 
 def conv5x5s2_c3_wgrad(img, dy):

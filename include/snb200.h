@@ -118,6 +118,9 @@ SNB_API int snb_phase_merge(const float* in, float* dx, int B, int H, int W, voi
  * snb_conv5x5s2_c3: FeatureExtractorNetwork.downsample[0] (stereo_net.py:64-70,81): NCHW image [B,3,H,W] -> [B,OH,OW,32]. */
 SNB_API int snb_conv5x5s2_c3(const float* img, const float* w /*[32][3][5][5]*/, const float* bias, float* y,
                      int B, int H, int W, void* stream);
+/* Same convolution, written directly as the four polyphase images [4][B][OH/2][OW/2][32] that the following stride-2 layer
+ * consumes (inference path: saves the separate snb_phase_split pass).  OH and OW must be even. */
+SNB_API int snb_conv5x5s2_c3_phases(const float* img, const float* w, const float* bias, float* yph, int B, int H, int W, void* stream);
 /* snb_refine_in_conv: EdgeAwareRefinement stereo_net.py:105-117 fused: bilinear upsample of coarse [B,h,w] to HxW
  * (align_corners=False), * disp_scale, concat with NCHW rgb, Conv2d(4->32,3x3,p1) + bias.  Writes the upsampled
  * disparity to up [B,H,W] and z [B,H,W,32]; epilogue fields as in snb_conv_c32 (residual unused). */
@@ -178,6 +181,9 @@ SNB_API int snb_bn_lrelu_bwd_apply(const float* z, const float* dy, const float*
                            float* dz, float* dzpart, void* stream);
 /* out[j] = mul * sum_i partial[i][j], i < n, j < len (fixed order, double accumulation). */
 SNB_API int snb_reduce_partials(const float* partial, int n, int len, float* out, float mul, void* stream);
+/* Sum the per-CTA weight-gradient partials [n][taps][32 cin][32 cout] and write PyTorch's layout out[cout][cin][taps]
+ * (fixed order, double accumulation): reduction and layout change of snb_conv_c32_wgrad[_tc] in one launch. */
+SNB_API int snb_reduce_wgrad_partials(const float* partial, int n, int taps, float* out, void* stream);
 /* partial[blk][32] = per-channel sums of x [npos][32] (bias gradient of a plain convolution). */
 SNB_API int snb_channel_sum(const float* x, float* partial, long long npos, void* stream);
 /* Weight gradient of a 32->32 convolution: partial[cta][taps][cin][cout]; sum over cta with snb_reduce_partials. */
