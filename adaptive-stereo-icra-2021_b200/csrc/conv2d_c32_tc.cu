@@ -277,7 +277,8 @@ conv2d_c32_tc_kernel(const Params2 p) {
       }
       __syncwarp();
       tc::mbar_wait_spin(wbar, 0);
-      const uint32_t sb_u32 = base_u32 + NA * AWIN_BYTES;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform copies for the uniform datapath
+      const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NA * AWIN_BYTES;
       uint32_t buf = 0, phase = 0;
       long long tile_base = 0;                 // tiles issued so far by this CTA (TMEM slot = counter % NACC)
       uint32_t win_count = 0;                  // windows consumed so far (TMEM A slot = counter & 1)
@@ -289,46 +290,57 @@ conv2d_c32_tc_kernel(const Params2 p) {
           const uint32_t aslot = win_count & 1;
           uint64_t* fbar = TA ? &full[aslot] : &full[buf];
           const uint32_t fphase = TA ? ((win_count >> 1) & 1) : phase;
-          if (PROF) t_full += mbar_wait_timed<PROF>(fbar, fphase); else tc::mbar_wait_spin(fbar, fphase);
+          if (PROF) t_full += mbar_wait_timed<PROF>(fbar, fphase); else mbar_wait_warp(fbar, fphase);
           tc_fence_after();
           const uint32_t sa = base_u32 + buf * AWIN_BYTES;
-          const uint32_t ta = tmem_base + TA_BASE + aslot * 64;
+          const uint32_t ta = tmem_u + TA_BASE + aslot * 64;
+          // accumulator bookkeeping first (waits are warp-uniform), then ONE election for the window's 36 MMAs + commits
+          uint32_t tmem_d[3], sbw[3]; bool act[3]; int slot_done = -1;
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk) {
             const int kh = 2 - kk;             // finish the oldest tile first so the epilogue can start on it
             const int j = u - kh;
-            if (j < 0 || j >= s.ntiles) continue;
-            const long long tcount = tile_base + j;
+            act[kk] = j >= 0 && j < s.ntiles;
+            const long long tcount = tile_base + (act[kk] ? j : 0);
             const int slot = (int)(tcount & (NACC - 1));
-            if (kh == 0) {                     // first touch of this tile's accumulator: the epilogue must have drained it
+            if (act[kk] && kh == 0) {          // first touch of this tile's accumulator: the epilogue must have drained it
               if (PROF) t_tempty += mbar_wait_timed<PROF>(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
-              else tc::mbar_wait_spin(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
+              else mbar_wait_warp(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
               tc_fence_after();
             }
-            const uint32_t tmem_d = tmem_base + slot * ACC_STRIDE;
-            const uint32_t sbw = sb_u32 + kh * BWIN_BYTES;
+            if (act[kk] && kh == 2) slot_done = slot;
+            tmem_d[kk] = tmem_u + slot * ACC_STRIDE;
+            sbw[kk] = sb_u32 + kh * BWIN_BYTES;
+          }
+          if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bh = make_desc(sbw + ks * 32);
-              if (TA) {
-                mma_tf32_ts(tmem_d, ta + ks * 8, bh, (kh | ks) != 0);
-                if (p.passes == 3) {
-                  mma_tf32_ts(tmem_d, ta + 32 + ks * 8, bh, 1);
-                  mma_tf32_ts(tmem_d, ta + ks * 8, make_desc(sbw + B_BYTES + ks * 32), 1);
-                }
-              } else {
-                const uint64_t ah = make_desc(sa + ks * 32);
-                mma_tf32(tmem_d, ah, bh, (kh | ks) != 0);
-                if (p.passes == 3) {
-                  mma_tf32(tmem_d, make_desc(sa + A_BYTES + ks * 32), bh, 1);
-                  mma_tf32(tmem_d, ah, make_desc(sbw + B_BYTES + ks * 32), 1);
+            for (int kk = 0; kk < 3; ++kk) {
+              if (!act[kk]) continue;
+              const int kh = 2 - kk;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bh = make_desc(sbw[kk] + ks * 32);
+                if (TA) {
+                  mma_tf32_ts_raw(tmem_d[kk], ta + ks * 8, bh, (kh | ks) != 0);
+                  if (p.passes == 3) {
+                    mma_tf32_ts_raw(tmem_d[kk], ta + 32 + ks * 8, bh, 1);
+                    mma_tf32_ts_raw(tmem_d[kk], ta + ks * 8, make_desc(sbw[kk] + B_BYTES + ks * 32), 1);
+                  }
+                } else {
+                  const uint64_t ah = make_desc(sa + ks * 32);
+                  mma_tf32_raw(tmem_d[kk], ah, bh, (kh | ks) != 0);
+                  if (p.passes == 3) {
+                    mma_tf32_raw(tmem_d[kk], make_desc(sa + A_BYTES + ks * 32), bh, 1);
+                    mma_tf32_raw(tmem_d[kk], ah, make_desc(sbw[kk] + B_BYTES + ks * 32), 1);
+                  }
                 }
               }
+              if (kh == 2) mma_commit_raw(&tfull[slot_done]);      // tile u-2 has received all three kh contributions
             }
-            if (kh == 2) mma_commit(&tfull[slot]);      // tile j = u-2 has received all three kh contributions
+            mma_commit_raw(TA ? &empty[aslot] : &empty[buf]);      // window u consumed (TA: its TMEM slot, else its smem buffer)
           }
+          __syncwarp();
           ++win_count;
-          mma_commit(TA ? &empty[aslot] : &empty[buf]);   // window u fully consumed (TA: its TMEM slot, else its smem buffer)
           if (++buf == NA) { buf = 0; phase ^= 1; }
         }
         tile_base += s.ntiles;

@@ -82,8 +82,7 @@ __device__ __forceinline__ uint32_t mn_off(int rr, int chunk) {
   return rr * 128 + (((((chunk >> 1) ^ (rr & 3)) << 1) | (chunk & 1)) << 4);
 }
 
-__device__ __forceinline__ void mma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  if (elect_one())
+__device__ __forceinline__ void mma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {   // un-predicated: call inside `if (elect_one())`
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -230,53 +229,57 @@ conv_c32_wgrad_tc_kernel(const WParams p) {
     {
       uint32_t xc = 0, zc = 0, used = 0;
       bool any = false;
-      const uint32_t zb_u32 = base_u32 + ring_bytes;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), smem_u = __shfl_sync(0xffffffffu, base_u32, 0);
+      const uint32_t zb_u32 = smem_u + ring_bytes;
       for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
         const Strip s = decode_strip(p, sid);
         if (s.nt == 0) continue;
         int valid = p.W - s.cb * p.Kc; if (valid > p.Kc) valid = p.Kc;
         const int nks = (valid + 7) >> 3;
-        tc::mbar_wait_spin(&xfull[xc % R], (xc / R) & 1);
-        tc::mbar_wait_spin(&xfull[(xc + 1) % R], ((xc + 1) / R) & 1);
+        mbar_wait_warp(&xfull[xc % R], (xc / R) & 1);
+        mbar_wait_warp(&xfull[(xc + 1) % R], ((xc + 1) / R) & 1);
         for (int j = 0; j < s.nt; ++j) {
           const uint32_t c0 = xc + j;
-          tc::mbar_wait_spin(&xfull[(c0 + 2) % R], ((c0 + 2) / R) & 1);
-          tc::mbar_wait_spin(&zfull[zc & 1], (zc >> 1) & 1);
+          mbar_wait_warp(&xfull[(c0 + 2) % R], ((c0 + 2) / R) & 1);
+          mbar_wait_warp(&zfull[zc & 1], (zc >> 1) & 1);
           tc_fence_after();
           const uint32_t zb = zb_u32 + (zc & 1) * 2 * p.zimg;
           const uint32_t blbo = p.dil * 128;
-          if (p.three_d) {
+          const uint32_t used_before = used;
+          used |= p.three_d ? 7u : (1u << (c0 & 3));
+          if (elect_one()) {                         // one election for the tile's MMAs + commits (see tc_common.cuh)
+            if (p.three_d) {
 #pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-              const uint32_t sa = base_u32 + ((c0 + kd) % R) * p.slot_stride;
-              const uint32_t albo = p.Kc * 128;
-              const bool fresh = !((used >> kd) & 1);
-              used |= 1u << kd;
+              for (int kd = 0; kd < 3; ++kd) {
+                const uint32_t sa = smem_u + ((c0 + kd) % R) * p.slot_stride;
+                const uint32_t albo = p.Kc * 128;
+                const bool fresh = !((used_before >> kd) & 1);
+                for (int ks = 0; ks < nks; ++ks) {
+                  const uint64_t ah = make_desc_mn(sa + ks * 1024, albo), bh = make_desc_mn(zb + ks * 1024, blbo);
+                  mma_tf32_mn(tmem_u + kd * 128, ah, bh, !(fresh && ks == 0));
+                  if (p.passes == 3) {
+                    mma_tf32_mn(tmem_u + kd * 128, make_desc_mn(sa + p.ximg + ks * 1024, albo), bh, 1);
+                    mma_tf32_mn(tmem_u + kd * 128, ah, make_desc_mn(zb + p.zimg + ks * 1024, blbo), 1);
+                  }
+                }
+              }
+            } else {
+              const uint32_t acc = c0 & 3;
+              const bool fresh = !((used_before >> acc) & 1);
               for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t ah = make_desc_mn(sa + ks * 1024, albo), bh = make_desc_mn(zb + ks * 1024, blbo);
-                mma_tf32_mn(tmem_base + kd * 128, ah, bh, !(fresh && ks == 0));
+                const uint64_t ah = make_desc_mn(smem_u + ks * 1024, p.slot_stride), bh = make_desc_mn(zb + ks * 1024, blbo);
+                mma_tf32_mn(tmem_u + acc * 128, ah, bh, !(fresh && ks == 0));
                 if (p.passes == 3) {
-                  mma_tf32_mn(tmem_base + kd * 128, make_desc_mn(sa + p.ximg + ks * 1024, albo), bh, 1);
-                  mma_tf32_mn(tmem_base + kd * 128, ah, make_desc_mn(zb + p.zimg + ks * 1024, blbo), 1);
+                  mma_tf32_mn(tmem_u + acc * 128, make_desc_mn(smem_u + p.ximg + ks * 1024, p.slot_stride), bh, 1);
+                  mma_tf32_mn(tmem_u + acc * 128, ah, make_desc_mn(zb + p.zimg + ks * 1024, blbo), 1);
                 }
               }
             }
-          } else {
-            const uint32_t acc = c0 & 3;
-            const bool fresh = !((used >> acc) & 1);
-            used |= 1u << acc;
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t ah = make_desc_mn(base_u32 + ks * 1024, p.slot_stride), bh = make_desc_mn(zb + ks * 1024, blbo);
-              mma_tf32_mn(tmem_base + acc * 128, ah, bh, !(fresh && ks == 0));
-              if (p.passes == 3) {
-                mma_tf32_mn(tmem_base + acc * 128, make_desc_mn(base_u32 + p.ximg + ks * 1024, p.slot_stride), bh, 1);
-                mma_tf32_mn(tmem_base + acc * 128, ah, make_desc_mn(zb + p.zimg + ks * 1024, blbo), 1);
-              }
-            }
+            mma_commit_raw(&xempty[c0 % R]);           // window/slot j is not needed by later tiles
+            mma_commit_raw(&zempty[zc & 1]);
           }
+          __syncwarp();
           any = true;
-          mma_commit(&xempty[c0 % R]);               // window/slot j is not needed by later tiles
-          mma_commit(&zempty[zc & 1]);
           ++zc;
         }
         mma_commit(&xempty[(xc + s.nt) % R]);        // the two trailing halo slots of this strip

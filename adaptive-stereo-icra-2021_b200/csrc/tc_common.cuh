@@ -161,6 +161,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
   const long long t0 = clock64();
   while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    __nanosleep(20);                                 // a spinning warp must not take issue slots from the epilogue warps it waits for
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }

@@ -14,13 +14,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int N, bool TA, int NACC>
-__global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters) {
+template <int N, bool TA, int NACC, int BG>
+__global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters) {
+  __shared__ volatile int stop_flag;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
   const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  for (int i = threadIdx.x; i < (16384 + 32768 + 65536) / 4; i += 288) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (threadIdx.x == 0) stop_flag = 0;
   if (threadIdx.x < 32) {
     if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;\n"); }
     __syncwarp();
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
             const uint32_t td = tmem + a * (N <= 96 ? 96 : (N <= 128 ? 128 : 256)) % 448;
-            const uint64_t bd = make_desc(sb + ks * 32);
+            const uint64_t bd = make_desc(sb + ks * 32 + (BG == 4 ? ((it * 4 + ks) % 2) * 12288 : 0));
             if (TA) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
                                  :: "r"(td), "r"(ta + ks * 8), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
             else    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
@@ -59,18 +61,44 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
     uint32_t ok = 0;
     while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
     t1 = clock64();
+    stop_flag = 1;
+  } else if (threadIdx.x >= 32) {
+    // background warps 1..8 (two per TMEM lane quadrant)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, quad = w & 3;
+    float4* sp = reinterpret_cast<float4*>(smem + 16384 + 32768 + 1024) + (w - 1) * 512 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t r[16];
+    for (int i = 0; i < 16; ++i) r[i] = i;
+    while (!stop_flag) {
+      if (BG == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { float4 v = sp[k * 32]; acc.x += v.x; sp[k * 32 + 256] = acc; }
+      } else if (BG == 2) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(r[0]),"=r"(r[1]),"=r"(r[2]),"=r"(r[3]),"=r"(r[4]),"=r"(r[5]),"=r"(r[6]),"=r"(r[7]),"=r"(r[8]),"=r"(r[9]),"=r"(r[10]),"=r"(r[11]),"=r"(r[12]),"=r"(r[13]),"=r"(r[14]),"=r"(r[15])
+                     : "r"(tmem + ((uint32_t)(quad * 32) << 16) + 256) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      } else if (BG == 3) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                     :: "r"(tmem + ((uint32_t)(quad * 32) << 16) + 480), "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),"r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      } else {
+        __nanosleep(200);
+      }
+    }
+    if (acc.x == 123.f && r[3] == 77) out[0] = 1;
   }
   __syncthreads();
   if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
 }
 
-template <int N, bool TA, int NACC>
+template <int N, bool TA, int NACC, int BG>
 void run(const char* tag) {
   long long* d; cudaMalloc(&d, 148 * sizeof(long long));
-  const int iters = 200, smem = 16384 + 32768 + 2048;
-  cudaFuncSetAttribute(rate_kernel<N, TA, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC><<<148, 128, smem>>>(d, iters);
+  const int iters = 200, smem = 16384 + 32768 + 65536 + 2048;
+  cudaFuncSetAttribute(rate_kernel<N, TA, NACC, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC, BG><<<148, 288, smem>>>(d, iters);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   double s = 0; for (int i = 0; i < 148; ++i) s += h[i];
@@ -80,8 +108,11 @@ void run(const char* tag) {
 }
 
 int main() {
-  run<32, false, 1>("A smem"); run<64, false, 1>("A smem"); run<96, false, 1>("A smem"); run<128, false, 1>("A smem"); run<192, false, 1>("A smem"); run<256, false, 1>("A smem");
-  run<96, true, 1>("A tmem"); run<128, true, 1>("A tmem"); run<192, true, 1>("A tmem"); run<256, true, 1>("A tmem");
-  run<96, false, 3>("A smem, 3 accumulators"); run<96, true, 3>("A tmem, 3 accumulators");
+  run<32, false, 1, 0>("A smem"); run<64, false, 1, 0>("A smem"); run<96, false, 1, 0>("A smem"); run<128, false, 1, 0>("A smem"); run<192, false, 1, 0>("A smem"); run<256, false, 1, 0>("A smem");
+  run<96, true, 1, 0>("A tmem"); run<128, true, 1, 0>("A tmem"); run<192, true, 1, 0>("A tmem"); run<256, true, 1, 0>("A tmem");
+  run<96, false, 3, 0>("A smem, 3 accumulators"); run<96, true, 3, 0>("A tmem, 3 accumulators");
+  run<96, true, 3, 4>("A tmem, alternating B images");
+  run<96, true, 3, 1>("A tmem + 8 warps LDS/STS"); run<96, false, 3, 1>("A smem + 8 warps LDS/STS");
+  run<96, true, 3, 2>("A tmem + 8 warps tcgen05.ld"); run<96, true, 3, 3>("A tmem + 8 warps tcgen05.st");
   return 0;
 }
