@@ -36,21 +36,12 @@ struct Params {
 
 
 // PROF = true adds clock64() timers around every wait (snb_conv_c32_tc_profile); the product path is PROF = false.
-// TA = true: the A window is staged RAW (fp32, no split) in a 16 KB smem ring by 3 loader warps, 4 converter warps (one per
-// TMEM lane quadrant, thread = pixel row) split it into hi/lo and tcgen05.st it into one of two A slots in TMEM, and the
-// MMAs read A from TMEM: per MMA only the 3 KB B operand is fetched from shared memory instead of 7 KB (A + B) — the
-// smem-operand kernel is bound by exactly that fetch.  smem (TA): raw ring | B ring (hi|lo per window) | epilogue tiles;
-// TMEM (TA): 4 accumulators x 96 columns | 2 A slots x 64 columns (hi 32 | lo 32).
-template <bool PROF, bool TA>
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_c32_tc_kernel(const Params p) {
-  constexpr int ACC_STRIDE = TA ? 96 : 128;
-  constexpr int TA_BASE = NACC * 96;
-  constexpr int TA_LOADERS = 3;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
-  constexpr int BRING_OFF = NSTAGE * A_BYTES;                 // TA: B ring behind the raw A ring
   unsigned char* sOutB = base + NSTAGE * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOutB + OUT_BYTES);
   uint64_t* full = bars;                 // [NSTAGE]  loaders (+TMA bytes) -> MMA
@@ -58,11 +49,7 @@ conv_c32_tc_kernel(const Params p) {
   uint64_t* tfull = bars + 2 * NSTAGE;   // [NACC]    MMA commit -> epilogue
   uint64_t* tempty = tfull + NACC;       // [NACC]    epilogue -> MMA
   uint64_t* wbar = tempty + NACC;        // resident-weights barrier (2-D)
-  uint64_t* rfull = wbar + 1;            // [NSTAGE]  TA: loaders -> converters (raw window in smem)
-  uint64_t* rempty = rfull + NSTAGE;     // [NSTAGE]  TA: converters -> loaders
-  uint64_t* afull = rempty + NSTAGE;     // [2]       TA: converters -> MMA (A slot in TMEM)
-  uint64_t* aempty = afull + 2;          // [2]       TA: MMA commit -> converters
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -70,10 +57,7 @@ conv_c32_tc_kernel(const Params p) {
 
   if (warp == NUM_LOADER_WARPS) {
     if (lane == 0) {
-      // !TA: full = 7 loader warps + the TMA issuer's arrive(.expect_tx);  TA: full/empty track only the B ring (TMA)
-      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], TA ? 1 : NUM_LOADER_WARPS + 1); mbar_init(&empty[i], 1); }
-      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&rfull[i], TA_LOADERS); mbar_init(&rempty[i], 4); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], NUM_LOADER_WARPS + 1); mbar_init(&empty[i], 1); }
       for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
       mbar_init(wbar, 1);
       mbar_fence_init();
@@ -87,66 +71,18 @@ conv_c32_tc_kernel(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (TA && warp >= TA_LOADERS && warp < NUM_LOADER_WARPS) {
-    // =============================================================== TA converters (warps 3-6; TMEM lane quadrant = warp % 4)
-    const int quad = warp & 3;
-    const int m = quad * 32 + lane;                        // window row = TMEM lane
-    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_items = my_tiles * p.nwin;
-    uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < n_items; ++it) {
-      const uint32_t slot = (uint32_t)it & 1;
-      mbar_wait(&rfull[stage], phase);
-      const unsigned char* st = base + stage * A_BYTES + m * 128;
-      float4 v[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(st + ((c ^ (m & 7)) << 4));
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rempty[stage]);          // raw window consumed (values are in registers)
-      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-      mbar_wait(&aempty[slot], (((uint32_t)it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + slot * 64;
-      {
-        uint32_t h[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          h[4 * c] = __float_as_uint(v[c].x) & 0xffffe000u; h[4 * c + 1] = __float_as_uint(v[c].y) & 0xffffe000u;
-          h[4 * c + 2] = __float_as_uint(v[c].z) & 0xffffe000u; h[4 * c + 3] = __float_as_uint(v[c].w) & 0xffffe000u;
-        }
-        tmem_st32(ta, h);
-      }
-      if (p.passes == 3) {
-        uint32_t l[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x4 = v[c];
-          l[4 * c] = __float_as_uint(x4.x - __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u));
-          l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u));
-          l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u));
-          l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u));
-        }
-        tmem_st32(ta + 32, l);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&afull[slot]);
-    }
-  } else if (warp < NUM_LOADER_WARPS) {
-    // =============================================================== loaders (all 7 warps, or warps 0-2 when TA)
+  if (warp < NUM_LOADER_WARPS) {
+    // =============================================================== loaders
     // Software-pipelined: the global loads of window i+PF are in flight (registers) while window i is split and
     // stored to smem, so a loader thread never sits out a full L2/HBM round trip per window.
-    constexpr int PF = TA ? 2 : 3;
-    constexpr int LSTRIDE = TA ? TA_LOADERS * 4 : tc::LSTRIDE;                  // rows covered per pass of the loader threads
-    constexpr int LROWS = TA ? (128 + LSTRIDE - 1) / LSTRIDE : tc::LROWS;      // rows per loader thread
+    constexpr int PF = 3;
     const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes cover one 128-B row; rows rgrp + LSTRIDE*j (< 128)
     const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * p.nwin;                 // item = (tile, window)
     // ---- load cursor state
     int l_item = 0, l_widx = 0, l_b = 0, l_d = 0;
     int l_tile = blockIdx.x;
-    int hw0[LROWS];                         // (h + 1) << 16 | w of this thread's rows in the current tile (h >= -1)
+    int h0[LROWS], w0[LROWS];
     auto decode_tile = [&]() {
       const int slice = l_tile / p.tiles_per_slice, tt = l_tile - slice * p.tiles_per_slice;
       l_b = slice / p.D; l_d = slice - l_b * p.D;
@@ -154,7 +90,7 @@ conv_c32_tc_kernel(const Params p) {
       int h = floordiv(q, p.P), w = q - h * p.P;
 #pragma unroll
       for (int j = 0; j < LROWS; ++j) {  // rows rgrp + LSTRIDE*j: one division per tile, then increments
-        hw0[j] = ((h + 1) << 16) | w;
+        h0[j] = h; w0[j] = w;
         w += LSTRIDE;
         while (w >= p.P) { w -= p.P; ++h; }
       }
@@ -166,12 +102,11 @@ conv_c32_tc_kernel(const Params p) {
       const bool slice_ok = (unsigned)di < (unsigned)p.D;
 #pragma unroll
       for (int j = 0; j < LROWS; ++j) {
-        const int w0j = hw0[j] & 0xffff;
-        const int h = (hw0[j] >> 16) - 1 + (kh - 1) * p.dil;
-        const bool ok = slice_ok && rgrp + LSTRIDE * j < 128 && w0j < p.W && (unsigned)h < (unsigned)p.H;
+        const int h = h0[j] + (kh - 1) * p.dil;
+        const bool ok = slice_ok && rgrp + LSTRIDE * j < 128 && w0[j] < p.W && (unsigned)h < (unsigned)p.H;
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) v[j] = __ldcg(reinterpret_cast<const float4*>(
-                       p.x + ((((size_t)l_b * p.D + di) * p.H + h) * p.W + w0j) * 32 + chunk * 4));
+                       p.x + ((((size_t)l_b * p.D + di) * p.H + h) * p.W + w0[j]) * 32 + chunk * 4));
       }
       ++l_item;
       if (++l_widx == p.nwin) { l_widx = 0; l_tile += gridDim.x; }
@@ -188,22 +123,6 @@ conv_c32_tc_kernel(const Params p) {
 #pragma unroll
       for (int k = 0; k < PF; ++k) {
         if (item0 + k >= n_items) break;
-        if (TA) {
-          unsigned char* st = base + stage * A_BYTES;
-          t_wait += mbar_wait_timed<PROF>(&rempty[stage], phase ^ 1);
-          if (tid == 0 && stream_b) {                // B ring slot `stage`: free once the MMAs of 3 windows ago completed
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], 2 * B_BYTES);
-            bulk_g2s(base + BRING_OFF + stage * 2 * B_BYTES, p.wimg + (size_t)s_widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &full[stage]);
-          }
-#pragma unroll
-          for (int j = 0; j < LROWS; ++j) {
-            const int r = rgrp + LSTRIDE * j;
-            if (r < 128) *reinterpret_cast<float4*>(st + r * 128 + ((chunk ^ (r & 7)) << 4)) = v[k][j];
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&rfull[stage]);
-        } else {
         unsigned char* st = base + stage * STAGE_BYTES;
         t_wait += mbar_wait_timed<PROF>(&empty[stage], phase ^ 1);
         if (tid == 0) {
@@ -228,7 +147,6 @@ conv_c32_tc_kernel(const Params p) {
         fence_async_smem();            // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
-        }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         if (++s_widx == p.nwin) s_widx = 0;
         if (l_item < n_items) issue_loads(v[k]);   // refill this register slot with window item+PF
@@ -242,13 +160,12 @@ conv_c32_tc_kernel(const Params p) {
         if (lane == 0) {
           mbar_expect_tx(wbar, (uint32_t)p.nwin * 2 * B_BYTES);
           for (int w = 0; w < p.nwin; ++w)
-            bulk_g2s(TA ? base + BRING_OFF + w * 2 * B_BYTES : base + w * STAGE_BYTES + 2 * A_BYTES,
-                   p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, wbar);
+            bulk_g2s(base + w * STAGE_BYTES + 2 * A_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, wbar);
         }
         __syncwarp();
         mbar_wait_spin(wbar, 0);
       }
-      uint32_t stage = 0, phase = 0, wcount = 0;
+      uint32_t stage = 0, phase = 0;
       int it = 0;
       long long t_full = 0, t_tempty = 0; const long long t_begin = prof_clock<PROF>();
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -256,28 +173,8 @@ conv_c32_tc_kernel(const Params p) {
         const uint32_t accphase = (it / NACC) & 1;
         t_tempty += mbar_wait_timed<PROF>(&tempty[acc], accphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+        const uint32_t tmem_d = tmem_base + acc * 128;
         for (int widx = 0; widx < p.nwin; ++widx) {
-          if (TA) {
-            const uint32_t aslot = wcount & 1;
-            t_full += mbar_wait_timed<PROF>(&afull[aslot], (wcount >> 1) & 1);
-            if (stream_b) t_full += mbar_wait_timed<PROF>(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t ta = tmem_base + TA_BASE + aslot * 64;
-            const uint32_t sb = base_u32 + BRING_OFF + (stream_b ? stage : (uint32_t)widx) * 2 * B_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bh = make_desc(sb + ks * 32);
-              mma_tf32_ts(tmem_d, ta + ks * 8, bh, (widx | ks) != 0);
-              if (p.passes == 3) {
-                mma_tf32_ts(tmem_d, ta + 32 + ks * 8, bh, 1);
-                mma_tf32_ts(tmem_d, ta + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
-              }
-            }
-            mma_commit(&aempty[aslot]);
-            if (stream_b) mma_commit(&empty[stage]);
-            ++wcount;
-          } else {
           t_full += mbar_wait_timed<PROF>(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = base_u32 + stage * STAGE_BYTES;
@@ -292,7 +189,6 @@ conv_c32_tc_kernel(const Params p) {
             }
           }
           mma_commit(&empty[stage]);                 // smem slot reusable once these MMAs have read it
-          }
           if (widx == p.nwin - 1) mma_commit(&tfull[acc]);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -354,7 +250,7 @@ conv_c32_tc_kernel(const Params p) {
       t_tfull += mbar_wait_timed<PROF>(&tfull[acc], accphase);
       tc_fence_after();
       const long long tB = prof_clock<PROF>();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_STRIDE + half * 16;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 128 + half * 16;
       {
         float v0[16], v1[16], v2[16];
         tmem_ld16x3(taddr, taddr + 32, taddr + 64, v0, v1, v2);
@@ -464,7 +360,8 @@ static int tc_setup(const snb_conv_geom* g, tc::Params& p, const char* who) {
   return 0;
 }
 
-// 3-D default path: TMA producer + A operand in TMEM (conv3d_c32_tma.cu)
+// 3-D product path: TMA producer + A operand in TMEM (conv3d_c32_tma.cu).  This file keeps the loader-warp kernel: the 2-D
+// `flat` variant used by tests / A-B measurements, and the older 3-D kernel behind passes | 0x400.
 int snb_conv3d_tma_num_tiles(const snb_conv_geom* g);
 int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                           int passes, long long* dbg, void* stream);
@@ -510,11 +407,7 @@ static int conv_c32_tc_launch(const float* x, const float* wimg, float* y, const
     SNB_REQUIRE(!e->scale || e->shift, "snb_conv_c32_tc: scale without shift");
     return snb_conv3d_tma_launch(x, wimg, y, g, e, passes & 0xff, dbg, stream);
   }
-  SNB_REQUIRE(g->KD != 3 || e->stats == nullptr, "snb_conv_c32_tc: the legacy 3-D kernels (diagnostics) do not emit BN statistics");
-  // The flat-tiled kernel loads 9 windows per tile; with the A operand in TMEM only 3 warps are left to load them and the
-  // kernel becomes loader-bound (measured 113 us vs 72 us at KITTI size), so the smem-operand path stays the default here
-  // and passes | 0x200 selects the TMEM path for measurements.  (The 2-D walk kernel, 1 window per tile, defaults to TMEM.)
-  const bool legacy = (passes & 0x200) == 0;
+  SNB_REQUIRE(g->KD != 3 || e->stats == nullptr, "snb_conv_c32_tc: the loader-warp 3-D kernel (diagnostics) does not emit BN statistics");
   passes &= 0xff;
   SNB_REQUIRE(passes == 1 || passes == 3, "snb_conv_c32_tc: passes must be 1 or 3");
   SNB_REQUIRE(!e->scale || e->shift, "snb_conv_c32_tc: scale without shift");
@@ -523,12 +416,13 @@ static int conv_c32_tc_launch(const float* x, const float* wimg, float* y, const
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.ntiles < sms ? p.ntiles : sms;
-#define SNB_TC_GO(PROF_, TA_) do { \
-    SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<PROF_, TA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES)); \
-    tc::conv_c32_tc_kernel<PROF_, TA_><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p); } while (0)
-  if (dbg) { if (legacy) SNB_TC_GO(true, false); else SNB_TC_GO(true, true); }
-  else     { if (legacy) SNB_TC_GO(false, false); else SNB_TC_GO(false, true); }
-#undef SNB_TC_GO
+  if (dbg) {
+    SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    tc::conv_c32_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  } else {
+    SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    tc::conv_c32_tc_kernel<false><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  }
   SNB_LAUNCH_CHECK("conv_c32_tc_kernel");
   return 0;
 }

@@ -57,12 +57,6 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
 }
-// shared memory (128 rows x 32 bytes, described like an MMA operand) -> TMEM (128 lanes x 8 columns); asynchronous, ordered
-// with the tcgen05.mma / tcgen05.commit issued by the same thread
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
-  if (elect_one())
-  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" :: "r"(tmem_dst), "l"(sdesc) : "memory");
-}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   if (elect_one())
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");

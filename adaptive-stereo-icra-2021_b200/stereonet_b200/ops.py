@@ -129,7 +129,7 @@ def prep_conv_weights_tc(w, mode=0):
 
 
 def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
-                flat=False, a_smem=False, out=None, a_tmem=False, legacy3d=False):
+                flat=False, a_smem=False, out=None, legacy3d=False):
   """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.
   2-D inputs use the vertical-walk kernel (snb_conv2d_c32_tc) unless flat=True; 3-D inputs the flat-tiled one."""
   three_d = x.dim() == 5
@@ -153,10 +153,8 @@ def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lr
   e = ConvEpilogue(_p(bias), _p(scale), _p(shift), _p(residual), _p(stats), 1 if lrelu else 0)
   if a_smem and use2d:
     passes |= 0x100                      # diagnostics: 2-D kernel with the A operand from shared memory instead of TMEM
-  if three_d and (legacy3d or a_tmem):
-    passes |= 0x400                      # diagnostics: 3-D flat-tiled kernel with loader warps instead of the TMA kernel
-  if (not use2d) and a_tmem:
-    passes |= 0x200                      # diagnostics: flat kernel with the A operand from TMEM (default: shared memory)                      # diagnostics: A operand from shared memory instead of TMEM
+  if three_d and legacy3d:
+    passes |= 0x400                      # diagnostics: 3-D flat-tiled kernel with loader warps instead of the TMA kernel                      # diagnostics: A operand from shared memory instead of TMEM
   check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
   _count()
   return y, stats

@@ -83,8 +83,8 @@ SNB_API int snb_conv_c32(const float* x, const float* wprep, float* y, const snb
  * `stats` rows are indexed by this kernel's own tiles: snb_conv_c32_tc_num_tiles().
  * 3-D (KD = 3) runs conv3d_c32_tma.cu: one TMA tile load per (kd,kh) window of the un-padded flat index, converter warps
  * (hi/lo split -> tcgen05.st) and the A operand in TMEM; passes | 0x400 selects the older loader-warp kernel (no `stats`).
- * Diagnostics: passes | 0x200 feeds the A operand from TMEM (loader -> raw smem -> converter warps -> tcgen05.st) instead
- * of shared memory; slower for this flat-tiled kernel (9 windows per tile), default for the 2-D walk kernel. */
+ * (A TMEM-operand variant of the loader-warp kernel was measured and dropped: with 3 warps left to load 9 windows per tile it is
+ * loader-bound, 113 us vs 72 us.) */
 SNB_API int snb_conv_c32_tc(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                     int passes, void* stream);
 SNB_API int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g);

@@ -1,3 +1,4 @@
+# One GPU call: the whole `-m gpu` suite file by file, then a short bench.  Usage: gpurun -- 'bash scripts/gpu_check.sh'
 mkdir -p gpurun_out
 for f in test_gpu_kernels test_gpu_conv_tc test_gpu_wgrad_tc test_gpu_e2e test_gpu_backward; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q --tb=short -x > gpurun_out/$f.log 2>&1

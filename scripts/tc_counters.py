@@ -1,4 +1,5 @@
-"""Per-role cycle counters of the tensor-core conv kernel (diagnostics)."""
+"""Per-role cycle counters of the flat-tiled loader-warp conv kernel on a 2-D problem (diagnostics; the 2-D walk kernel:
+tc2d_counters.py, the 3-D TMA kernel: tc3_counters.py)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "adaptive-stereo-icra-2021_b200"))
@@ -23,5 +24,3 @@ def run(tag, x, w, g, residual, passes):
 for passes in (3, 1):
   x2 = torch.randn(1, 376, 1248, 32, device=dev)
   run("2d dil1", x2, torch.randn(32, 32, 3, 3, device=dev) * 0.1, ops.geom((1, 376, 1248, 32), 3, dil=1), True, passes)
-  x3 = torch.randn(1, 24, 47, 156, 32, device=dev)
-  run("3d", x3, torch.randn(32, 32, 3, 3, 3, device=dev) * 0.05, ops.geom((1, 24, 47, 156, 32), 3), False, passes)
