@@ -362,6 +362,7 @@ conv2d_c32_tc_kernel(const Params2 p) {
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bias4;
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
+    const float slope = e.lrelu ? SNB_LRELU_SLOPE : 1.f;
     long long tcount = 0;
     long long t_tfull = 0, t_pre = 0, t_tmem = 0, t_out = 0, t_bar = 0; const long long t_ebegin = prof_clock<PROF>();
     for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
@@ -381,12 +382,10 @@ conv2d_c32_tc_kernel(const Params2 p) {
           okr[jj] = r >= p.dil && r < 128 - p.dil && (unsigned)xs[jj] < (unsigned)p.W;
         }
         float4 res[4];
-        if (has_res) {
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            res[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (okr[jj]) res[jj] = __ldcg(reinterpret_cast<const float4*>(e.residual + (rowbase + xs[jj]) * 32 + chunk * 4));
-          }
+        for (int jj = 0; jj < 4; ++jj) {
+          res[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && okr[jj]) res[jj] = __ldcg(reinterpret_cast<const float4*>(e.residual + (rowbase + xs[jj]) * 32 + chunk * 4));
         }
         t_pre += prof_clock<PROF>() - tA;
         t_tfull += mbar_wait_timed<PROF>(&tfull[slot], accphase);
@@ -411,25 +410,37 @@ conv2d_c32_tc_kernel(const Params2 p) {
         t_tmem += prof_clock<PROF>() - tB;
         { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }
         const long long tC = prof_clock<PROF>();
+        // Straight-line pointwise chain: absent stages are identities (scale 1 / shift 0, LeakyReLU slope 1, residual 0, stats
+        // weight 0), so a tile costs no data-dependent branches — only the final store is predicated.
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 o[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {       // branch-free: out-of-range rows read clamped smem rows and skip only the store
+        for (int jj = 0; jj < 4; ++jj) {
           const int r = rg + 32 * jj;
           const int r0 = max(r - p.dil, 0), r2 = min(r + p.dil, 127);
           const float4 a = *reinterpret_cast<const float4*>(sY + r0 * 32 + ((chunk ^ (r0 & 7)) << 2));
           const float4 b = *reinterpret_cast<const float4*>(sY + 128 * 32 + r * 32 + ((chunk ^ (r & 7)) << 2));
           const float4 c = *reinterpret_cast<const float4*>(sY + 2 * 128 * 32 + r2 * 32 + ((chunk ^ (r2 & 7)) << 2));
-          float4 o;
-          o.x = (a.x + b.x) + c.x + bias4.x; o.y = (a.y + b.y) + c.y + bias4.y;
-          o.z = (a.z + b.z) + c.z + bias4.z; o.w = (a.w + b.w) + c.w + bias4.w;
-          if (has_stats && okr[jj]) {
-            s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
-            s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+          o[jj].x = (a.x + b.x) + c.x + bias4.x; o[jj].y = (a.y + b.y) + c.y + bias4.y;
+          o[jj].z = (a.z + b.z) + c.z + bias4.z; o[jj].w = (a.w + b.w) + c.w + bias4.w;
+        }
+        if (has_stats) {                       // one warp-uniform branch per tile (train-mode BN only)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float wst = okr[jj] ? 1.f : 0.f;
+            const float ox = o[jj].x * wst, oy = o[jj].y * wst, oz = o[jj].z * wst, ow = o[jj].w * wst;
+            s1[0] += ox; s1[1] += oy; s1[2] += oz; s1[3] += ow;
+            s2[0] = fmaf(ox, o[jj].x, s2[0]); s2[1] = fmaf(oy, o[jj].y, s2[1]); s2[2] = fmaf(oz, o[jj].z, s2[2]); s2[3] = fmaf(ow, o[jj].w, s2[3]);
           }
-          if (e.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
-          if (e.lrelu) { o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w); }
-          if (has_res) { o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w; }
-          if (okr[jj]) __stcg(reinterpret_cast<float4*>(p.y + (rowbase + xs[jj]) * 32 + chunk * 4), o);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float4 v = o[jj];
+          v.x = fmaf(v.x, sc4.x, sh4.x); v.y = fmaf(v.y, sc4.y, sh4.y); v.z = fmaf(v.z, sc4.z, sh4.z); v.w = fmaf(v.w, sc4.w, sh4.w);
+          v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+          v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+          v.x += res[jj].x; v.y += res[jj].y; v.z += res[jj].z; v.w += res[jj].w;
+          if (okr[jj]) __stcg(reinterpret_cast<float4*>(p.y + (rowbase + xs[jj]) * 32 + chunk * 4), v);
         }
         if (has_stats) {      // stats row = (image row, column block): [(b*H + h)*ncb + cb][2][32]
 #pragma unroll
