@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 bn_lrelu_bwd_reduce_kernel(const float4* __restrict__ z, const float4* __restrict__ dy, const float* __restrict__ scale,
                            const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                            float* __restrict__ partial, long long n4, int do_lrelu) {
+  pdl_launch(); pdl_wait();
   __shared__ float red[2][256][4];
   const int t = threadIdx.x, ch = t & 7;                    // this thread always sees channels 4*ch .. 4*ch+3
   const float4 sc = reinterpret_cast<const float4*>(scale)[ch], sh = reinterpret_cast<const float4*>(shift)[ch];
@@ -50,6 +51,7 @@ bn_lrelu_bwd_apply_kernel(const float4* __restrict__ z, const float4* __restrict
                           const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ sums, float inv_count, int train, int do_lrelu,
                           float4* __restrict__ dz, float* __restrict__ dzpart, long long n4) {
+  pdl_launch(); pdl_wait();
   __shared__ float red[256][4];
   const int t = threadIdx.x, ch = t & 7;
   const float4 sc = reinterpret_cast<const float4*>(scale)[ch], sh = reinterpret_cast<const float4*>(shift)[ch];
@@ -89,6 +91,7 @@ bn_lrelu_bwd_apply_kernel(const float4* __restrict__ z, const float4* __restrict
 // taps > 0: the row is a [taps][32 ci][32 co] weight-gradient block and is written in PyTorch's [co][ci][taps] layout.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int n, int len, float* __restrict__ out, float mul, int taps) {
+  pdl_launch(); pdl_wait();
   __shared__ double red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -110,6 +113,7 @@ reduce_partials_kernel(const float* __restrict__ partial, int n, int len, float*
 // Here a block owns 4 columns and 64 row lanes (4 independent accumulators each), then a fixed-order tree -> deterministic.
 __global__ void __launch_bounds__(256)
 reduce_partials_narrow_kernel(const float* __restrict__ partial, int n, int len, float* __restrict__ out, float mul) {
+  pdl_launch(); pdl_wait();
   __shared__ double red[64][4];
   const int c = threadIdx.x & 3, r = threadIdx.x >> 2;
   const int j = blockIdx.x * 4 + c;
@@ -134,6 +138,7 @@ reduce_partials_narrow_kernel(const float* __restrict__ partial, int n, int len,
 // per-channel column sums of a [npos][32] tensor -> partial[blk][32]
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const float4* __restrict__ x, float* __restrict__ partial, long long n4) {
+  pdl_launch(); pdl_wait();
   __shared__ float red[256][4];
   const int t = threadIdx.x;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -183,6 +188,7 @@ __device__ __forceinline__ void wgrad_load_x(SmemWgrad& s, int buf, const float*
 __global__ void __launch_bounds__(256)
 conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ partial,
                       snb_conv_geom g, long long npos, int chunks_per_cta) {
+  pdl_launch(); pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemWgrad& s = *reinterpret_cast<SmemWgrad*>(smem_raw);
   float* sAcc = reinterpret_cast<float*>(smem_raw + sizeof(SmemWgrad));     // [taps][32 ci][32 co]
@@ -279,6 +285,7 @@ conv_c32_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
 __global__ void __launch_bounds__(256)
 softargmin_bwd_kernel(const float* __restrict__ cost, const float* __restrict__ pred, const float* __restrict__ dpred,
                       const float* __restrict__ extra, float* __restrict__ dcost, int D, long long plane, long long total) {
+  pdl_launch(); pdl_wait();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;     // over B*H*W
   if (i >= total) return;
   const long long b = i / plane, q = i - b * plane;
@@ -299,6 +306,7 @@ softargmin_bwd_kernel(const float* __restrict__ cost, const float* __restrict__ 
 // dres = dout * (out > 0)    (ReLU of stereo_net.py:121)
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ dres, long long n) {
+  pdl_launch(); pdl_wait();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < n) dres[i] = out[i] > 0.f ? dout[i] : 0.f;
 }
@@ -313,6 +321,7 @@ template <int NT>
 __global__ void __launch_bounds__(128)
 conv_c32_taps_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g,
                          float* __restrict__ dx, float* __restrict__ partial, long long npos, int D, int H, int W) {
+  pdl_launch(); pdl_wait();
   constexpr int NTP = NT + 1;
   __shared__ __align__(16) float sX[128][32];
   __shared__ float sG[128][NTP];
@@ -407,7 +416,7 @@ extern "C" int snb_bn_lrelu_bwd_reduce(const float* z, const float* dy, const fl
                                        const float* invstd, float* partial, long long npos, int lrelu_flag, void* stream) {
   SNB_REQUIRE(z && dy && scale && shift && mean && invstd && partial && npos > 0, "snb_bn_lrelu_bwd_reduce: bad args");
   const long long n4 = npos * 8;
-  bn_lrelu_bwd_reduce_kernel<<<grid_for(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)z, (const float4*)dy, scale, shift, mean,
+  snb_launch(bn_lrelu_bwd_reduce_kernel, grid_for(n4), 256, 0, stream, (const float4*)z, (const float4*)dy, scale, shift, mean,
                                                                             invstd, partial, n4, lrelu_flag);
   SNB_LAUNCH_CHECK("bn_lrelu_bwd_reduce_kernel");
   return 0;
@@ -418,7 +427,7 @@ extern "C" int snb_bn_lrelu_bwd_apply(const float* z, const float* dy, const flo
                                       float* dz, float* dzpart, void* stream) {
   SNB_REQUIRE(z && dy && scale && shift && mean && invstd && sums && dz && dzpart && npos > 0, "snb_bn_lrelu_bwd_apply: bad args");
   const long long n4 = npos * 8;
-  bn_lrelu_bwd_apply_kernel<<<grid_for(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)z, (const float4*)dy, scale, shift, mean,
+  snb_launch(bn_lrelu_bwd_apply_kernel, grid_for(n4), 256, 0, stream, (const float4*)z, (const float4*)dy, scale, shift, mean,
                                                                            invstd, sums, 1.0f / (float)npos, train, lrelu_flag,
                                                                            (float4*)dz, dzpart, n4);
   SNB_LAUNCH_CHECK("bn_lrelu_bwd_apply_kernel");
@@ -428,16 +437,16 @@ extern "C" int snb_bn_lrelu_bwd_apply(const float* z, const float* dy, const flo
 extern "C" int snb_reduce_partials(const float* partial, int n, int len, float* out, float mul, void* stream) {
   SNB_REQUIRE(partial && out && n > 0 && len > 0, "snb_reduce_partials: bad args");
   if (len <= 512 && n >= 64)
-    reduce_partials_narrow_kernel<<<snb_ceil_div(len, 4), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul);
+    snb_launch(reduce_partials_narrow_kernel, snb_ceil_div(len, 4), 256, 0, stream, partial, n, len, out, mul);
   else
-    reduce_partials_kernel<<<snb_ceil_div(len, 32), 256, 0, (cudaStream_t)stream>>>(partial, n, len, out, mul, 0);
+    snb_launch(reduce_partials_kernel, snb_ceil_div(len, 32), 256, 0, stream, partial, n, len, out, mul, 0);
   SNB_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
 
 extern "C" int snb_reduce_wgrad_partials(const float* partial, int n, int taps, float* out, void* stream) {
   SNB_REQUIRE(partial && out && n > 0 && taps > 0, "snb_reduce_wgrad_partials: bad args");
-  reduce_partials_kernel<<<taps * 32, 256, 0, (cudaStream_t)stream>>>(partial, n, taps * 1024, out, 1.0f, taps);
+  snb_launch(reduce_partials_kernel, taps * 32, 256, 0, stream, partial, n, taps * 1024, out, 1.0f, taps);
   SNB_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
@@ -445,7 +454,7 @@ extern "C" int snb_reduce_wgrad_partials(const float* partial, int n, int taps, 
 extern "C" int snb_channel_sum(const float* x, float* partial, long long npos, void* stream) {
   SNB_REQUIRE(x && partial && npos > 0, "snb_channel_sum: bad args");
   const long long n4 = npos * 8;
-  channel_sum_kernel<<<grid_for(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, partial, n4);
+  snb_launch(channel_sum_kernel, grid_for(n4), 256, 0, stream, (const float4*)x, partial, n4);
   SNB_LAUNCH_CHECK("channel_sum_kernel");
   return 0;
 }
@@ -478,7 +487,7 @@ extern "C" int snb_conv_c32_wgrad(const float* x, const float* dz, float* partia
   const int smem = (int)(sizeof(SmemWgrad) + (size_t)ntaps * 4096);
   SNB_REQUIRE(smem <= 227 * 1024, "snb_conv_c32_wgrad: too many taps for shared memory");
   SNB_CUDA(cudaFuncSetAttribute(conv_c32_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv_c32_wgrad_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(x, dz, partial, *g, npos, per);
+  snb_launch(conv_c32_wgrad_kernel, ctas, 256, smem, stream, x, dz, partial, *g, npos, per);
   SNB_LAUNCH_CHECK("conv_c32_wgrad_kernel");
   return 0;
 }
@@ -487,14 +496,14 @@ extern "C" int snb_softargmin_bwd(const float* cost, const float* pred, const fl
                                   int B, int D, int H, int W, void* stream) {
   SNB_REQUIRE(cost && pred && dcost && B > 0 && D > 0 && H > 0 && W > 0, "snb_softargmin_bwd: bad args");
   const long long plane = (long long)H * W, total = plane * B;
-  softargmin_bwd_kernel<<<snb_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(cost, pred, dpred, dcost_extra, dcost, D, plane, total);
+  snb_launch(softargmin_bwd_kernel, snb_ceil_div(total, 256), 256, 0, stream, cost, pred, dpred, dcost_extra, dcost, D, plane, total);
   SNB_LAUNCH_CHECK("softargmin_bwd_kernel");
   return 0;
 }
 
 extern "C" int snb_relu_bwd(const float* out, const float* dout, float* dres, long long n, void* stream) {
   SNB_REQUIRE(out && dout && dres && n > 0, "snb_relu_bwd: bad args");
-  relu_bwd_kernel<<<snb_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(out, dout, dres, n);
+  snb_launch(relu_bwd_kernel, snb_ceil_div(n, 256), 256, 0, stream, out, dout, dres, n);
   SNB_LAUNCH_CHECK("relu_bwd_kernel");
   return 0;
 }
@@ -505,8 +514,8 @@ extern "C" int snb_conv_c32_taps_bwd(const float* x, const float* w, const float
   SNB_REQUIRE((ntaps == 27) || (ntaps == 9 && D == 1), "snb_conv_c32_taps_bwd: ntaps must be 27 (3-D) or 9 (2-D, D = 1)");
   const long long npos = (long long)B * D * H * W;
   const int grid = snb_ceil_div(npos, 128);
-  if (ntaps == 27) conv_c32_taps_bwd_kernel<27><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w, g, dx, partial, npos, D, H, W);
-  else             conv_c32_taps_bwd_kernel<9><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w, g, dx, partial, npos, D, H, W);
+  if (ntaps == 27) snb_launch(conv_c32_taps_bwd_kernel<27>, grid, 128, 0, stream, x, w, g, dx, partial, npos, D, H, W);
+  else             snb_launch(conv_c32_taps_bwd_kernel<9>, grid, 128, 0, stream, x, w, g, dx, partial, npos, D, H, W);
   SNB_LAUNCH_CHECK("conv_c32_taps_bwd_kernel");
   return 0;
 }

@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
                    float* scale, float* shift, float* mean_out, float* invstd_out) {
+  pdl_launch(); pdl_wait();
   __shared__ double red[16][64];
   const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;          // 4 independent chains: the loop is bound by the fp64 add latency
@@ -47,6 +48,7 @@ bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, co
 // block at full resolution) is bound by one SM's load bandwidth: 12-23 us per layer, 23 layers per adaptation step.
 __global__ void __launch_bounds__(256)
 bn_stats_prereduce_kernel(const float* __restrict__ stats, int ntiles, int chunk, float* __restrict__ scratch) {
+  pdl_launch(); pdl_wait();
   __shared__ double red[4][64];
   const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
   const int lo = blockIdx.x * chunk, hi = min(lo + chunk, ntiles);
@@ -60,6 +62,7 @@ bn_stats_prereduce_kernel(const float* __restrict__ stats, int ntiles, int chunk
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                 const float4* __restrict__ residual, float4* __restrict__ y, long long n4, int do_lrelu) {
+  pdl_launch(); pdl_wait();
   __shared__ float4 sSc[8], sSh[8];
   if (threadIdx.x < 8) {
     sSc[threadIdx.x] = reinterpret_cast<const float4*>(scale)[threadIdx.x];
@@ -83,7 +86,7 @@ extern "C" int snb_bn_finalize(const float* stats, int ntiles, long long count, 
                                float* scale, float* shift, float* mean, float* invstd, void* stream) {
   SNB_REQUIRE(stats && gamma && beta && scale && shift && ntiles > 0 && count > 0, "snb_bn_finalize: bad args");
   SNB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "snb_bn_finalize: running stats must come in pairs");
-  bn_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats, ntiles, (double)count, gamma, beta, running_mean, running_var,
+  snb_launch(bn_finalize_kernel, 1, 1024, 0, stream, stats, ntiles, (double)count, gamma, beta, running_mean, running_var,
                                                            momentum, eps, scale, shift, mean, invstd);
   SNB_LAUNCH_CHECK("bn_finalize_kernel");
   return 0;
@@ -97,7 +100,7 @@ extern "C" int snb_bn_finalize_ws(const float* stats, int ntiles, long long coun
     return snb_bn_finalize(stats, ntiles, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, stream);
   SNB_REQUIRE(stats && gamma && beta && scale && shift && count > 0, "snb_bn_finalize_ws: bad args");
   const int nblk = 64, chunk = (ntiles + nblk - 1) / nblk;
-  bn_stats_prereduce_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(stats, ntiles, chunk, scratch);
+  snb_launch(bn_stats_prereduce_kernel, nblk, 256, 0, stream, stats, ntiles, chunk, scratch);
   SNB_LAUNCH_CHECK("bn_stats_prereduce_kernel");
   return snb_bn_finalize(scratch, nblk, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, stream);
 }
@@ -108,7 +111,7 @@ extern "C" int snb_bn_apply(const float* z, const float* scale, const float* shi
   const long long n4 = npos * 8;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_apply_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)z, scale, shift, (const float4*)residual,
+  snb_launch(bn_apply_kernel, (int)blocks, 256, 0, stream, (const float4*)z, scale, shift, (const float4*)residual,
                                                                 (float4*)y, n4, lrelu_flag);
   SNB_LAUNCH_CHECK("bn_apply_kernel");
   return 0;

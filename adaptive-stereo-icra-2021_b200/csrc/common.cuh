@@ -16,6 +16,28 @@ int snb_fail(const char* fmt, ...);
 #define SNB_CUDA(call) do { cudaError_t _e = (call); \
   if (_e != cudaSuccess) return snb_fail("%s: %s", #call, cudaGetErrorString(_e)); } while (0)
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and starts with pdl_launch() (lets the NEXT kernel's CTAs be scheduled as soon as all CTAs of this
+// one have started and SM resources free up) followed — before it touches any global memory — by pdl_wait() (blocks until the
+// PREVIOUS kernel has completed and its writes are visible).  Correctness is the plain stream order; what is gained is the
+// launch latency / ramp-up of kernel N+1 overlapping the tail of kernel N (34 dependent launches per forward, ~390 per
+// adaptation step).  SNB200_PDL=0 launches without the attribute (both instructions are then no-ops).
+bool snb_pdl_enabled();
+template <class... KA, class... A>
+static inline void snb_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, void* stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = snb_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);     // errors are picked up by SNB_LAUNCH_CHECK
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+#endif
+
 static inline int snb_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- small device helpers

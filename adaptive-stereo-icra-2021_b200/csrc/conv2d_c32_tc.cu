@@ -55,6 +55,7 @@ __device__ __forceinline__ Strip decode_strip(const Params2& p, int sid) {
 template <bool TA, bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv2d_c32_tc_kernel(const Params2 p) {
+  pdl_launch();
   constexpr int ACC_STRIDE = TA ? 96 : 128;
   constexpr int TA_BASE = NACC * 96;
   constexpr int TA_LOADERS = 3;              // TA: warps 0-2 load, warps 3-6 convert (one per TMEM lane quadrant)
@@ -92,6 +93,7 @@ conv2d_c32_tc_kernel(const Params2 p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // everything above touched no global memory
 
   if (TA && warp < TA_LOADERS) {
     // =============================================================== TA loaders (warps 0-2): coalesced LDG.128 -> raw fp32 window in
@@ -180,8 +182,8 @@ conv2d_c32_tc_kernel(const Params2 p) {
         uint32_t h[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          h[4 * c] = __float_as_uint(v[c].x) & 0xffffe000u; h[4 * c + 1] = __float_as_uint(v[c].y) & 0xffffe000u;
-          h[4 * c + 2] = __float_as_uint(v[c].z) & 0xffffe000u; h[4 * c + 3] = __float_as_uint(v[c].w) & 0xffffe000u;
+          h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
+          h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
         }
         tmem_st32(ta, h);
       }
@@ -190,10 +192,10 @@ conv2d_c32_tc_kernel(const Params2 p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 x4 = v[c];
-          l[4 * c] = __float_as_uint(x4.x - __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u));
-          l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u));
-          l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u));
-          l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u));
+          l[4 * c] = __float_as_uint(x4.x - __uint_as_float(tc::tf32_hi_bits(x4.x)));
+          l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(tc::tf32_hi_bits(x4.y)));
+          l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(tc::tf32_hi_bits(x4.z)));
+          l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(tc::tf32_hi_bits(x4.w)));
         }
         tmem_st32(ta + 32, l);
       }
@@ -534,7 +536,7 @@ extern "C" int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, floa
 template <bool TA, bool PROF>
 static int conv2d_tc_go(const tc2d::Params2& p, int grid, void* stream) {
   SNB_CUDA(cudaFuncSetAttribute(tc2d::conv2d_c32_tc_kernel<TA, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2d::SMEM_BYTES2));
-  tc2d::conv2d_c32_tc_kernel<TA, PROF><<<grid, tc::NTHREADS, tc2d::SMEM_BYTES2, (cudaStream_t)stream>>>(p);
+  snb_launch(tc2d::conv2d_c32_tc_kernel<TA, PROF>, grid, tc::NTHREADS, tc2d::SMEM_BYTES2, stream, p);
   SNB_LAUNCH_CHECK("conv2d_c32_tc_kernel");
   return 0;
 }

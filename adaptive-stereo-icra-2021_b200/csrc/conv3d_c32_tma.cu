@@ -53,6 +53,7 @@ __device__ __forceinline__ void epi_bar3() { asm volatile("bar.sync 1, 256;\n" :
 
 __global__ void __launch_bounds__(NTHREADS3, 1)
 conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p) {
+  pdl_launch();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -88,6 +89,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // everything above touched no global memory
   const int HW = p.H * p.W;
 
   if (warp == 0) {
@@ -200,8 +202,8 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
           uint32_t h[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            h[4 * c] = __float_as_uint(v[c].x) & 0xffffe000u; h[4 * c + 1] = __float_as_uint(v[c].y) & 0xffffe000u;
-            h[4 * c + 2] = __float_as_uint(v[c].z) & 0xffffe000u; h[4 * c + 3] = __float_as_uint(v[c].w) & 0xffffe000u;
+            h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
+            h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
           }
           tmem_st32(ta, h);
         }
@@ -210,10 +212,10 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 x4 = v[c];
-            l[4 * c] = __float_as_uint(x4.x - __uint_as_float(__float_as_uint(x4.x) & 0xffffe000u));
-            l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(__float_as_uint(x4.y) & 0xffffe000u));
-            l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(__float_as_uint(x4.z) & 0xffffe000u));
-            l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(__float_as_uint(x4.w) & 0xffffe000u));
+            l[4 * c] = __float_as_uint(x4.x - __uint_as_float(tc::tf32_hi_bits(x4.x)));
+            l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(tc::tf32_hi_bits(x4.y)));
+            l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(tc::tf32_hi_bits(x4.z)));
+            l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(tc::tf32_hi_bits(x4.w)));
           }
           tmem_st32(ta + 32, l);
         }
@@ -411,7 +413,7 @@ int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nsuper < sms ? p.nsuper : sms;
   SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
-  tc3::conv3d_c32_tma_kernel<<<grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, (cudaStream_t)stream>>>(tmap, p);
+  snb_launch(tc3::conv3d_c32_tma_kernel, grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
   SNB_LAUNCH_CHECK("conv3d_c32_tma_kernel");
   return 0;
 }

@@ -55,6 +55,7 @@ __device__ __forceinline__ void load_tap(SmemC32& s, int stage, const float* __r
 __global__ void __launch_bounds__(NTHREADS)
 conv_c32_ffma_kernel(const float* __restrict__ x, const float* __restrict__ wprep, float* __restrict__ y,
                      snb_conv_geom g, snb_conv_epilogue e, long long npos) {
+  pdl_launch(); pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemC32& s = *reinterpret_cast<SmemC32*>(smem_raw);
   const int t = threadIdx.x;
@@ -165,6 +166,7 @@ conv_c32_ffma_kernel(const float* __restrict__ x, const float* __restrict__ wpre
 }
 
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin, int taps, int mode) {
+  pdl_launch(); pdl_wait();
   const int n = cout * cin * taps;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int t = i % taps;
@@ -199,7 +201,7 @@ extern "C" int snb_conv_c32(const float* x, const float* wprep, float* y, const 
   const int ntiles = snb_ceil_div(npos, TILE_M);
   const int smem = (int)sizeof(SmemC32);
   SNB_CUDA(cudaFuncSetAttribute(conv_c32_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv_c32_ffma_kernel<<<ntiles, NTHREADS, smem, (cudaStream_t)stream>>>(x, wprep, y, *g, *e, npos);
+  snb_launch(conv_c32_ffma_kernel, ntiles, NTHREADS, smem, stream, x, wprep, y, *g, *e, npos);
   SNB_LAUNCH_CHECK("conv_c32_ffma_kernel");
   return 0;
 }
@@ -207,7 +209,7 @@ extern "C" int snb_conv_c32(const float* x, const float* wprep, float* y, const 
 extern "C" int snb_prep_conv_weights(const float* w, float* out, int cout, int cin, int taps, int mode, void* stream) {
   SNB_REQUIRE(w && out && cout > 0 && cin > 0 && taps > 0 && mode >= 0 && mode <= 2, "snb_prep_conv_weights: bad args");
   const int n = cout * cin * taps;
-  prep_weights_kernel<<<snb_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, out, cout, cin, taps, mode);
+  snb_launch(prep_weights_kernel, snb_ceil_div(n, 256), 256, 0, stream, w, out, cout, cin, taps, mode);
   SNB_LAUNCH_CHECK("prep_weights_kernel");
   return 0;
 }

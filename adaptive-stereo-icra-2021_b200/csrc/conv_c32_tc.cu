@@ -39,6 +39,7 @@ struct Params {
 template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_c32_tc_kernel(const Params p) {
+  pdl_launch();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -70,6 +71,7 @@ conv_c32_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // everything above touched no global memory
 
   if (warp < NUM_LOADER_WARPS) {
     // =============================================================== loaders
@@ -324,6 +326,7 @@ conv_c32_tc_kernel(const Params p) {
 // w [32 cout][32 cin][kd*kh*kw taps] -> per (kd,kh) window: B_hi[n = kw*32 + cout][k = cin] then B_lo, each in the
 // SWIZZLE_128B K-major smem image (row n = 128 B, 16-B chunk c stored at c ^ (n & 7)).  mode 1: data-gradient weights.
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int nwin, int mode) {
+  pdl_launch(); pdl_wait();
   const int taps = nwin * 3;
   const int total = nwin * 96 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -335,7 +338,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
     float v;
     if (mode == 0) v = w[((size_t)co * 32 + k) * taps + tap];
     else           v = w[((size_t)k * 32 + co) * taps + (taps - 1 - tap)];   // dgrad: swap channels, flip taps
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const float hi = __uint_as_float(tc::tf32_hi_bits(v));
     const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
     out[o] = hi;
     out[o + B_BYTES / 4] = v - hi;
@@ -378,7 +381,7 @@ extern "C" int snb_conv_weights_tc_floats(int kd) { return kd * 3 * tc::WIMG_FLO
 extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream) {
   SNB_REQUIRE(w && out && (kd == 1 || kd == 3) && (mode == 0 || mode == 1), "snb_prep_conv_weights_tc: bad args");
   const int nwin = kd * 3;
-  tc::prep_weights_tc_kernel<<<snb_ceil_div(nwin * 96 * 32, 256), 256, 0, (cudaStream_t)stream>>>(w, out, nwin, mode);
+  snb_launch(tc::prep_weights_tc_kernel, snb_ceil_div(nwin * 96 * 32, 256), 256, 0, stream, w, out, nwin, mode);
   SNB_LAUNCH_CHECK("prep_weights_tc_kernel");
   return 0;
 }
@@ -418,10 +421,10 @@ static int conv_c32_tc_launch(const float* x, const float* wimg, float* y, const
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   if (dbg) {
     SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    tc::conv_c32_tc_kernel<true><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    snb_launch(tc::conv_c32_tc_kernel<true>, grid, tc::NTHREADS, tc::SMEM_BYTES, stream, p);
   } else {
     SNB_CUDA(cudaFuncSetAttribute(tc::conv_c32_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    tc::conv_c32_tc_kernel<false><<<grid, tc::NTHREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    snb_launch(tc::conv_c32_tc_kernel<false>, grid, tc::NTHREADS, tc::SMEM_BYTES, stream, p);
   }
   SNB_LAUNCH_CHECK("conv_c32_tc_kernel");
   return 0;

@@ -93,6 +93,7 @@ __device__ __forceinline__ void mma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uin
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_c32_wgrad_tc_kernel(const WParams p) {
+  pdl_launch();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -127,6 +128,7 @@ conv_c32_wgrad_tc_kernel(const WParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // everything above touched no global memory
 
   if (warp < LW) {
     // =============================================================== loaders
@@ -434,7 +436,7 @@ static int wgtc_launch(const float* x, const float* dz, float* partial, const sn
   SNB_REQUIRE(passes == 1 || passes == 3, "snb_conv_c32_wgrad_tc: passes must be 1 or 3");
   p.x = x; p.dz = dz; p.partial = partial; p.passes = passes; p.dbg = dbg;
   SNB_CUDA(cudaFuncSetAttribute(wg::conv_c32_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  wg::conv_c32_wgrad_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(p);
+  snb_launch(wg::conv_c32_wgrad_tc_kernel, grid, tc::NTHREADS, smem, stream, p);
   SNB_LAUNCH_CHECK("conv_c32_wgrad_tc_kernel");
   return 0;
 }

@@ -58,6 +58,7 @@ template <int CIN, int KS, int S, class Loader>
 __global__ void __launch_bounds__(256)
 conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y, float* __restrict__ up_out,
                   int OH, int OW, int pad, snb_conv_epilogue e, int phaseB) {
+  pdl_launch(); pdl_wait();
   using T = TileDims<CIN, KS, S>;
   extern __shared__ __align__(16) float smem[];
   float* sIn = smem;
@@ -276,7 +277,7 @@ __device__ __forceinline__ void build_a_chunk(const float* __restrict__ px, uint
   for (int j = 0; j < N; ++j) {
     const int k = K0 + j;
     const float x = (k < D::K) ? px[D::in_off(k < D::K ? k : 0)] : 0.f;
-    h[j] = __float_as_uint(x) & 0xffffe000u;
+    h[j] = tc::tf32_hi_bits(x);
     l[j] = __float_as_uint(x - __uint_as_float(h[j]));
   }
   tmem_st_n<N>(ta + K0, h);
@@ -310,6 +311,7 @@ template <int CIN, int KS, int S, class Loader>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y, float* __restrict__ up_out,
                      int OH, int OW, int pad, snb_conv_epilogue e, int phaseB) {
+  pdl_launch();
   using T = TileDims<CIN, KS, S>;
   using D = TcDims<CIN, KS, S>;
   constexpr int NMT = TH * TW / 128;                 // 4 M-tiles of 2 rows x 64 pixels
@@ -332,12 +334,13 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
   const int oy0 = (trem / tiles_x) * TH, ox0 = (trem % tiles_x) * TW;
   const int iy0 = oy0 * S - pad, ix0 = ox0 * S - pad;
 
-#ifdef SNB_SMALL_DBG
-  long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long dbg_c = clock64(); const long long dbg_start = dbg_c;
-#define DBG_MARK(i) do { const long long _n = clock64(); dbg_t[i] += _n - dbg_c; dbg_c = _n; } while (0)
-#else
-#define DBG_MARK(i) do { } while (0)
-#endif
+  if (warp == 8) {
+    if (lane == 0) { mbar_init(mma_done, 1); mbar_init(a_full, 8); mbar_fence_init(); }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  pdl_wait();                                        // nothing above touched global memory
   {  // input halo tile, one row per warp at a time (no per-element index arithmetic: this kernel is instruction-issue bound).
      // Plain image channels go global -> smem with 4-byte cp.async (everything in flight at once, zero fill outside the
      // image); computed channels (the bilinear disparity plane of the refinement) go through registers.
@@ -368,13 +371,6 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
     }
     cp_async_commit();
   }
-  DBG_MARK(0);
-  if (warp == 8) {
-    if (lane == 0) { mbar_init(mma_done, 1); mbar_init(a_full, 8); mbar_fence_init(); }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
   {  // weight image: w is [32][K] (PyTorch [co][ci][kh][kw]) = K-major rows of the B operand; zero padded to KPB
     constexpr int NJ = D::KPB / 32;
     for (int co = warp; co < 32; co += TC_THREADS / 32) {
@@ -383,22 +379,19 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
       for (int j = 0; j < NJ; ++j) { const int k = lane + 32 * j; v[j] = k < D::K ? __ldg(w + co * D::K + k) : 0.f; }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const float hi = __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
+        const float hi = __uint_as_float(tc::tf32_hi_bits(v[j]));
         const int o = j * 1024 + co * 32 + (((lane >> 2) ^ (co & 7)) << 2) + (lane & 3);
         sB[o] = hi;
         sB[D::KPB * 32 + o] = v[j] - hi;
       }
     }
   }
-  DBG_MARK(1);
   cp_async_wait<0>();
-  DBG_MARK(2);
   tc::fence_async_smem();                            // generic-proxy smem writes -> visible to the MMA's async-proxy reads
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  DBG_MARK(3);
 
   if (warp == 8) {
     // =============================================================== MMA issuer (converged warp, one election per M-tile)
@@ -476,7 +469,6 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
 
     for (int mt = 0; mt < NMT; ++mt) {
       if (mt > 0) { tc::mbar_wait(mma_done, (mt - 1) & 1); tc::tc_fence_after(); }   // MMAs of mt-1 done: A slot free, accumulator ready
-      DBG_MARK(4);
       {
         const int ty = 2 * mt + (m >> 6), tx = m & 63;
         const float* px = sIn + ty * S * T::ROW + tx;
@@ -494,20 +486,11 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
       tc::tc_fence_before();                           // orders this warp's tcgen05.st (and the tcgen05.ld of epilogue mt-2) before the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
-      DBG_MARK(5);
       if (mt > 0) epilogue(mt - 1);                    // overlaps the MMAs of mt
-      DBG_MARK(6);
     }
     tc::mbar_wait(mma_done, (NMT - 1) & 1);
     tc::tc_fence_after();
-    DBG_MARK(4);
     epilogue(NMT - 1);
-    DBG_MARK(6);
-#ifdef SNB_SMALL_DBG
-    if (t == 0 && (blockIdx.x == 0 || blockIdx.x == 400))
-      printf("blk %d K %d: load-issue %lld wbuild %lld cpwait %lld sync %lld | wait %lld build %lld epi %lld | total %lld\n", blockIdx.x, D::K,
-             dbg_t[0], dbg_t[1], dbg_t[2], dbg_t[3], dbg_t[4], dbg_t[5], dbg_t[6], clock64() - dbg_start);
-#endif
 
     if (has_stats) {
 #pragma unroll
@@ -542,6 +525,7 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
 template <int CIN, int KS, int S, class Loader>
 __global__ void __launch_bounds__(256)
 conv_small_wgrad_kernel(Loader ld, const float* __restrict__ dy, float* __restrict__ partial, int OH, int OW, int pad) {
+  pdl_launch(); pdl_wait();
   using T = TileDims<CIN, KS, S>;
   constexpr int K = CIN * KS * KS;
   constexpr int JMAX = (K + 7) / 8;
@@ -629,7 +613,7 @@ static int snb_launch_small(const char* name, Loader ld, const float* w, float* 
     using T = TileDims<CIN, KS, S>;
     auto kern = conv_small_kernel<CIN, KS, S, Loader>;
     SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    kern<<<tiles, 256, T::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, y, up, OH, OW, pad, e, phaseB);
+    snb_launch(kern, tiles, 256, T::SMEM_BYTES, stream, ld, w, y, up, OH, OW, pad, e, phaseB);
   } else {
     using D = TcDims<CIN, KS, S>;
     SNB_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "%s: output must be 16-byte aligned", name);
@@ -637,7 +621,7 @@ static int snb_launch_small(const char* name, Loader ld, const float* w, float* 
     SNB_REQUIRE(!e.scale || ((reinterpret_cast<uintptr_t>(e.scale) | reinterpret_cast<uintptr_t>(e.shift)) & 15) == 0, "%s: scale/shift must be 16-byte aligned", name);
     auto kern = conv_small_tc_kernel<CIN, KS, S, Loader>;
     SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES));
-    kern<<<tiles, TC_THREADS, D::SMEM_BYTES, (cudaStream_t)stream>>>(ld, w, y, up, OH, OW, pad, e, phaseB);
+    snb_launch(kern, tiles, TC_THREADS, D::SMEM_BYTES, stream, ld, w, y, up, OH, OW, pad, e, phaseB);
   }
   SNB_LAUNCH_CHECK(name);
   return 0;
@@ -687,7 +671,7 @@ extern "C" int snb_conv5x5s2_c3_wgrad(const float* img, const float* dy, float* 
   auto kern = conv_small_wgrad_kernel<3, 5, 2, ImgLoader>;
   const int smem = (T::IN_FLOATS + 512 * 32) * 4;
   SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<snb_conv5x5s2_c3_num_tiles(B, H, W), 256, smem, (cudaStream_t)stream>>>(ld, dy, partial, OH, OW, 2);
+  snb_launch(kern, snb_conv5x5s2_c3_num_tiles(B, H, W), 256, smem, stream, ld, dy, partial, OH, OW, 2);
   SNB_LAUNCH_CHECK("conv5x5s2_c3_wgrad");
   return 0;
 }
@@ -700,7 +684,7 @@ extern "C" int snb_refine_in_wgrad(const float* coarse, const float* rgb, const 
   auto kern = conv_small_wgrad_kernel<4, 3, 1, RefineLoader>;
   const int smem = (T::IN_FLOATS + 512 * 32) * 4;
   SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<snb_refine_in_conv_num_tiles(B, H, W), 256, smem, (cudaStream_t)stream>>>(ld, dz, partial, H, W, 1);
+  snb_launch(kern, snb_refine_in_conv_num_tiles(B, H, W), 256, smem, stream, ld, dz, partial, H, W, 1);
   SNB_LAUNCH_CHECK("refine_in_wgrad");
   return 0;
 }

@@ -10,6 +10,7 @@
 __global__ void __launch_bounds__(256)
 cost_volume_fwd_kernel(const float4* __restrict__ left, const float4* __restrict__ right, float4* __restrict__ cost,
                        int D, int H, int W, int dper) {
+  pdl_launch(); pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* sL = reinterpret_cast<float4*>(smem_raw);
   float4* sR = sL + (size_t)W * 8;
@@ -53,6 +54,7 @@ cost_volume_fwd_kernel(const float4* __restrict__ left, const float4* __restrict
 __global__ void __launch_bounds__(256)
 cost_volume_bwd_kernel(const float4* __restrict__ g, float4* __restrict__ dleft, float4* __restrict__ dright,
                        int D, int H, int W) {
+  pdl_launch(); pdl_wait();
   const int row = blockIdx.x;
   const int b = row / H, y = row - b * H;
   const int row_f4 = W * 8;
@@ -81,7 +83,7 @@ extern "C" int snb_cost_volume_fwd(const float* left, const float* right, float*
   int dper = (D + groups - 1) / groups;
   groups = (D + dper - 1) / dper;
   SNB_CUDA(cudaFuncSetAttribute(cost_volume_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cost_volume_fwd_kernel<<<dim3(rows, groups), 256, smem, (cudaStream_t)stream>>>(
+  snb_launch(cost_volume_fwd_kernel, dim3(rows, groups), 256, smem, stream, 
       (const float4*)left, (const float4*)right, (float4*)cost, D, H, W, dper);
   SNB_LAUNCH_CHECK("cost_volume_fwd_kernel");
   return 0;
@@ -89,7 +91,7 @@ extern "C" int snb_cost_volume_fwd(const float* left, const float* right, float*
 
 extern "C" int snb_cost_volume_bwd(const float* dcost, float* dleft, float* dright, int B, int D, int H, int W, void* stream) {
   SNB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "snb_cost_volume_bwd: bad dims");
-  cost_volume_bwd_kernel<<<B * H, 256, 0, (cudaStream_t)stream>>>((const float4*)dcost, (float4*)dleft, (float4*)dright, D, H, W);
+  snb_launch(cost_volume_bwd_kernel, B * H, 256, 0, stream, (const float4*)dcost, (float4*)dleft, (float4*)dright, D, H, W);
   SNB_LAUNCH_CHECK("cost_volume_bwd_kernel");
   return 0;
 }

@@ -15,6 +15,7 @@ template <int NT>
 __global__ void __launch_bounds__(128)
 conv_c32_taps_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ taps,
                      long long npos, int plane) {
+  pdl_launch(); pdl_wait();
   constexpr int NTP = (NT + 3) & ~3;
   __shared__ __align__(16) float sA[128][32];
   __shared__ __align__(16) float sW[32][NTP];
@@ -74,6 +75,7 @@ conv_c32_taps_kernel(const float* __restrict__ x, const float* __restrict__ w, f
 __global__ void __launch_bounds__(1024)
 tapsum_softargmin_kernel(const float* __restrict__ taps, const float* __restrict__ bias, float* __restrict__ cost_out,
                          float* __restrict__ pred, int D, int H, int W) {
+  pdl_launch(); pdl_wait();
   __shared__ float sC[32][33];
   const int lane = threadIdx.x, d = threadIdx.y;
   const int b = blockIdx.x / H, y = blockIdx.x - b * H;
@@ -116,6 +118,7 @@ tapsum_softargmin_kernel(const float* __restrict__ taps, const float* __restrict
 __global__ void __launch_bounds__(256)
 tapsum_refine_out_kernel(const float* __restrict__ taps, const float* __restrict__ bias, const float* __restrict__ up,
                          float* __restrict__ out, int H, int W, int relu) {
+  pdl_launch(); pdl_wait();
   const int x = blockIdx.x * 256 + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
@@ -139,6 +142,7 @@ tapsum_refine_out_kernel(const float* __restrict__ taps, const float* __restrict
 
 __global__ void __launch_bounds__(256)
 upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int H, int W, float mul) {
+  pdl_launch(); pdl_wait();
   const int x = blockIdx.x * 256 + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
@@ -149,6 +153,7 @@ upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, 
 // Deterministic gather form of the adjoint: each coarse pixel visits the fine pixels whose 2x2 footprint contains it.
 __global__ void __launch_bounds__(128)
 upsample_bilinear_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int h, int w, int H, int W, float mul) {
+  pdl_launch(); pdl_wait();
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int i = blockIdx.y, b = blockIdx.z;
   if (j >= w) return;
@@ -187,6 +192,7 @@ upsample_bilinear_bwd_kernel(const float* __restrict__ dout, float* __restrict__
 // One pass over D with a running top-2 and sum instead of a torch.sort over [B,D,H,W].
 __global__ void __launch_bounds__(256)
 feature_contrast_kernel(const float* __restrict__ cost, float* __restrict__ out, int D, long long plane, long long total) {
+  pdl_launch(); pdl_wait();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const long long b = i / plane, q = i - b * plane;
@@ -205,7 +211,7 @@ feature_contrast_kernel(const float* __restrict__ cost, float* __restrict__ out,
 extern "C" int snb_feature_contrast(const float* cost, float* out, int B, int D, int H, int W, void* stream) {
   SNB_REQUIRE(cost && out && B > 0 && D > 2 && H > 0 && W > 0, "snb_feature_contrast: bad args (needs D > 2)");
   const long long plane = (long long)H * W, total = plane * B;
-  feature_contrast_kernel<<<snb_ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(cost, out, D, plane, total);
+  snb_launch(feature_contrast_kernel, snb_ceil_div(total, 256), 256, 0, stream, cost, out, D, plane, total);
   SNB_LAUNCH_CHECK("feature_contrast_kernel");
   return 0;
 }
@@ -215,8 +221,8 @@ extern "C" int snb_conv_c32_taps(const float* x, const float* w, float* taps, lo
   SNB_REQUIRE(ntaps == 27 || ntaps == 9, "snb_conv_c32_taps: ntaps must be 27 or 9");
   const long long npos = nslices * plane;
   const int grid = snb_ceil_div(npos, 128);
-  if (ntaps == 27) conv_c32_taps_kernel<27><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w, taps, npos, plane);
-  else             conv_c32_taps_kernel<9><<<grid, 128, 0, (cudaStream_t)stream>>>(x, w, taps, npos, plane);
+  if (ntaps == 27) snb_launch(conv_c32_taps_kernel<27>, grid, 128, 0, stream, x, w, taps, npos, plane);
+  else             snb_launch(conv_c32_taps_kernel<9>, grid, 128, 0, stream, x, w, taps, npos, plane);
   SNB_LAUNCH_CHECK("conv_c32_taps_kernel");
   return 0;
 }
@@ -225,7 +231,7 @@ extern "C" int snb_tapsum_softargmin(const float* taps, const float* bias, float
                                      int B, int D, int H, int W, void* stream) {
   SNB_REQUIRE(taps && bias && pred && B > 0 && D > 0 && H > 0 && W > 0, "snb_tapsum_softargmin: bad args");
   SNB_REQUIRE(D <= 32, "snb_tapsum_softargmin: at most 32 coarse disparity levels (got %d)", D);
-  tapsum_softargmin_kernel<<<dim3(B * H, snb_ceil_div(W, 32)), dim3(32, D), 0, (cudaStream_t)stream>>>(
+  snb_launch(tapsum_softargmin_kernel, dim3(B * H, snb_ceil_div(W, 32)), dim3(32, D), 0, stream, 
       taps, bias, cost_out, pred, D, H, W);
   SNB_LAUNCH_CHECK("tapsum_softargmin_kernel");
   return 0;
@@ -234,21 +240,21 @@ extern "C" int snb_tapsum_softargmin(const float* taps, const float* bias, float
 extern "C" int snb_tapsum_refine_out(const float* taps, const float* bias, const float* up, float* out,
                                      int B, int H, int W, int relu, void* stream) {
   SNB_REQUIRE(taps && out && B > 0 && H > 0 && W > 0, "snb_tapsum_refine_out: bad args");
-  tapsum_refine_out_kernel<<<dim3(snb_ceil_div(W, 256), H, B), 256, 0, (cudaStream_t)stream>>>(taps, bias, up, out, H, W, relu);
+  snb_launch(tapsum_refine_out_kernel, dim3(snb_ceil_div(W, 256), H, B), 256, 0, stream, taps, bias, up, out, H, W, relu);
   SNB_LAUNCH_CHECK("tapsum_refine_out_kernel");
   return 0;
 }
 
 extern "C" int snb_upsample_bilinear(const float* in, float* out, int B, int h, int w, int H, int W, float mul, void* stream) {
   SNB_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "snb_upsample_bilinear: bad args");
-  upsample_bilinear_kernel<<<dim3(snb_ceil_div(W, 256), H, B), 256, 0, (cudaStream_t)stream>>>(in, out, h, w, H, W, mul);
+  snb_launch(upsample_bilinear_kernel, dim3(snb_ceil_div(W, 256), H, B), 256, 0, stream, in, out, h, w, H, W, mul);
   SNB_LAUNCH_CHECK("upsample_bilinear_kernel");
   return 0;
 }
 
 extern "C" int snb_upsample_bilinear_bwd(const float* dout, float* din, int B, int h, int w, int H, int W, float mul, void* stream) {
   SNB_REQUIRE(dout && din && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "snb_upsample_bilinear_bwd: bad args");
-  upsample_bilinear_bwd_kernel<<<dim3(snb_ceil_div(w, 128), h, B), 128, 0, (cudaStream_t)stream>>>(dout, din, h, w, H, W, mul);
+  snb_launch(upsample_bilinear_bwd_kernel, dim3(snb_ceil_div(w, 128), h, B), 128, 0, stream, dout, din, h, w, H, W, mul);
   SNB_LAUNCH_CHECK("upsample_bilinear_bwd_kernel");
   return 0;
 }

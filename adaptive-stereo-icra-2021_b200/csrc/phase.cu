@@ -12,6 +12,7 @@ namespace {
 // x [B,H,W,32] -> out [4][B,OH,OW,32] (phase index a*2+b), rows/cols past the image are zero.  One thread = one float4.
 __global__ void __launch_bounds__(256)
 phase_split_kernel(const float4* __restrict__ x, float4* __restrict__ out, int B, int H, int W, int OH, int OW, long long n4) {
+  pdl_launch(); pdl_wait();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const int chunk = (int)(i & 7);
     long long p = i >> 3;
@@ -28,6 +29,7 @@ phase_split_kernel(const float4* __restrict__ x, float4* __restrict__ out, int B
 // in [4][B,OH,OW,32] -> dx [B,H,W,32]
 __global__ void __launch_bounds__(256)
 phase_merge_kernel(const float4* __restrict__ in, float4* __restrict__ dx, int B, int H, int W, int OH, int OW, long long n4) {
+  pdl_launch(); pdl_wait();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const int chunk = (int)(i & 7);
     long long p = i >> 3;
@@ -50,7 +52,7 @@ extern "C" int snb_phase_split(const float* x, float* out, int B, int H, int W, 
   SNB_REQUIRE(x && out && B > 0 && H > 0 && W > 0, "snb_phase_split: bad args");
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const long long n4 = 4ll * B * OH * OW * 8;
-  phase_split_kernel<<<phase_grid(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)out, B, H, W, OH, OW, n4);
+  snb_launch(phase_split_kernel, phase_grid(n4), 256, 0, stream, (const float4*)x, (float4*)out, B, H, W, OH, OW, n4);
   SNB_LAUNCH_CHECK("phase_split_kernel");
   return 0;
 }
@@ -59,7 +61,7 @@ extern "C" int snb_phase_merge(const float* in, float* dx, int B, int H, int W, 
   SNB_REQUIRE(in && dx && B > 0 && H > 0 && W > 0, "snb_phase_merge: bad args");
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const long long n4 = (long long)B * H * W * 8;
-  phase_merge_kernel<<<phase_grid(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)in, (float4*)dx, B, H, W, OH, OW, n4);
+  snb_launch(phase_merge_kernel, phase_grid(n4), 256, 0, stream, (const float4*)in, (float4*)dx, B, H, W, OH, OW, n4);
   SNB_LAUNCH_CHECK("phase_merge_kernel");
   return 0;
 }

@@ -25,6 +25,7 @@ constexpr int NSUMBLK = 64;                     // partial sums of d per batch
 
 __global__ void __launch_bounds__(256)
 disp_partial_sum_kernel(const float* __restrict__ d, float* __restrict__ part, int HW) {
+  pdl_launch(); pdl_wait();
   __shared__ double red[256];
   const int b = blockIdx.y;
   const float* p = d + (size_t)b * HW;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256)
 photo_loss_tile_kernel(const float* __restrict__ left, const float* __restrict__ right, const float* __restrict__ disp,
                        const float* __restrict__ dsum_part, float* __restrict__ g_out, float* __restrict__ part,
                        int H, int W, float smooth_w) {
+  pdl_launch(); pdl_wait();
   extern __shared__ float sm[];
   float* sL = sm;                              // [3][R2H*R2W]   left image (0 outside the image = avg_pool zero padding)
   float* sI = sL + 3 * R2H * R2W;              // [3][R2H*R2W]   warped right image
@@ -228,6 +230,7 @@ photo_loss_tile_kernel(const float* __restrict__ left, const float* __restrict__
 __global__ void __launch_bounds__(256)
 photo_loss_finalize_kernel(const float* __restrict__ part, const float* __restrict__ dsum_part, float* __restrict__ g,
                            float* __restrict__ loss_out, int B, int HW, int blocks_per_batch) {
+  pdl_launch(); pdl_wait();
   __shared__ double sh[3];
   __shared__ double red[256];
   const int b = blockIdx.y, t = threadIdx.x;
@@ -268,14 +271,14 @@ extern "C" int snb_photo_loss(const float* left, const float* right, const float
   const int HW = H * W;
   float* dsum = workspace;
   float* part = workspace + B * NSUMBLK;
-  disp_partial_sum_kernel<<<dim3(NSUMBLK, B), 256, 0, st>>>(disp, dsum, HW);
+  snb_launch(disp_partial_sum_kernel, dim3(NSUMBLK, B), 256, 0, st, disp, dsum, HW);
   SNB_LAUNCH_CHECK("disp_partial_sum_kernel");
   const dim3 grid(snb_ceil_div(W, TW), snb_ceil_div(H, TH), B);
   const int smem = (3 * R2H * R2W * 2 + R2H * R2W * 2 + 3 * TH * TW + 9 * R1H * R1W) * 4;
   SNB_CUDA(cudaFuncSetAttribute(photo_loss_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  photo_loss_tile_kernel<<<grid, 256, smem, st>>>(left, right, disp, dsum, ddisp, part, H, W, smooth_w);
+  snb_launch(photo_loss_tile_kernel, grid, 256, smem, st, left, right, disp, dsum, ddisp, part, H, W, smooth_w);
   SNB_LAUNCH_CHECK("photo_loss_tile_kernel");
-  photo_loss_finalize_kernel<<<dim3(148, B), 256, 0, st>>>(part, dsum, ddisp, loss_out, B, HW, (int)(grid.x * grid.y));
+  snb_launch(photo_loss_finalize_kernel, dim3(148, B), 256, 0, st, part, dsum, ddisp, loss_out, B, HW, (int)(grid.x * grid.y));
   SNB_LAUNCH_CHECK("photo_loss_finalize_kernel");
   return 0;
 }

@@ -188,12 +188,15 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;\n" ::
 
 __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b < 0) ? q - 1 : q; }
 
-// hi = top 19 bits (exactly representable in TF32), lo = x - hi (exact in fp32)
+// 3xTF32 operand split: hi = x rounded to nearest TF32 (11-bit significand; ties away from zero, done on the bit pattern),
+// lo = x - hi (exact in fp32, |lo| <= 2^-12 |x|; the tensor core reads its top 19 bits).  Rounding instead of truncating hi
+// halves |lo|, so both the dropped lo*lo term and the truncation of lo are 4x smaller (~2^-22 relative per product).
+__device__ __forceinline__ uint32_t tf32_hi_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  hi.x = __uint_as_float(tf32_hi_bits(x.x));
+  hi.y = __uint_as_float(tf32_hi_bits(x.y));
+  hi.z = __uint_as_float(tf32_hi_bits(x.z));
+  hi.w = __uint_as_float(tf32_hi_bits(x.w));
   lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
 }
 

@@ -1,7 +1,7 @@
 # One GPU call: the whole `-m gpu` suite file by file, then a short bench.  Usage: gpurun -- 'bash scripts/gpu_check.sh'
 mkdir -p gpurun_out
 for f in test_gpu_kernels test_gpu_conv_tc test_gpu_wgrad_tc test_gpu_e2e test_gpu_backward; do
-  timeout 900 python -m pytest tests/$f.py -m gpu -q --tb=short -x > gpurun_out/$f.log 2>&1
+  timeout 900 python -m pytest tests/$f.py -m gpu -q --tb=short > gpurun_out/$f.log 2>&1
   echo "$f exit $?: $(grep -E 'passed|failed' gpurun_out/$f.log | tail -1)"
 done
 timeout 900 python bench.py --steps 30 --warmup 5 --skip-cpu > gpurun_out/bench.log 2>&1; python - <<'PY'
