@@ -204,17 +204,6 @@ conv_small_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y,
 }
 
 // ------------------------------------------------------------------------------------------------ tensor-core variant
-constexpr uint32_t IDESC_N32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void mma_n32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC_N32), "r"(accumulate) : "memory");
-}
-
 // registers -> TMEM, N consecutive 32-bit columns of the thread's lane
 template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r);
 template <> __device__ __forceinline__ void tmem_st_n<4>(uint32_t taddr, const uint32_t* r) {
@@ -405,9 +394,9 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
         for (int ks = 0; ks < D::KP / 8; ++ks) {
           const uint32_t bo = smem_u + (ks >> 2) * 4096 + (ks & 3) * 32;
           const uint64_t bh = tc::make_desc(bo), bl = tc::make_desc(bo + D::KPB * 128);
-          mma_n32_ts(tmem_d, ta + ks * 8, bh, ks > 0);
-          mma_n32_ts(tmem_d, ta + D::KP + ks * 8, bh, 1);
-          mma_n32_ts(tmem_d, ta + ks * 8, bl, 1);
+          tc::mma_n32_ts(tmem_d, ta + ks * 8, bh, ks > 0);
+          tc::mma_n32_ts(tmem_d, ta + D::KP + ks * 8, bh, 1);
+          tc::mma_n32_ts(tmem_d, ta + ks * 8, bl, 1);
         }
         tc::mma_commit_raw(mma_done);
       }

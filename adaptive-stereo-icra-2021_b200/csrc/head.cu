@@ -6,7 +6,9 @@
 //   conv3d_alone + softmax + DisparityRegression (stereo_net.py:187-192,124-134) -> snb_tapsum_softargmin
 //   conv2d_out + residual add + ReLU           (stereo_net.py:121)              -> snb_tapsum_refine_out
 // Tap planes are stored [slice][tap][H][W] so both the scatter (thread = position) and the gather (thread = x) are coalesced.
-#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include "tc_common.cuh"
 #include <math.h>
 
 namespace {
@@ -66,6 +68,147 @@ conv_c32_taps_kernel(const float* __restrict__ x, const float* __restrict__ w, f
     float* out = taps + slice * (long long)NT * plane + q;
 #pragma unroll
     for (int j = 0; j < NT; ++j) out[(size_t)j * plane] = acc[j];
+  }
+}
+
+// ---- the same contraction on the tensor cores: taps[p][t] = sum_c x[p][c] w[t][c] is a GEMM with M = positions, N = 32
+// (27 or 9 tap rows used), K = 32 channels; 3xTF32 split, A operand from TMEM.  Two groups of 4 warps alternate over the
+// CTA's 128-position tiles: cp.async the tile (16-B chunks XOR-swizzled) -> each thread reads its position's row, splits
+// hi/lo and tcgen05.st's it into the group's A slot -> the MMA warp issues 12 MMAs -> the group reads the 27 taps of its
+// position back (tcgen05.ld) and stores them plane-major (coalesced over positions).  The FFMA kernel above was bound by
+// its 27 x 32 FMAs per position (20 us at KITTI size against a 6 us memory floor); it stays selectable with
+// SNB200_TAPS=ffma as the independent cross-check.
+constexpr int TAPS_TC_THREADS = 9 * 32;
+constexpr int TAPS_TC_SMEM = 80 * 1024;           // 8 KB weights + 4 x 16 KB tile buffers + barriers; >= 78 KB keeps it at 2 CTAs / SM (2 x 256 TMEM columns)
+
+template <int NT>
+__global__ void __launch_bounds__(TAPS_TC_THREADS, 2)
+conv_c32_taps_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ taps,
+                        long long npos, int plane, int ntiles) {
+  pdl_launch();
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
+  float* sB = reinterpret_cast<float*>(base);                      // [hi|lo][32 tap rows][32 channels] swizzled
+  unsigned char* sTile = base + 8192;                              // [group][2][128 x 128 B]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sTile + 4 * 16384);   // [2] group -> MMA warp
+  uint64_t* done = a_full + 2;                                     // [2] MMA commit -> group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  constexpr int ACC_COL = 0, A_COL = 64;                           // TMEM: 2 accumulators x 32 | 2 A slots x (hi 32 | lo 32)
+
+  if (warp == 8) {
+    if (lane == 0) { mbar_init(&a_full[0], 4); mbar_init(&a_full[1], 4); mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  pdl_wait();                                                      // nothing above touched global memory
+  for (int i = t; i < 32 * 32; i += TAPS_TC_THREADS) {             // B row = tap, K = channel; w is [1][32][NT]
+    const int tp = i >> 5, c = i & 31;
+    const float v = tp < NT ? __ldg(w + c * NT + tp) : 0.f;
+    const float hi = __uint_as_float(tc::tf32_hi_bits(v));
+    const int o = tp * 32 + (((c >> 2) ^ (tp & 7)) << 2) + (c & 3);
+    sB[o] = hi;
+    sB[1024 + o] = v - hi;
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nmine = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles blockIdx.x + i * gridDim.x
+
+  if (warp == 8) {
+    // =============================================================== MMA issuer
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), smem_u = __shfl_sync(0xffffffffu, base_u32, 0);
+    for (int i = 0; i < nmine; ++i) {
+      const int g = i & 1, j = i >> 1;
+      tc::mbar_wait_warp(&a_full[g], j & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const uint32_t tmem_d = tmem_u + ACC_COL + g * 32, ta = tmem_u + A_COL + g * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bh = tc::make_desc(smem_u + ks * 32), bl = tc::make_desc(smem_u + 4096 + ks * 32);
+          tc::mma_n32_ts(tmem_d, ta + ks * 8, bh, ks > 0);
+          tc::mma_n32_ts(tmem_d, ta + 32 + ks * 8, bh, 1);
+          tc::mma_n32_ts(tmem_d, ta + ks * 8, bl, 1);
+        }
+        tc::mma_commit_raw(&done[g]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================================================== two groups of 4 warps: load, convert, store
+    const int g = warp >> 2, quad = warp & 3;
+    const int gt = t & 127;                                         // thread within the group = position row = TMEM lane
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    unsigned char* buf = sTile + g * 2 * 16384;
+    const int ngrp = (nmine - g + 1) / 2;                           // this group's tiles: i = g, g + 2, ...
+    auto prefetch = [&](int j) {
+      const long long pos0 = ((long long)blockIdx.x + (long long)(2 * j + g) * gridDim.x) * 128;
+      unsigned char* dst = buf + (j & 1) * 16384;
+      const int chunk = gt & 7;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (gt >> 3) + 16 * k;
+        const bool ok = pos0 + r < npos;
+        cp_async16(dst + r * 128 + ((chunk ^ (r & 7)) << 4), x + (ok ? (pos0 + r) * 32 + chunk * 4 : 0), ok);
+      }
+      cp_async_commit();
+    };
+    if (ngrp > 0) prefetch(0);
+    for (int j = 0; j < ngrp; ++j) {
+      cp_async_wait<0>();
+      asm volatile("bar.sync %0, 128;\n" :: "r"(1 + g) : "memory");   // the whole tile has landed; buffer (j+1)&1 is no longer read
+      if (j + 1 < ngrp) prefetch(j + 1);
+      const unsigned char* rowp = buf + (j & 1) * 16384 + gt * 128;
+      float4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (gt & 7)) << 4));
+      // the A slot and the accumulator of this group are free: done[g] of tile j-1 was waited for below
+      const uint32_t ta = tlane + A_COL + g * 64;
+      {
+        uint32_t h[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
+          h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
+        }
+        tc::tmem_st32(ta, h);
+        uint32_t l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          l[4 * c] = __float_as_uint(v[c].x - __uint_as_float(h[4 * c])); l[4 * c + 1] = __float_as_uint(v[c].y - __uint_as_float(h[4 * c + 1]));
+          l[4 * c + 2] = __float_as_uint(v[c].z - __uint_as_float(h[4 * c + 2])); l[4 * c + 3] = __float_as_uint(v[c].w - __uint_as_float(h[4 * c + 3]));
+        }
+        tc::tmem_st32(ta + 32, l);
+      }
+      tc::tmem_wait_st();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[g]);
+      tc::mbar_wait(&done[g], j & 1);
+      tc::tc_fence_after();
+      float acc[32];
+      tc::tmem_ld32(tlane + ACC_COL + g * 32, acc);
+      tc::tc_fence_before();
+      const long long p = ((long long)blockIdx.x + (long long)(2 * j + g) * gridDim.x) * 128 + gt;
+      if (p < npos) {
+        const long long slice = p / plane;
+        const int q = (int)(p - slice * plane);
+        float* out = taps + slice * (long long)NT * plane + q;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) __stcg(out + (size_t)k * plane, acc[k]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(tmem_base) : "memory");
   }
 }
 
@@ -221,6 +364,23 @@ extern "C" int snb_conv_c32_taps(const float* x, const float* w, float* taps, lo
   SNB_REQUIRE(ntaps == 27 || ntaps == 9, "snb_conv_c32_taps: ntaps must be 27 or 9");
   const long long npos = nslices * plane;
   const int grid = snb_ceil_div(npos, 128);
+  static const bool use_ffma = []() { const char* s = getenv("SNB200_TAPS"); return s != nullptr && strcmp(s, "ffma") == 0; }();
+  if (!use_ffma) {
+    SNB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "snb_conv_c32_taps: x must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    SNB_CUDA(cudaGetDevice(&dev));
+    SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ctas = grid < 2 * sms ? grid : 2 * sms;
+    if (ntaps == 27) {
+      SNB_CUDA(cudaFuncSetAttribute(conv_c32_taps_tc_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAPS_TC_SMEM));
+      snb_launch(conv_c32_taps_tc_kernel<27>, ctas, TAPS_TC_THREADS, TAPS_TC_SMEM, stream, x, w, taps, npos, plane, grid);
+    } else {
+      SNB_CUDA(cudaFuncSetAttribute(conv_c32_taps_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAPS_TC_SMEM));
+      snb_launch(conv_c32_taps_tc_kernel<9>, ctas, TAPS_TC_THREADS, TAPS_TC_SMEM, stream, x, w, taps, npos, plane, grid);
+    }
+    SNB_LAUNCH_CHECK("conv_c32_taps_tc_kernel");
+    return 0;
+  }
   if (ntaps == 27) snb_launch(conv_c32_taps_kernel<27>, grid, 128, 0, stream, x, w, taps, npos, plane);
   else             snb_launch(conv_c32_taps_kernel<9>, grid, 128, 0, stream, x, w, taps, npos, plane);
   SNB_LAUNCH_CHECK("conv_c32_taps_kernel");

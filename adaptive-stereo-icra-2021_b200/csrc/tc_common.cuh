@@ -147,6 +147,18 @@ __device__ __forceinline__ void mma_commit_raw(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// M128 N32 K8 variant (small-Cin im2col convolutions, 32->1 tap contractions), A from TMEM; call inside one elected region
+constexpr uint32_t IDESC_N32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void mma_n32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC_N32), "r"(accumulate) : "memory");
+}
+
 // Warp-uniform wait for the CONVERGED MMA-issuing warp: every lane polls and the loop exits on a warp vote, so the loop
 // is provably non-divergent and nvcc keeps the loop-carried state (stage counters, smem/TMEM addresses, descriptors) in
 // the uniform datapath — with a per-lane exit condition they live in vector registers and every tcgen05.mma pays
