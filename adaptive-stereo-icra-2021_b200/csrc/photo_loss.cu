@@ -253,6 +253,21 @@ photo_loss_finalize_kernel(const float* __restrict__ part, const float* __restri
   const float m_eps = mean_disp(dsum_part, b, HW) + 1e-7f;
   const float coupling = (float)(sh[2] / ((double)m_eps * (double)m_eps * (double)HW));
   if (blockIdx.x == 0 && b == 0 && t == 0) loss_out[0] = (float)(sh[0] / cnt);
+  if (blockIdx.x == 0) {                       // masked mean over sample b alone -> loss_out[1 + b] (OVS validation, adapt.py:122-142)
+    for (int q = 0; q < 2; ++q) {
+      double s = 0.0;
+      for (int i = b * blocks_per_batch + t; i < (b + 1) * blocks_per_batch; i += 256) s += (double)part[i * 4 + q];
+      red[t] = s;
+      __syncthreads();
+      for (int off = 128; off > 0; off >>= 1) {
+        if (t < off) red[t] += red[t + off];
+        __syncthreads();
+      }
+      if (t == 0) sh[q] = red[0];
+      __syncthreads();
+    }
+    if (t == 0) loss_out[1 + b] = (float)(sh[0] / sh[1]);
+  }
   float* gb = g + (size_t)b * HW;
   for (int i = blockIdx.x * 256 + t; i < HW; i += gridDim.x * 256) gb[i] = (gb[i] - coupling) * inv_cnt;
 }

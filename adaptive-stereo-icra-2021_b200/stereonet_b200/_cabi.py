@@ -69,6 +69,9 @@ SIGNATURES = {
   "snb_photo_loss": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
   "snb_photo_loss_workspace_floats": (_I, [_I, _I, _I]),
   "snb_conv_c32_taps_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+  "snb_khamis_loss": (_I, [_P, _P, _P, _P, _P, _LL, _P]),
+  "snb_khamis_loss_workspace_floats": (_I, [_LL]),
+  "snb_eval_metrics": (_I, [_P, _P, _P, _I, _LL, _P]),
 }
 
 _lib = None

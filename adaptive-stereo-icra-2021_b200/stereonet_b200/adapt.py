@@ -4,8 +4,8 @@ parameters only, Adam step.  The state machine / OVS / logging of adapt.py stay 
 import torch
 import torch.nn as nn
 
-from .losses import (LinearWarping, feature_contrast_mean, khamis_robust_loss, monodepth_single_loss,
-                     monodepth_single_loss_fused)
+from .losses import (LinearWarping, feature_contrast_mean, khamis_robust_loss, khamis_robust_loss_fused,
+                     monodepth_single_loss, monodepth_single_loss_fused)
 
 
 def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
@@ -23,13 +23,17 @@ class AdaptStepper:
   execution is bound by host launch latency.  Requires an optimizer built with capturable=True and no replay term."""
 
   def __init__(self, feature_net, stereo_net, optimizer, height, width, clip_grad_norm=True, er_loss_weight=0.05,
-               use_graph=False, fused_loss=False):
+               use_graph=False, fused_loss=False, batched_replay=False):
     self.feature_net, self.stereo_net, self.optimizer = feature_net, stereo_net, optimizer
     self.clip, self.er_loss_weight = clip_grad_norm, er_loss_weight
     dev = next(stereo_net.parameters()).device
     self.warper = LinearWarping(height, width, dev)
     self.use_graph = use_graph
     self.fused_loss = fused_loss            # photometric loss + its gradient from snb_photo_loss instead of ~150 torch kernels
+    # SURVEY.md section 8 row f3: run the replay sample through the model in the SAME batch-2 forward/backward as the stream
+    # frame instead of a second full pass (adapt.py:339-349).  Off by default: train-mode BatchNorm then normalises with the
+    # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
+    self.batched_replay = batched_replay
     self._graphs = {}
     self.launches_per_step = None
     if use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
@@ -59,6 +63,8 @@ class AdaptStepper:
   def _fwd_bwd(self, left, right, replay, static_shapes):
     s = self.stereo_net.input_scale
     self.feature_net.train(); self.stereo_net.train()
+    if replay is not None and self.batched_replay:
+      return self._fwd_bwd_batched(left, right, replay)
     outputs = self.predict(left, right)
     if self.fused_loss:
       loss = monodepth_single_loss_fused(left, right, outputs, s)
@@ -71,6 +77,25 @@ class AdaptStepper:
     self.optimizer.zero_grad()
     loss.backward()
     return loss.detach(), fcs, outputs
+
+  def _fwd_bwd_batched(self, left, right, replay):
+    """Row f3: one batch-(n+m) pass for the n stream frames and the m replay samples; Monodepth loss on the first n
+    predictions, Khamis robust loss on the rest (snb_khamis_loss), same 1 : er_loss_weight mix as adapt.py:383-388."""
+    s = self.stereo_net.input_scale
+    n = left.shape[0]
+    outputs = self.predict(torch.cat([left, replay[0]], 0), torch.cat([right, replay[1]], 0))
+    key = "pred_disp_l/{}".format(s)
+    head = {k: v[:n] for k, v in outputs.items()}
+    if self.fused_loss:
+      loss = monodepth_single_loss_fused(left, right, head, s)
+    else:
+      loss = monodepth_single_loss(left, right, head, self.warper, s)
+    gt = replay[2].reshape(outputs[key][n:].shape)
+    loss = loss + self.er_loss_weight * khamis_robust_loss_fused(outputs[key][n:], gt)
+    fcs = feature_contrast_mean(head["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
+    self.optimizer.zero_grad()
+    loss.backward()
+    return loss.detach(), fcs, head
 
   def _update(self):
     if self.clip:

@@ -101,6 +101,27 @@ def khamis_robust_loss(pred_disp, gt_disp):
   return torch.sum(torch.sqrt(torch.pow(gt_disp[mask] - pred_disp[mask], 2) + 4) / 2 - 1) / num_valid
 
 
+class _FusedKhamisLoss(torch.autograd.Function):
+  """snb_khamis_loss: value and d loss / d pred from two launches, no boolean indexing."""
+
+  @staticmethod
+  def forward(ctx, pred, gt):
+    from . import ops
+    loss, dpred = ops.khamis_loss(pred.contiguous(), gt.contiguous())
+    ctx.save_for_backward(dpred)
+    return loss[0]
+
+  @staticmethod
+  def backward(ctx, gout):
+    (dpred,) = ctx.saved_tensors
+    return dpred * gout, None
+
+
+def khamis_robust_loss_fused(pred_disp, gt_disp):
+  """Same value and gradient as khamis_robust_loss, static shapes (CUDA-graph capturable)."""
+  return _FusedKhamisLoss.apply(pred_disp, gt_disp)
+
+
 def feature_contrast_mean(cost_volume):
   """feature_contrast.py:12-23.  CUDA tensors use the library's single-pass kernel (no sort); the torch expression below is
   the reference formulation (kept for CPU tensors in tests)."""

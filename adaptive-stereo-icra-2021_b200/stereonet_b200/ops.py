@@ -426,19 +426,46 @@ def conv_c32_taps_bwd(x, w, g, ntaps):
 
 
 def photo_loss(left, right, disp, smooth_w=1e-3):
-  """Fused Monodepth photometric loss (adapt.py:78-86): returns (loss [1], dloss/ddisp [B,H,W])."""
+  """Fused Monodepth photometric loss (adapt.py:78-86): returns (loss [1 + B], dloss[0]/ddisp [B,H,W]); loss[0] is the
+  masked mean over the batch, loss[1 + b] the masked mean over sample b alone (OVS validation, adapt.py:122-142)."""
   _req(left, "left_img", 4); _req(right, "right_img", 4); _req(disp, "disp", 3)
   B, Cc, H, W = left.shape
   if Cc != 3 or right.shape != left.shape or tuple(disp.shape) != (B, H, W):
     raise RuntimeError(f"stereonet_b200: photo_loss expects [B,3,H,W] images and a [B,H,W] disparity, got "
                        f"{tuple(left.shape)} {tuple(right.shape)} {tuple(disp.shape)}")
-  loss = torch.empty((1,), device=left.device, dtype=torch.float32)
+  loss = torch.empty((1 + B,), device=left.device, dtype=torch.float32)
   ddisp = torch.empty((B, H, W), device=left.device, dtype=torch.float32)
   ws = torch.empty((_cabi.lib().snb_photo_loss_workspace_floats(B, H, W),), device=left.device, dtype=torch.float32)
   check(_cabi.lib().snb_photo_loss(_p(left), _p(right), _p(disp), _p(loss), _p(ddisp), _p(ws), B, H, W, float(smooth_w),
                                    _stream(left)), "snb_photo_loss")
   _count(3)
   return loss, ddisp
+
+
+def khamis_loss(pred, gt):
+  """khamis_robust_loss (loss_functions.py:6-15): returns (loss [1], dloss/dpred like pred)."""
+  _req(pred, "pred_disp"); _req(gt, "gt_disp")
+  if pred.shape != gt.shape:
+    raise RuntimeError(f"stereonet_b200: khamis_loss expects equal shapes, got {tuple(pred.shape)} {tuple(gt.shape)}")
+  n = pred.numel()
+  loss = torch.empty((1,), device=pred.device, dtype=torch.float32)
+  dpred = torch.empty_like(pred)
+  ws = torch.empty((_cabi.lib().snb_khamis_loss_workspace_floats(n),), device=pred.device, dtype=torch.float32)
+  check(_cabi.lib().snb_khamis_loss(_p(pred), _p(gt), _p(loss), _p(dpred), _p(ws), n, _stream(pred)), "snb_khamis_loss")
+  _count(2)
+  return loss, dpred
+
+
+def eval_metrics(pred, gt):
+  """Per-sample evaluation sums (train.py:98-107): [B,6] = {sum|e|, #valid, #(|e|>2), #(|e|>3), #(|e|>4), #(|e|>5)} over gt > 0."""
+  _req(pred, "pred_disp"); _req(gt, "gt_disp")
+  if pred.shape != gt.shape:
+    raise RuntimeError(f"stereonet_b200: eval_metrics expects equal shapes, got {tuple(pred.shape)} {tuple(gt.shape)}")
+  B = pred.shape[0]
+  out = torch.empty((B, 6), device=pred.device, dtype=torch.float32)
+  check(_cabi.lib().snb_eval_metrics(_p(pred), _p(gt), _p(out), B, pred.numel() // B, _stream(pred)), "snb_eval_metrics")
+  _count()
+  return out
 
 
 def feature_contrast(cost):

@@ -218,7 +218,9 @@ SNB_API int snb_conv_c32_taps_bwd(const float* x, const float* w, const float* g
  * fused photometric loss of the adaptation step (adapt.py:78-86; LinearWarping
  * linear_warping.py:18-57; SSIM / L1 / edge-aware smoothness loss_functions.py:41-138), forward value AND gradient
  * w.r.t. the predicted disparity in three launches.  left/right [B,3,H,W] NCHW, disp [B,H,W] (full resolution),
- * loss_out [1], ddisp [B,H,W] = d loss / d disp, workspace of snb_photo_loss_workspace_floats(B,H,W) floats.
+ * loss_out [1 + B]: [0] = the masked mean over the whole batch (what adapt.py:83 returns), [1 + b] = the same masked mean
+ * over sample b alone (= what StateMachine.validate, adapt.py:122-142, gets from its one-pair-at-a-time loop; row f4);
+ * ddisp [B,H,W] = d loss_out[0] / d disp, workspace of snb_photo_loss_workspace_floats(B,H,W) floats.
  * smooth_w = 1e-3 in adapt.py:81-83. */
 SNB_API int snb_photo_loss(const float* left, const float* right, const float* disp, float* loss_out, float* ddisp,
                    float* workspace, int B, int H, int W, float smooth_w, void* stream);
@@ -226,6 +228,16 @@ SNB_API int snb_photo_loss_workspace_floats(int B, int H, int W);
 /* Row f2: feature-contrast score of a cost volume [B,D,H,W] -> [B,H,W] (feature_contrast.py:12-23, adapt.py:352-353):
  * max_d cost - mean of all but the two largest costs, without sorting. */
 SNB_API int snb_feature_contrast(const float* cost, float* out, int B, int D, int H, int W, void* stream);
+/* Row f3: khamis_robust_loss (loss_functions.py:6-15; the experience-replay term of adapt.py:339-349) over n elements:
+ * loss_out [1] = sum_{gt > 0} (sqrt((gt - pred)^2 + 4) / 2 - 1) / max(#valid, 1), dpred [n] = d loss / d pred,
+ * workspace of snb_khamis_loss_workspace_floats(n) floats.  Two launches, deterministic, no host sync. */
+SNB_API int snb_khamis_loss(const float* pred, const float* gt, float* loss_out, float* dpred, float* workspace, long long n,
+                    void* stream);
+SNB_API int snb_khamis_loss_workspace_floats(long long n);
+/* Row f4: evaluation metrics of train.py:98-107 as per-sample sums over gt > 0 (hw = H*W elements per sample):
+ * out [B][6] = {sum |pred - gt|, #valid, #(|e| > 2), #(|e| > 3), #(|e| > 4), #(|e| > 5)}; EPE = out[0] / out[1],
+ * D1-all_t = out[2 + t] / out[1].  One CTA per sample, deterministic. */
+SNB_API int snb_eval_metrics(const float* pred, const float* gt, float* out, int B, long long hw, void* stream);
 
 #ifdef __cplusplus
 }
