@@ -8,7 +8,7 @@ namespace {
 
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
+                   const float* __restrict__ beta, float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                    float* scale, float* shift, float* mean_out, float* invstd_out) {
   pdl_launch(); pdl_wait();
   __shared__ double red[16][64];
@@ -34,6 +34,7 @@ bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, co
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
       running_mean[ch] = (float)((1.0 - momentum) * (double)running_mean[ch] + momentum * mean);
       running_var[ch] = (float)((1.0 - momentum) * (double)running_var[ch] + momentum * unbiased);
+      if (ch == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;      // nn.BatchNorm's int64 counter, same launch
     }
     const float sc = gamma[ch] * (float)invstd;
     scale[ch] = sc;
@@ -81,28 +82,34 @@ bn_apply_kernel(const float4* __restrict__ z, const float* __restrict__ scale, c
 
 }  // namespace
 
-extern "C" int snb_bn_finalize(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
-                               float* running_mean, float* running_var, float momentum, float eps,
-                               float* scale, float* shift, float* mean, float* invstd, void* stream) {
+static int bn_finalize_impl(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                            float* scale, float* shift, float* mean, float* invstd, void* stream) {
   SNB_REQUIRE(stats && gamma && beta && scale && shift && ntiles > 0 && count > 0, "snb_bn_finalize: bad args");
   SNB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "snb_bn_finalize: running stats must come in pairs");
   snb_launch(bn_finalize_kernel, 1, 1024, 0, stream, stats, ntiles, (double)count, gamma, beta, running_mean, running_var,
-                                                           momentum, eps, scale, shift, mean, invstd);
+             num_batches_tracked, momentum, eps, scale, shift, mean, invstd);
   SNB_LAUNCH_CHECK("bn_finalize_kernel");
   return 0;
 }
 
+extern "C" int snb_bn_finalize(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  return bn_finalize_impl(stats, ntiles, count, gamma, beta, running_mean, running_var, nullptr, momentum, eps, scale, shift, mean, invstd, stream);
+}
+
 extern "C" int snb_bn_finalize_ws(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
-                                  float* running_mean, float* running_var, float momentum, float eps,
+                                  float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                                   float* scale, float* shift, float* mean, float* invstd, float* scratch, void* stream) {
   SNB_REQUIRE(scratch != nullptr, "snb_bn_finalize_ws: null scratch");
   if (ntiles <= 256)
-    return snb_bn_finalize(stats, ntiles, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, stream);
+    return bn_finalize_impl(stats, ntiles, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd, stream);
   SNB_REQUIRE(stats && gamma && beta && scale && shift && count > 0, "snb_bn_finalize_ws: bad args");
   const int nblk = 64, chunk = (ntiles + nblk - 1) / nblk;
   snb_launch(bn_stats_prereduce_kernel, nblk, 256, 0, stream, stats, ntiles, chunk, scratch);
   SNB_LAUNCH_CHECK("bn_stats_prereduce_kernel");
-  return snb_bn_finalize(scratch, nblk, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, stream);
+  return bn_finalize_impl(scratch, nblk, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd, stream);
 }
 
 extern "C" int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,

@@ -345,6 +345,38 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
   }
 }
 
+// Batched variant: blockIdx.y picks a table entry {w, out, config, 0} (see snb_prep_conv_weights_tc_batch in snb200.h).
+__global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table) {
+  pdl_launch(); pdl_wait();
+  const long long* e = table + 4 * blockIdx.y;
+  const float* __restrict__ w = reinterpret_cast<const float*>(e[0]);
+  float* __restrict__ out = reinterpret_cast<float*>(e[1]);
+  const int cfg = (int)e[2];
+  const int nwin = cfg & 0xff, mode = (cfg >> 8) & 0xff, kind = (cfg >> 16) & 0xff, pa = (cfg >> 24) & 0xf, pb = (cfg >> 28) & 0xf;
+  const int taps = nwin * 3;
+  const int total = nwin * 96 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 31;
+    const int n = (i >> 5) % 96;
+    const int win = i / (96 * 32);
+    const int kw = n >> 5, co = n & 31;
+    int tap = win * 3 + kw;
+    const int oc = mode == 0 ? co : k, ic = mode == 0 ? k : co;        // dgrad: swap channels, flip taps
+    if (mode != 0) tap = taps - 1 - tap;
+    float v;
+    if (kind == 0) {
+      v = w[((size_t)oc * 32 + ic) * taps + tap];
+    } else {
+      const int y5 = 2 * (tap / 3) + pa, x5 = 2 * (tap % 3) + pb;
+      v = (y5 < 5 && x5 < 5) ? w[((size_t)oc * 32 + ic) * 25 + y5 * 5 + x5] : 0.f;
+    }
+    const float hi = __uint_as_float(tc::tf32_hi_bits(v));
+    const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
+    out[o] = hi;
+    out[o + B_BYTES / 4] = v - hi;
+  }
+}
+
 }  // namespace tc
 
 static int tc_setup(const snb_conv_geom* g, tc::Params& p, const char* who) {
@@ -383,6 +415,13 @@ extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int 
   const int nwin = kd * 3;
   snb_launch(tc::prep_weights_tc_kernel, snb_ceil_div(nwin * 96 * 32, 256), 256, 0, stream, w, out, nwin, mode);
   SNB_LAUNCH_CHECK("prep_weights_tc_kernel");
+  return 0;
+}
+
+extern "C" int snb_prep_conv_weights_tc_batch(const long long* table, int n, void* stream) {
+  SNB_REQUIRE(table && n > 0 && n <= 65535, "snb_prep_conv_weights_tc_batch: bad args");
+  snb_launch(tc::prep_weights_tc_batch_kernel, dim3(36, n), 256, 0, stream, table);
+  SNB_LAUNCH_CHECK("prep_weights_tc_batch_kernel");
   return 0;
 }
 

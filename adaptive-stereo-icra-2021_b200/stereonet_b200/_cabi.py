@@ -35,6 +35,7 @@ SIGNATURES = {
   "snb_conv_c32_tc_profile": (_I, [_P, _P, _P, _GP, _EP, _I, _P, _P]),
   "snb_prep_conv_weights_tc": (_I, [_P, _P, _I, _I, _P]),
   "snb_conv_weights_tc_floats": (_I, [_I]),
+  "snb_prep_conv_weights_tc_batch": (_I, [_P, _I, _P]),
   "snb_phase_split": (_I, [_P, _P, _I, _I, _I, _P]),
   "snb_phase_merge": (_I, [_P, _P, _I, _I, _I, _P]),
   "snb_conv5x5s2_c3": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
@@ -47,7 +48,7 @@ SIGNATURES = {
   "snb_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_upsample_bilinear_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_bn_finalize": (_I, [_P, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
-  "snb_bn_finalize_ws": (_I, [_P, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
+  "snb_bn_finalize_ws": (_I, [_P, _I, _LL, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
   "snb_bn_apply": (_I, [_P, _P, _P, _P, _P, _LL, _I, _P]),
   "snb_bwd_num_blocks": (_I, [_LL]),
   "snb_bn_lrelu_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P]),

@@ -35,6 +35,7 @@ class AdaptStepper:
     # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
     self.batched_replay = batched_replay
     self._graphs = {}
+    self._wprep = None                      # fused.WeightPrepBatch: all derived weight images in one launch per step
     self.launches_per_step = None
     if use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
       raise RuntimeError("AdaptStepper(use_graph=True) needs make_optimizer(..., capturable=True)")
@@ -63,6 +64,7 @@ class AdaptStepper:
   def _fwd_bwd(self, left, right, replay, static_shapes):
     s = self.stereo_net.input_scale
     self.feature_net.train(); self.stereo_net.train()
+    self._refresh_weights()
     if replay is not None and self.batched_replay:
       return self._fwd_bwd_batched(left, right, replay)
     outputs = self.predict(left, right)
@@ -77,6 +79,14 @@ class AdaptStepper:
     self.optimizer.zero_grad()
     loss.backward()
     return loss.detach(), fcs, outputs
+
+  def _refresh_weights(self):
+    from .autograd import fused
+    if fused.CONV_BACKEND == "ffma" or not torch.is_grad_enabled():
+      return
+    if self._wprep is None or not self._wprep.valid():
+      self._wprep = fused.WeightPrepBatch([self.feature_net, self.stereo_net])
+    self._wprep.refresh()
 
   def _fwd_bwd_batched(self, left, right, replay):
     """Row f3: one batch-(n+m) pass for the n stream frames and the m replay samples; Monodepth loss on the first n

@@ -148,6 +148,56 @@ def wprep_tc_phases(conv, mode):
   return _cached(conv, ("wtc_phase", mode), [conv.weight], make)
 
 
+class WeightPrepBatch:
+  """Every tensor-core weight image the adaptation step needs (forward and data-gradient images of all used 3x3 / 3x3x3
+  32->32 convolutions, the polyphase images of the 5x5 stride-2 ones) refreshed by ONE launch after an optimizer update,
+  instead of ~50 prep launches plus ~50 torch slicing / padding kernels per step.  The images live in one persistent
+  buffer; refresh() re-validates the per-module caches (`_cached`) so the layers find them as hits."""
+
+  def __init__(self, nets, modes=(0, 1)):
+    self.items = []                      # (conv, cache key, views, source pointer)
+    rows = []
+    plan = []
+    for net in nets:
+      for name, m in net.named_modules():
+        if not isinstance(m, (torch.nn.Conv2d, torch.nn.Conv3d)) or ".conv2" in name or name.startswith("conv2"):
+          continue                       # BasicBlock.conv2 is constructed but never used (stereo_net.py:40,44-51)
+        w = m.weight
+        if tuple(w.shape[:2]) != (32, 32):
+          continue
+        if tuple(w.shape[2:]) in ((3, 3), (3, 3, 3)) and m.stride[0] == 1:
+          kd = 3 if w.dim() == 5 else 1
+          for mode in modes:
+            plan.append((m, ("wtc", mode), [(kd * 3, mode, 0, 0, 0)]))
+        elif tuple(w.shape[2:]) == (5, 5) and m.stride[0] == 2:
+          for mode in modes:
+            plan.append((m, ("wtc_phase", mode), [(3, mode, 1, a, b) for a in (0, 1) for b in (0, 1)]))
+    per_win = ops.conv_weights_tc_floats(1) // 3
+    total = sum(cfg[0] * per_win for _, _, cfgs in plan for cfg in cfgs)
+    dev = plan[0][0].weight.device
+    self.buf = torch.empty((total,), device=dev, dtype=torch.float32)
+    off = 0
+    for m, key, cfgs in plan:
+      views = []
+      for nwin, mode, kind, a, b in cfgs:
+        v = self.buf[off:off + nwin * per_win]
+        off += nwin * per_win
+        views.append(v)
+        rows.append([m.weight.data_ptr(), v.data_ptr(), nwin | (mode << 8) | (kind << 16) | (a << 24) | (b << 28), 0])
+      self.items.append((m, key, views, m.weight.data_ptr()))
+    self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+    self.n = len(rows)
+
+  def valid(self):
+    return all(m.weight.data_ptr() == ptr and m.weight.is_contiguous() for m, _, _, ptr in self.items)
+
+  def refresh(self):
+    ops.prep_conv_weights_tc_batch(self.table, self.n)
+    for m, key, views, _ in self.items:
+      ver = (EPOCH, (m.weight.data_ptr(), m.weight._version))
+      m.__dict__.setdefault("_snb_cache", {})[key] = (ver, views[0] if key[0] == "wtc" else views)
+
+
 def conv5x5s2_c32(x, conv, bias, phases=None):
   """5x5 stride-2 pad-2 32->32 convolution: FFMA kernel, or four chained tensor-core 3x3 convs over the phase images
   (`phases`: the input already in polyphase form)."""

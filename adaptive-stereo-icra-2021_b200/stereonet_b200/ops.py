@@ -128,6 +128,16 @@ def prep_conv_weights_tc(w, mode=0):
   return out
 
 
+def conv_weights_tc_floats(kd):
+  return _cabi.lib().snb_conv_weights_tc_floats(kd)
+
+
+def prep_conv_weights_tc_batch(table, n):
+  """One launch for n weight images; `table` is an int64 device tensor [n,4] (see snb_prep_conv_weights_tc_batch)."""
+  check(_cabi.lib().snb_prep_conv_weights_tc_batch(_p(table), n, _stream(table)), "snb_prep_conv_weights_tc_batch")
+  _count()
+
+
 def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
                 flat=False, a_smem=False, out=None, legacy3d=False):
   """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.
@@ -280,12 +290,11 @@ def bn_finalize(stats, count, bn, update_running=True):
   rm = bn.running_mean if update_running else None
   rv = bn.running_var if update_running else None
   scratch = torch.empty((64, 64), device=dev, dtype=torch.float32)
+  nbt = bn.num_batches_tracked if (update_running and bn.num_batches_tracked is not None) else None   # += 1 in the same launch
   check(_cabi.lib().snb_bn_finalize_ws(_p(stats), stats.shape[0], int(count), _p(bn.weight.detach()), _p(bn.bias.detach()),
-                                       _p(rm), _p(rv), BN_MOMENTUM, BN_EPS, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                       _p(rm), _p(rv), _p(nbt), BN_MOMENTUM, BN_EPS, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
                                        _p(scratch), _stream(stats)), "snb_bn_finalize_ws")
   _count(2 if stats.shape[0] > 256 else 1)
-  if update_running and bn.num_batches_tracked is not None:
-    bn.num_batches_tracked += 1
   return out[0], out[1], out[2], out[3]
 
 

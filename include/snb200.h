@@ -106,6 +106,12 @@ SNB_API int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, float* 
  * one 24 KB block per (kd,kh) window).  kd = 1 (2-D) or 3 (3-D).  mode 0: forward, 1: data gradient. */
 SNB_API int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream);
 SNB_API int snb_conv_weights_tc_floats(int kd);
+/* All weight images of a model in ONE launch (the adaptation step re-derives ~50 of them after every optimizer update).
+ * table: n device-resident entries of 4 int64 = {source weight pointer, output image pointer, config, 0};
+ * config = nwin | mode << 8 | kind << 16 | a << 24 | b << 28.  kind 0: a [32][32][nwin*3] weight as in
+ * snb_prep_conv_weights_tc (nwin = 3 kd).  kind 1: the polyphase 3x3 sub-kernel (a, b) of a [32][32][5][5] stride-2 weight,
+ * sub[i][j] = w[2i + a][2j + b] (zero outside the 5x5 support), nwin = 3 (csrc/phase.cu). */
+SNB_API int snb_prep_conv_weights_tc_batch(const long long* table, int n, void* stream);
 
 /* Polyphase helpers for the stride-2 5x5 32->32 layers (stereo_net.py:64-70): the convolution is the sum of four stride-1
  * 'same' 3x3 convolutions over the phase images P_ab[i][j] = x[2i+a][2j+b], so forward and data gradient run on
@@ -156,9 +162,10 @@ SNB_API int snb_bn_finalize(const float* stats, int ntiles, long long count, con
                     float* running_mean, float* running_var, float momentum, float eps,
                     float* scale, float* shift, float* mean, float* invstd, void* stream);
 /* Same, with a caller-provided scratch of 64 x 64 floats: more than 256 partial rows are first reduced by 64 CTAs (a single
- * CTA walking ~1 MB of partials is bound by one SM's load bandwidth). */
+ * CTA walking ~1 MB of partials is bound by one SM's load bandwidth).  num_batches_tracked (nn.BatchNorm's int64 counter, or
+ * NULL) is incremented by the same launch when the running statistics are updated. */
 SNB_API int snb_bn_finalize_ws(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
-                       float* running_mean, float* running_var, float momentum, float eps,
+                       float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                        float* scale, float* shift, float* mean, float* invstd, float* scratch, void* stream);
 /* y = [residual +] LeakyReLU(z*scale + shift) over n positions x 32 channels. */
 SNB_API int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,
