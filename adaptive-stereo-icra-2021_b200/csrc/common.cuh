@@ -33,6 +33,19 @@ static inline void snb_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t
   cfg.attrs = at; cfg.numAttrs = snb_pdl_enabled() ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);     // errors are picked up by SNB_LAUNCH_CHECK
 }
+// same, as clusters of two CTAs (tcgen05 cta_group::2 kernels); grid.x must be even
+template <class... KA, class... A>
+static inline void snb_launch_cluster2(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, void* stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = snb_pdl_enabled() ? 2 : 1;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }

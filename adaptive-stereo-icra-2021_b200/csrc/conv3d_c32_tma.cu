@@ -11,11 +11,21 @@
 //   * windows of slices outside the volume (d' = -1, D) are skipped instead of multiplied as zeros.
 // Warps: 0 producer (TMA A + bulk B), 1 MMA issuer, 2-9 converters (two per TMEM lane quadrant, alternating windows),
 // 10-17 epilogue (two per quadrant).  smem: 6 x 16 KB raw A ring | 3 x 24 KB B ring (hi|lo) | 48 KB epilogue tiles.
-// TMEM: 4 accumulators x 96 (two tiles in flight + two draining) | 2 A slots x 64.
+// TMEM: 3 accumulators x 96 | 3 A slots x 64.
 // A CTA works on SUPER-TILES of two consecutive tiles of one slice: every (kd,kh) weight image is fetched once per pair, which
 // halves the dominant L2->smem stream (24 KB of weights against 16 KB of activations per window) and doubles the MMA work
 // behind each in-flight weight stage (the single-tile version was bound by exactly that stream / its latency).
+// PAIR = true (default): the same kernel as a cluster of two CTAs driving tcgen05.mma.cta_group::2 (M = 256: each CTA's TMEM
+// holds the A rows / accumulator of ITS tile, each CTA's smem holds HALF of the weight tile's N = 96 rows).  One CTA per tile
+// fetches the full 3 KB B operand per MMA and the kernel is bound by the 128 B/clk shared-memory port (725 cycles of smem
+// traffic per window against 581 cycles of MMA math); in a pair the B fetch and the streamed weight
+// image are halved per SM.  The leader (cluster rank 0) issues all MMAs; converters / epilogue warps of the peer arrive
+// remotely on the leader's barriers, the peer's otherwise idle MMA warp forwards "my weight half has landed", and every
+// tcgen05.commit is multicast to both CTAs.  A pair works on two consecutive super-tiles of one slice (same kd windows);
+// missing tiles at the end of a slice are dummies (TMA zero fill, no stores).
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include "tc_common.cuh"
 
 namespace tc3 {
@@ -26,7 +36,8 @@ constexpr int NR = 6;                                    // raw A ring depth (TM
 constexpr int NB = 3;                                    // B ring depth (one weight image serves both tiles of a pair)
 constexpr int NTHREADS3 = 18 * 32;
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;                // 8 converter warps: two per quadrant, alternating windows
-constexpr int NACC3 = 4, NA = 2;                           // TMEM: 4 accumulators x 96 columns | 2 A slots x 64 columns
+constexpr int NACC3 = 3, NA = 3;                           // TMEM: 3 accumulators x 96 columns | 3 A slots x 64 columns (the A-slot turnaround
+                                                           // commit -> convert -> tcgen05.st -> arrive is longer than one 12-MMA batch: 2 slots starve the MMA warp)
 constexpr int ACC_STRIDE = 96, TA_BASE = NACC3 * 96;
 constexpr int SMEM_BYTES3 = NR * A_BYTES + NB * 2 * B_BYTES + OUT_BYTES + 3072 /*barriers, stats scratch*/ + 1024 /*alignment slack*/;
 
@@ -49,8 +60,67 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n"
+               :: "r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+template <bool PAIR> __device__ __forceinline__ void arrive_on_leader(uint64_t* bar, uint32_t rank) {
+  if (PAIR && rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// warp-uniform wait (see tc::mbar_wait_warp) with cluster-scope acquire: barriers that receive remote arrivals
+__device__ __forceinline__ void mbar_wait_warp_cluster(uint64_t* bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) return;
+  const long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) {
+    __nanosleep(20);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+constexpr uint32_t IDESC_M256 = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((256u >> 4) << 24);
+__device__ __forceinline__ void mma2_tf32_ts_raw(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC_M256), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_commit_raw(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// work decomposition shared by all roles.  PAIR: unit = two consecutive super-tiles of one slice, this CTA takes the one with
+// its cluster rank; always two tiles per super-tile (missing ones are dummies).  Single: unit = one super-tile.
+struct Unit { int slice, sst, nh; };
+template <bool PAIR> __device__ __forceinline__ int unit_first(uint32_t rank) { return PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+template <bool PAIR> __device__ __forceinline__ int unit_step() { return PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
+template <bool PAIR> __device__ __forceinline__ Unit unit_of(int u, int spt, int tiles_per_slice, uint32_t rank) {
+  Unit r;
+  if (PAIR) {
+    const int ppu = (spt + 1) >> 1;
+    r.slice = u / ppu; r.sst = 2 * (u - r.slice * ppu) + (int)rank; r.nh = 2;
+  } else {
+    r.slice = u / spt; r.sst = u - r.slice * spt; r.nh = (2 * r.sst + 1 < tiles_per_slice) ? 2 : 1;
+  }
+  return r;
+}
+
 __device__ __forceinline__ void epi_bar3() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS3, 1)
 conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p) {
   pdl_launch();
@@ -68,25 +138,35 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
   uint64_t* aempty = afull + NA;         // [NA]    MMA commit -> converters
   uint64_t* tfull = aempty + NA;         // [NACC3] MMA commit -> epilogue
   uint64_t* tempty = tfull + NACC3;      // [NACC3] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC3);
+  uint64_t* bpeer = tempty + NACC3;       // [NB]    PAIR: the peer's weight half has landed (remote arrive) -> leader's MMA warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bpeer + NB);
   float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  const int nunits = PAIR ? p.B * p.D * ((p.spt + 1) >> 1) : p.nsuper;
 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); }
       for (int i = 0; i < NB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-      for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
-      for (int i = 0; i < NACC3; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
+      for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], PAIR ? 8 : 4); mbar_init(&aempty[i], 1); }
+      for (int i = 0; i < NACC3; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
+      for (int i = 0; i < NB; ++i) mbar_init(&bpeer[i], 1);
       mbar_fence_init();
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                      // everything above touched no global memory
@@ -94,32 +174,55 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
 
   if (warp == 0) {
     // =============================================================== producer: one TMA tile load (A) + one bulk copy (B) per window
+    // Two independent loops on two lanes: lane 0 streams the A windows, lane 1 the weight stages.  In one thread the wait for a
+    // free weight stage also held back the A loads behind it in program order, and the converters starved (cv_wait_rfull).
     if (lane == 0) {
-      uint32_t ac = 0, bc = 0;
-      long long w_r = 0, w_b = 0; const long long t0 = clock64();
-      for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x) {
-        const int slice = st / p.spt, sst = st - slice * p.spt;
+      uint32_t ac = 0;
+      long long w_r = 0; const long long t0 = clock64();
+      for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
+        const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+        const int slice = un.slice, sst = un.sst, nh = un.nh;
         const int b = slice / p.D, d = slice - b * p.D;
-        const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
         for (int widx = 0; widx < 9; ++widx) {
           const int kd = widx / 3, kh = widx - kd * 3;
           const int dd = d + kd - 1;
           if ((unsigned)dd >= (unsigned)p.D) continue;
-          const uint32_t sb = bc % NB;
-          T3WAIT(w_b, tc::mbar_wait(&bempty[sb], ((bc / NB) & 1) ^ 1));
-          mbar_expect_tx(&bfull[sb], 2 * B_BYTES);
-          bulk_g2s(sBring + sb * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[sb]);
-          ++bc;
           for (int h = 0; h < nh; ++h) {
             const uint32_t sa = ac % NR;
             T3WAIT(w_r, tc::mbar_wait(&rempty[sa], ((ac / NR) & 1) ^ 1));
             mbar_expect_tx(&rfull[sa], A_BYTES);
-            tma_load_4d(base + sa * A_BYTES, &tmap, &rfull[sa], 0, (2 * sst + h) * p.step - 1 + (kh - 1) * p.W, dd, b);
+            int q = (2 * sst + h) * p.step - 1 + (kh - 1) * p.W;
+            if (2 * sst + h >= p.tiles_per_slice) q = HW + 1024;          // dummy tile of a pair: everything out of bounds -> zero fill
+            tma_load_4d(base + sa * A_BYTES, &tmap, &rfull[sa], 0, q, dd, b);
             ++ac;
           }
         }
       }
-      if (p.dbg) { long long* dd = p.dbg + blockIdx.x * 16; dd[0] = w_r; dd[1] = w_b; dd[2] = clock64() - t0; }
+      if (p.dbg) { long long* dd = p.dbg + blockIdx.x * 16; dd[0] = w_r; dd[2] = clock64() - t0; }
+    } else if (lane == 1) {
+      uint32_t bc = 0;
+      long long w_b = 0;
+      for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
+        const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+        const int d = un.slice % p.D;
+        for (int widx = 0; widx < 9; ++widx) {
+          const int dd = d + widx / 3 - 1;
+          if ((unsigned)dd >= (unsigned)p.D) continue;
+          const uint32_t sb = bc % NB;
+          T3WAIT(w_b, tc::mbar_wait(&bempty[sb], ((bc / NB) & 1) ^ 1));
+          if (PAIR) {       // this CTA's half of the N = 96 weight rows: rows [48 rank, 48 rank + 48) of B_hi and of B_lo
+            mbar_expect_tx(&bfull[sb], B_BYTES);
+            const float* wsrc = p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW + rank * (48 * 32);
+            bulk_g2s(sBring + sb * 2 * B_BYTES, wsrc, B_BYTES / 2, &bfull[sb]);
+            bulk_g2s(sBring + sb * 2 * B_BYTES + B_BYTES / 2, wsrc + B_BYTES / 4, B_BYTES / 2, &bfull[sb]);
+          } else {
+            mbar_expect_tx(&bfull[sb], 2 * B_BYTES);
+            bulk_g2s(sBring + sb * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[sb]);
+          }
+          ++bc;
+        }
+      }
+      if (p.dbg) { long long* dd = p.dbg + blockIdx.x * 16; dd[1] = w_b; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -129,12 +232,31 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     uint32_t ac = 0, bc = 0, accpar = 0;         // accpar bit a = (number of earlier uses of accumulator a) & 1
     long long w_a = 0, w_bf = 0, w_t = 0; const long long t0 = clock64();
     int it = 0;
-    for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x, ++it) {
-      const int slice = st / p.spt, sst = st - slice * p.spt;
-      const int d = slice % p.D;
-      const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
-      const int acc0 = (it & 1) * 2;
-      for (int h = 0; h < nh; ++h) T3WAIT(w_t, mbar_wait_warp(&tempty[acc0 + h], ((accpar >> (acc0 + h)) & 1) ^ 1));
+    if (PAIR && rank != 0) {
+      // peer CTA: no MMA issue; forward "my half of the weight stage has landed" to the leader
+      for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
+        const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+        const int d = un.slice % p.D;
+        for (int widx = 0; widx < 9; ++widx) {
+          const int dd = d + widx / 3 - 1;
+          if ((unsigned)dd >= (unsigned)p.D) continue;
+          const uint32_t sbi = bc % NB;
+          T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
+          if (lane == 0) mbar_arrive_remote(&bpeer[sbi], 0);
+          __syncwarp();
+          ++bc;
+        }
+      }
+    } else
+    for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>(), ++it) {
+      const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+      const int d = un.slice % p.D;
+      const int nh = un.nh;
+      const int accs[2] = {(2 * it) % NACC3, (2 * it + 1) % NACC3};
+      for (int h = 0; h < nh; ++h) {
+        if (PAIR) T3WAIT(w_t, mbar_wait_warp_cluster(&tempty[accs[h]], ((accpar >> accs[h]) & 1) ^ 1));
+        else      T3WAIT(w_t, mbar_wait_warp(&tempty[accs[h]], ((accpar >> accs[h]) & 1) ^ 1));
+      }
       tc_fence_after();
       bool first = true;
       for (int widx = 0; widx < 9; ++widx) {
@@ -142,33 +264,49 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         if ((unsigned)dd >= (unsigned)p.D) continue;
         const uint32_t sbi = bc % NB;
         T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
+        if (PAIR) T3WAIT(w_bf, mbar_wait_warp_cluster(&bpeer[sbi], (bc / NB) & 1));
         const uint32_t sb = smem_u + NR * A_BYTES + sbi * 2 * B_BYTES;
         for (int h = 0; h < nh; ++h) {
           const uint32_t aslot = ac % NA;
-          T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
+          if (PAIR) T3WAIT(w_a, mbar_wait_warp_cluster(&afull[aslot], (ac / NA) & 1));
+          else      T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
           tc_fence_after();
           const uint32_t ta = tmem_u + TA_BASE + aslot * 64;
-          const uint32_t tmem_d = tmem_u + (acc0 + h) * ACC_STRIDE;
+          const uint32_t tmem_d = tmem_u + accs[h] * ACC_STRIDE;
           if (elect_one()) {                     // one election per 12 MMAs + commit (see tc_common.cuh)
+            const uint32_t lo_off = PAIR ? B_BYTES / 2 : B_BYTES;       // B_lo follows B_hi (half-height images in a pair)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t bh = make_desc(sb + ks * 32);
-              mma_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
-              if (p.passes == 3) {
-                mma_tf32_ts_raw(tmem_d, ta + 32 + ks * 8, bh, 1);
-                mma_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
+              if (PAIR) {
+                mma2_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
+                if (p.passes == 3) {
+                  mma2_tf32_ts_raw(tmem_d, ta + 32 + ks * 8, bh, 1);
+                  mma2_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + lo_off + ks * 32), 1);
+                }
+              } else {
+                mma_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
+                if (p.passes == 3) {
+                  mma_tf32_ts_raw(tmem_d, ta + 32 + ks * 8, bh, 1);
+                  mma_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + lo_off + ks * 32), 1);
+                }
               }
             }
-            mma_commit_raw(&aempty[aslot]);
+            if (PAIR) mma2_commit_raw(&aempty[aslot]); else mma_commit_raw(&aempty[aslot]);
           }
           __syncwarp();
           ++ac;
         }
         first = false;
-        mma_commit(&bempty[sbi]);
+        if (elect_one()) { if (PAIR) mma2_commit_raw(&bempty[sbi]); else mma_commit_raw(&bempty[sbi]); }
+        __syncwarp();
         ++bc;
       }
-      for (int h = 0; h < nh; ++h) { mma_commit(&tfull[acc0 + h]); accpar ^= 1u << (acc0 + h); }
+      for (int h = 0; h < nh; ++h) {
+        if (elect_one()) { if (PAIR) mma2_commit_raw(&tfull[accs[h]]); else mma_commit_raw(&tfull[accs[h]]); }
+        __syncwarp();
+        accpar ^= 1u << accs[h];
+      }
     }
     if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[3] = w_a; dd[4] = w_bf; dd[5] = w_t; dd[6] = clock64() - t0; }
   } else if (warp < EPI_WARP0) {
@@ -178,10 +316,10 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     const int m = quad * 32 + lane;
     uint32_t cnt = 0;                                              // A items: (window, tile of the pair)
     long long w_rf = 0, w_ae = 0, w_st = 0; const long long t0 = clock64();
-    for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x) {
-      const int slice = st / p.spt, sst = st - slice * p.spt;
-      const int d = slice % p.D;
-      const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
+    for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
+      const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+      const int d = un.slice % p.D;
+      const int nh = un.nh;
       for (int item = 0; item < 9 * nh; ++item) {
         const int widx = item / nh;
         const int dd = d + widx / 3 - 1;
@@ -222,7 +360,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         T3WAIT(w_st, tmem_wait_st());
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&afull[aslot]);
+        if (lane == 0) arrive_on_leader<PAIR>(&afull[aslot], rank);
         ++cnt;
       }
     }
@@ -246,16 +384,17 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     int it = 0;
     long long w_tf = 0; const long long t0 = clock64();
     uint32_t accpar = 0;                             // same bookkeeping as the MMA warp (a single-tile pair skips one accumulator)
-    for (int st = blockIdx.x; st < p.nsuper; st += gridDim.x, ++it) {
-     const int slice = st / p.spt, sst = st - slice * p.spt;
-     const int nh = (2 * sst + 1 < p.tiles_per_slice) ? 2 : 1;
+    for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>(), ++it) {
+     const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+     const int slice = un.slice, sst = un.sst, nh = un.nh;
      for (int hh2 = 0; hh2 < nh; ++hh2) {
-      const int acc = (it & 1) * 2 + hh2;
+      const int acc = (2 * it + hh2) % NACC3;
       const uint32_t accphase = (accpar >> acc) & 1;
       accpar ^= 1u << acc;
       const int tt = 2 * sst + hh2;
+      const bool real_tile = tt < p.tiles_per_slice;      // false: dummy tile of a pair (nothing is stored)
       const int tile = slice * p.tiles_per_slice + tt;
-      const int q0 = tt * p.step - 1;
+      const int q0 = real_tile ? tt * p.step - 1 : HW;
       int ww[4]; bool okr[4]; size_t goff[4];
       {
         const int q = q0 + rg;
@@ -295,7 +434,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) arrive_on_leader<PAIR>(&tempty[acc], rank);
       epi_bar3();
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -331,7 +470,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
           for (int c = 0; c < 4; ++c) { sRed[ew * 64 + lane * 4 + c] = s1[c]; sRed[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
         }
         epi_bar3();
-        if (et < 64) {
+        if (et < 64 && real_tile) {
           float a = 0.f;
 #pragma unroll
           for (int wq = 0; wq < NUM_EPI_WARPS; ++wq) a += sRed[wq * 64 + et];
@@ -346,9 +485,11 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // the peer may still be reading its accumulators / receiving multicast arrivals
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
+    else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
   }
 }
 
@@ -411,9 +552,17 @@ int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = p.nsuper < sms ? p.nsuper : sms;
-  SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
-  snb_launch(tc3::conv3d_c32_tma_kernel, grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
+  static const bool single = []() { const char* s = getenv("SNB200_CONV3D"); return s != nullptr && strcmp(s, "1cta") == 0; }();
+  if (single || sms < 2) {
+    const int grid = p.nsuper < sms ? p.nsuper : sms;
+    SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
+    snb_launch(tc3::conv3d_c32_tma_kernel<false>, grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
+  } else {
+    const int npu = g->B * g->D * ((p.spt + 1) / 2);            // pair units
+    const int ncl = npu < sms / 2 ? npu : sms / 2;
+    SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
+    snb_launch_cluster2(tc3::conv3d_c32_tma_kernel<true>, 2 * ncl, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
+  }
   SNB_LAUNCH_CHECK("conv3d_c32_tma_kernel");
   return 0;
 }
