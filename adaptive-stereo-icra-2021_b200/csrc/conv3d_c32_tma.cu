@@ -15,14 +15,17 @@
 // A CTA works on SUPER-TILES of two consecutive tiles of one slice: every (kd,kh) weight image is fetched once per pair, which
 // halves the dominant L2->smem stream (24 KB of weights against 16 KB of activations per window) and doubles the MMA work
 // behind each in-flight weight stage (the single-tile version was bound by exactly that stream / its latency).
-// PAIR = true (default): the same kernel as a cluster of two CTAs driving tcgen05.mma.cta_group::2 (M = 256: each CTA's TMEM
+// PAIR = true (experimental, SNB200_CONV3D=pair): the same kernel as a cluster of two CTAs driving tcgen05.mma.cta_group::2 (M = 256: each CTA's TMEM
 // holds the A rows / accumulator of ITS tile, each CTA's smem holds HALF of the weight tile's N = 96 rows).  One CTA per tile
 // fetches the full 3 KB B operand per MMA and the kernel is bound by the 128 B/clk shared-memory port (725 cycles of smem
 // traffic per window against 581 cycles of MMA math); in a pair the B fetch and the streamed weight
 // image are halved per SM.  The leader (cluster rank 0) issues all MMAs; converters / epilogue warps of the peer arrive
 // remotely on the leader's barriers, the peer's otherwise idle MMA warp forwards "my weight half has landed", and every
 // tcgen05.commit is multicast to both CTAs.  A pair works on two consecutive super-tiles of one slice (same kd windows);
-// missing tiles at the end of a slice are dummies (TMA zero fill, no stores).
+// missing tiles at the end of a slice are dummies (TMA zero fill, no stores).  Parity-green but 20 % SLOWER than one CTA per tile
+// (255 vs 203 us at batch 4): an A slot now turns around through commit -> multicast arrive -> convert -> tcgen05.st -> REMOTE
+// arrive, longer than the two 12-MMA batches the other slots cover, and the pair runs in lock step.  Kept for the next round
+// (needs A slots / accumulators decoupled per CTA), not the default.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -552,7 +555,8 @@ int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static const bool single = []() { const char* s = getenv("SNB200_CONV3D"); return s != nullptr && strcmp(s, "1cta") == 0; }();
+  // SNB200_CONV3D=pair selects the experimental cta_group::2 variant (measured slower, see the header comment)
+  static const bool single = []() { const char* s = getenv("SNB200_CONV3D"); return !(s != nullptr && strcmp(s, "pair") == 0); }();
   if (single || sms < 2) {
     const int grid = p.nsuper < sms ? p.nsuper : sms;
     SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
