@@ -16,6 +16,8 @@ wa = torch.randn(1, 32, 3, 3, 3, device=dev)
 fl = torch.randn(1, 47, 156, 32, device=dev); fr = torch.randn(1, 47, 156, 32, device=dev)
 fl8 = torch.randn(8, 47, 156, 32, device=dev); fr8 = torch.randn(8, 47, 156, 32, device=dev)
 g2 = ops.geom((1, 376, 1248, 32), 3, dil=1); g28 = ops.geom((1, 376, 1248, 32), 3, dil=8); g3 = ops.geom((1, 24, 47, 156, 32), 3)
+img = torch.rand(2, 3, 376, 1248, device=dev); w5 = torch.randn(32, 3, 5, 5, device=dev) * 0.2
+coarse = torch.rand(1, 47, 156, device=dev) * 20; rgb = img[:1].contiguous(); w4 = torch.randn(32, 4, 3, 3, device=dev) * 0.2
 for rep in range(3):
   flush.zero_(); ops.conv_c32_tc(x2, w2, g2, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True)
   flush.zero_(); ops.conv_c32_tc(x2, w2, g28, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True)
@@ -26,5 +28,7 @@ for rep in range(3):
   flush.zero_(); ops.cost_volume(fl8, fr8, 24)
   flush.zero_(); taps = ops.conv_c32_taps(x3, wa, 27)
   flush.zero_(); ops.tapsum_softargmin(taps, b[:1].contiguous(), True)
+  flush.zero_(); ops.conv5x5s2_c3_phases(img, w5, b)
+  flush.zero_(); ops.refine_in_conv(coarse, rgb, w4, b, scale=sc, shift=sh, lrelu=True)
 torch.cuda.synchronize()
 print("ok")

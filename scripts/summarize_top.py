@@ -20,7 +20,7 @@ with open("profiles/r1_ncu_top_kernels_full.txt", "w") as f:
 def nbytes(d, k):
   v, unit = d[k]
   return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-names = ["conv2d_dil1", "conv2d_dil8", "conv3d", "wgrad2d", "wgrad3d", "cost_volume_b1", "cost_volume_b8", "taps27", "tapsum_softargmin"]
+names = ["conv2d_dil1", "conv2d_dil8", "conv3d", "wgrad2d", "wgrad3d", "cost_volume_b1", "cost_volume_b8", "taps27", "tapsum_softargmin", "first_conv5x5s2", "refine_in_conv"]
 summ = {}
 for n, d in zip(names, out):
   summ[n] = {"kernel": re.sub(r"\(.*", "", d["Kernel Name"][0]), "us": float(d["gpu__time_duration.sum"][0]),
