@@ -293,6 +293,17 @@ def gpu_arm(args):
       taps = ops.conv_c32_taps(x3, snet.conv3d_alone.weight, 27)
       sa_ms, _ = time_kernel(lambda: ops.tapsum_softargmin(taps, snet.conv3d_alone.bias, True), 20, flush, stream)
       sa_bytes = 4 * hc * wc * (27 * D + D + 1)
+      tp_ms, _ = time_kernel(lambda: ops.conv_c32_taps(x3, snet.conv3d_alone.weight, 27), 20, flush, stream)
+      tp_bytes = 4 * D * hc * wc * (32 + 27)
+      img2 = torch.rand(2, 3, H, W, device=dev)
+      c0 = fnet.downsample[0]
+      fc_ms, _ = time_kernel(lambda: ops.conv5x5s2_c3(img2, c0.weight, c0.bias), 20, flush, stream)
+      fc_flops = 2 * 2 * 75 * 32 * ((H - 1) // 2 + 1) * ((W - 1) // 2 + 1)
+      ref = snet.edge_aware_refinements[0]
+      cz = torch.rand(1, hc, wc, device=dev) * 20
+      rconv = ref.conv2d_feature[0][0]
+      ri_ms, _ = time_kernel(lambda: ops.refine_in_conv(cz, img2[:1], rconv.weight, rconv.bias.detach(), lrelu=True), 20, flush, stream)
+      ri_bytes = 4 * H * W * (32 + 3 + 1)
     kernels = {
       "cost_volume": {"bound": "hbm", "ms": cv_ms, "achieved": cv_bytes / cv_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
                       "frac": cv_bytes / cv_ms / 1e6 / pk["hbm"], "frac_of_nominal_8TBs": cv_bytes / cv_ms / 1e6 / 8000.0,
@@ -304,6 +315,12 @@ def gpu_arm(args):
                               "unit": "TFLOP/s", "frac": f3_flops / f3_ms / 1e9 / pk["tensor"], "algorithmic_flops": f3_flops},
       "refine_conv2d_32x32_dil4": {"bound": "tensor", "ms": r2_ms, "achieved": r2_flops / r2_ms / 1e9, "peak": pk["tensor"],
                                    "unit": "TFLOP/s", "frac": r2_flops / r2_ms / 1e9 / pk["tensor"], "algorithmic_flops": r2_flops},
+      "head_tap_contraction_27": {"bound": "hbm", "ms": tp_ms, "achieved": tp_bytes / tp_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                                  "frac": tp_bytes / tp_ms / 1e6 / pk["hbm"], "algorithmic_bytes": tp_bytes},
+      "first_conv5x5s2_2images": {"bound": "tensor", "ms": fc_ms, "achieved": fc_flops / fc_ms / 1e9, "peak": pk["tensor"],
+                                  "unit": "TFLOP/s", "frac": fc_flops / fc_ms / 1e9 / pk["tensor"], "algorithmic_flops": fc_flops},
+      "refine_in_conv": {"bound": "hbm", "ms": ri_ms, "achieved": ri_bytes / ri_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": ri_bytes / ri_ms / 1e6 / pk["hbm"], "algorithmic_bytes": ri_bytes},
       "tapsum_softargmin": {"bound": "hbm", "ms": sa_ms, "achieved": sa_bytes / sa_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
                             "frac": sa_bytes / sa_ms / 1e6 / pk["hbm"], "algorithmic_bytes": sa_bytes},
     }
