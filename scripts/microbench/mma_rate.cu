@@ -15,16 +15,20 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <int N, bool TA, int NACC, int BG>
-__global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters) {
+__global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters, int rnd, const float* gsrc) {
   __shared__ volatile int stop_flag;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;      // target of the periodic commits (BG == 5/6)
   __shared__ uint32_t tslot;
   const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
-  for (int i = threadIdx.x; i < (16384 + 32768 + 65536) / 4; i += 288) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  for (int i = threadIdx.x; i < (16384 + 32768 + 65536) / 4; i += 288) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    reinterpret_cast<float*>(smem)[i] = rnd ? ((float)(h & 0xffffff) / 8388608.0f - 1.0f) : 1.0f;     // random operands toggle far more bits than constants
+  }
   if (threadIdx.x == 0) stop_flag = 0;
   if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;\n"); }
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&bar))); asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&bar2))); asm volatile("fence.mbarrier_init.release.cluster;\n"); }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(&tslot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -34,6 +38,19 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tslot;
+  if (rnd && threadIdx.x >= 32 && threadIdx.x < 160) {       // random A operand in TMEM columns 448..479 (4 warps = 4 lane quadrants)
+    const int w = threadIdx.x >> 5, quad = w & 3;
+    uint32_t r[16];
+    for (int half = 0; half < 2; ++half) {
+      for (int i = 0; i < 16; ++i) { uint32_t h = (threadIdx.x * 64 + half * 16 + i) * 2654435761u; h ^= h >> 15; h *= 2246822519u; r[i] = __float_as_uint((float)(h & 0xffffff) / 8388608.0f - 1.0f); }
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                   :: "r"(tmem + ((uint32_t)(quad * 32) << 16) + 448 + half * 16), "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),"r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
   long long t0 = 0, t1 = 0;
   if (threadIdx.x < 32) {
@@ -53,6 +70,8 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters)
             else    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                                  :: "r"(td), "l"(make_desc(sa + ks * 32)), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
           }
+          // BG == 5: one commit per 12 MMAs (as the convolution kernels do per A slot); BG == 6: one per 3 MMAs
+          if (BG == 6 || (BG == 5 && ks == 3)) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(&bar2)) : "memory");
         }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(&bar)) : "memory");
@@ -82,6 +101,23 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters)
         asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
                      :: "r"(tmem + ((uint32_t)(quad * 32) << 16) + 480), "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),"r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15]) : "memory");
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      } else if (BG == 7) {
+        // one thread streams 16 KB TMA bulk copies global -> smem (async proxy writes, as the A windows / weight stages do)
+        if (threadIdx.x == 32) {
+          __shared__ uint64_t tbar;
+          asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&tbar)));
+          asm volatile("fence.mbarrier_init.release.cluster;\n");
+          uint32_t ph = 0; int slot = 0;
+          while (!stop_flag) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(&tbar)), "r"(2 * 16384) : "memory");
+            for (int k = 0; k < 2; ++k)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                           :: "r"(smem_u32(smem + 49152 + 1024 + ((slot + k) & 3) * 16384)), "l"(gsrc + (size_t)((blockIdx.x * 8 + slot + k) & 1023) * 4096), "r"(16384), "r"(smem_u32(&tbar)) : "memory");
+            uint32_t ok = 0;
+            while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(&tbar)), "r"(ph) : "memory");
+            ph ^= 1; slot += 2;
+          }
+        } else __nanosleep(200);
       } else {
         __nanosleep(200);
       }
@@ -94,11 +130,13 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters)
 }
 
 template <int N, bool TA, int NACC, int BG>
-void run(const char* tag) {
+void run(const char* tag, int rnd = 0, int iters = 200) {
   long long* d; cudaMalloc(&d, 148 * sizeof(long long));
-  const int iters = 200, smem = 16384 + 32768 + 65536 + 2048;
+  static float* gsrc = nullptr;
+  if (!gsrc) { cudaMalloc(&gsrc, 1024 * 16384); cudaMemset(gsrc, 0, 1024 * 16384); }
+  const int smem = 16384 + 32768 + 65536 + 2048;
   cudaFuncSetAttribute(rate_kernel<N, TA, NACC, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC, BG><<<148, 288, smem>>>(d, iters);
+  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC, BG><<<148, 288, smem>>>(d, iters, rnd, gsrc);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   double s = 0; for (int i = 0; i < 148; ++i) s += h[i];
@@ -114,5 +152,10 @@ int main() {
   run<96, true, 3, 4>("A tmem, alternating B images");
   run<96, true, 3, 1>("A tmem + 8 warps LDS/STS"); run<96, false, 3, 1>("A smem + 8 warps LDS/STS");
   run<96, true, 3, 2>("A tmem + 8 warps tcgen05.ld"); run<96, true, 3, 3>("A tmem + 8 warps tcgen05.st");
+  // operand data and duration: constants vs random values, 0.8k vs 20k MMAs per SM (power management reacts to both)
+  run<96, true, 3, 0>("A tmem, random data", 1); run<96, true, 3, 0>("A tmem, random, 20k MMAs", 1, 1700); run<96, true, 3, 0>("A tmem, ones, 20k MMAs", 0, 1700);
+  run<96, true, 3, 1>("A tmem, random + LDS/STS", 1, 1700);
+  run<96, true, 3, 7>("A tmem + TMA bulk g2s stream", 1, 1700);
+  run<96, true, 3, 5>("A tmem, commit per 12 MMAs"); run<96, true, 3, 6>("A tmem, commit per 3 MMAs");
   return 0;
 }
