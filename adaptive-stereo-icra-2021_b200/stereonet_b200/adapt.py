@@ -20,7 +20,8 @@ def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
 class AdaptStepper:
   """use_graph=True captures the WHOLE update (forward, loss, backward, [gradient all-reduce,] clip, Adam) in one CUDA
   graph per input shape and replays it per frame: at batch 1 the step is ~700 launches of 3-100 us kernels, so eager
-  execution is bound by host launch latency.  Requires an optimizer built with capturable=True and no replay term."""
+  execution is bound by host launch latency.  Requires an optimizer built with capturable=True.  The experience-replay term
+  (`replay=(left, right, gt)`) is captured too (static replay buffers, fused Khamis loss)."""
 
   def __init__(self, feature_net, stereo_net, optimizer, height, width, clip_grad_norm=True, er_loss_weight=0.05,
                use_graph=False, fused_loss=False, batched_replay=False):
@@ -50,8 +51,8 @@ class AdaptStepper:
     between backward and clip, eager path only) or `dp_params` (+ `dp_group`): the gradients of those parameters are
     packed into one flat bucket, SUM-all-reduced over NCCL and averaged.  With use_graph=True the step then becomes
     graph(fwd + loss + bwd + pack) -> eager all-reduce -> graph(unpack + clip + Adam): the collective is not captured."""
-    if self.use_graph and replay is None and sync_grads is None:
-      return self._step_graph(left, right, dp_params, dp_group)
+    if self.use_graph and sync_grads is None:
+      return self._step_graph(left, right, dp_params, dp_group, replay)
     if dp_params is not None and sync_grads is None:
       from . import parallel
       sync_grads = lambda: parallel.allreduce_gradients(dp_params, dp_group)
@@ -73,8 +74,12 @@ class AdaptStepper:
     else:
       loss = monodepth_single_loss(left, right, outputs, self.warper, s, static_shapes=static_shapes)
     if replay is not None:
-      out_er = self.predict(replay[0], replay[1])
-      loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
+      out_er = self.predict(replay[0], replay[1])                                   # adapt.py:339-349: a second full pass
+      pred_er = out_er["pred_disp_l/{}".format(s)]
+      # static shapes (graph capture): the fused kernel computes the same masked mean without boolean indexing
+      l_er = (khamis_robust_loss_fused(pred_er, replay[2].reshape(pred_er.shape)) if static_shapes
+              else khamis_robust_loss(pred_er, replay[2]))
+      loss = loss + self.er_loss_weight * l_er
     fcs = feature_contrast_mean(outputs["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
     self.optimizer.zero_grad()
     loss.backward()
@@ -120,13 +125,14 @@ class AdaptStepper:
       ts += [v for v in st.values() if isinstance(v, torch.Tensor)]
     return ts
 
-  def _capture(self, left, right, dp_params, dp_group):
+  def _capture(self, left, right, dp_params, dp_group, replay=None):
     import torch.distributed as dist
     from . import ops, parallel
     from .autograd import fused
     self.feature_net.train(); self.stereo_net.train()
     dev = left.device
     sl, sr = left.clone(), right.clone()
+    srep = None if replay is None else tuple(t.clone() for t in replay)        # static replay buffers (left, right, gt)
     world = dist.get_world_size(dp_group) if dp_params is not None else 1
     fresh = len(self.optimizer.state) == 0
     snap = [(t, t.detach().clone()) for t in self._state_tensors()]
@@ -137,7 +143,7 @@ class AdaptStepper:
       # One eager warm-up step allocates the lazily-created state (Adam moments and step counters, derived-weight
       # caches, allocator pools); model and optimizer state are restored afterwards so that capturing does not advance
       # the adaptation.
-      self._fwd_bwd(sl, sr, None, static_shapes=True)
+      self._fwd_bwd(sl, sr, srep, static_shapes=True)
       if dp_params is not None:
         parallel.allreduce_gradients(dp_params, dp_group)
       self._update()
@@ -156,7 +162,7 @@ class AdaptStepper:
     g1 = torch.cuda.CUDAGraph()
     flat = None
     with torch.cuda.graph(g1):
-      out = self._fwd_bwd(sl, sr, None, static_shapes=True)
+      out = self._fwd_bwd(sl, sr, srep, static_shapes=True)
       if dp_params is not None:
         flat = parallel.pack_gradients(dp_params)
       else:
@@ -169,17 +175,21 @@ class AdaptStepper:
           parallel.unpack_gradients(dp_params, flat, world)
         self._update()
     self.launches_per_step = ops.LAUNCHES - n0          # library kernels inside one replay
-    return dict(g1=g1, g2=g2, flat=flat, left=sl, right=sr, out=out)
+    return dict(g1=g1, g2=g2, flat=flat, left=sl, right=sr, replay=srep, out=out)
 
-  def _step_graph(self, left, right, dp_params, dp_group):
+  def _step_graph(self, left, right, dp_params, dp_group, replay=None):
     import torch.distributed as dist
     from .autograd import fused
-    key = (tuple(left.shape), str(left.device), None if dp_params is None else len(dp_params))
+    key = (tuple(left.shape), str(left.device), None if dp_params is None else len(dp_params),
+           None if replay is None else tuple(tuple(t.shape) for t in replay), self.batched_replay)
     e = self._graphs.get(key)
     if e is None:
-      e = self._graphs[key] = self._capture(left, right, dp_params, dp_group)
+      e = self._graphs[key] = self._capture(left, right, dp_params, dp_group, replay)
     e["left"].copy_(left, non_blocking=True)
     e["right"].copy_(right, non_blocking=True)
+    if replay is not None:
+      for dst, src in zip(e["replay"], replay):
+        dst.copy_(src, non_blocking=True)
     e["g1"].replay()
     if e["g2"] is not None:
       dist.all_reduce(e["flat"], op=dist.ReduceOp.SUM, group=dp_group)      # eager, between the two graphs

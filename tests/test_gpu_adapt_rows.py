@@ -151,3 +151,29 @@ def test_batched_replay_step():
   assert abs(la - lb) <= 2e-5 * max(1.0, abs(lb)), (la, lb)
   for n in wa:
     assert (wa[n] - wb[n]).abs().max().item() <= 2.1 * 5e-5, n      # one Adam step: entries differ by at most 2 * lr
+
+
+def test_replay_step_cuda_graph_matches_eager():
+  """The ER step (adapt.py:339-349: second pass on a replay sample, Khamis loss, 1 : 0.05 mix) replayed as a CUDA graph
+  must leave the same weights as the eager step with the reference's boolean-index loss, on changing frames / replay samples."""
+  from stereonet_b200.adapt import AdaptStepper, make_optimizer
+  H, W = 96, 256
+  frames = [O.make_stereo_pair(1, H, W, seed=1000 + i, max_disp_px=40.0) for i in range(3)]
+  replays = [O.make_stereo_pair(1, H, W, seed=2000 + i, max_disp_px=40.0) for i in range(3)]
+  res = []
+  for use_graph in (False, True):
+    f, s = _nets()
+    st = AdaptStepper(f, s, make_optimizer(f, s, lr=5e-5, capturable=True), H, W, use_graph=use_graph, fused_loss=True)
+    losses = []
+    for (l, r, _), (rl, rr, rgt) in zip(frames, replays):
+      loss, _, _ = st.step(l.to(DEV), r.to(DEV), replay=(rl.to(DEV), rr.to(DEV), rgt.to(DEV)))
+      losses.append(loss.item())
+    torch.cuda.synchronize()
+    res.append((losses, {n: v.detach().cpu().clone() for n, v in list(s.state_dict().items()) + list(f.state_dict().items())}))
+  (le, we), (lg, wg) = res
+  assert max(abs(a - b) for a, b in zip(le, lg)) < 2e-5, (le, lg)
+  for n in we:
+    if "num_batches_tracked" in n:
+      assert torch.equal(we[n], wg[n]), n
+    else:
+      assert (we[n] - wg[n]).abs().max().item() <= 3 * 2.1 * 5e-5 + 1e-5 * we[n].abs().max().item(), n
