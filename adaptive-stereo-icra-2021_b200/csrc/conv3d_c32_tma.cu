@@ -233,6 +233,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     // warp-uniform copies (a shuffle from lane 0 tells nvcc the value is uniform: addresses then stay in uniform registers)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), smem_u = __shfl_sync(0xffffffffu, base_u32, 0);
     uint32_t ac = 0, bc = 0, accpar = 0;         // accpar bit a = (number of earlier uses of accumulator a) & 1
+    uint32_t a_ready = 0, b_ready = 0;           // the next A slot / weight stage was already seen full by a look-ahead poll
     long long w_a = 0, w_bf = 0, w_t = 0; const long long t0 = clock64();
     int it = 0;
     if (PAIR && rank != 0) {
@@ -266,20 +267,30 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         const int dd = d + widx / 3 - 1;
         if ((unsigned)dd >= (unsigned)p.D) continue;
         const uint32_t sbi = bc % NB;
-        T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
+        if (!b_ready) T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
+        b_ready = 0;
         if (PAIR) T3WAIT(w_bf, mbar_wait_warp_cluster(&bpeer[sbi], (bc / NB) & 1));
         const uint32_t sb = smem_u + NR * A_BYTES + sbi * 2 * B_BYTES;
         for (int h = 0; h < nh; ++h) {
           const uint32_t aslot = ac % NA;
           if (PAIR) T3WAIT(w_a, mbar_wait_warp_cluster(&afull[aslot], (ac / NA) & 1));
-          else      T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
+          else if (!a_ready) T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
+          a_ready = 0;
           tc_fence_after();
+          uint32_t peek_a = 0, peek_b = 0;       // look-ahead polls of the elected lane (see below)
           const uint32_t ta = tmem_u + TA_BASE + aslot * 64;
           const uint32_t tmem_d = tmem_u + accs[h] * ACC_STRIDE;
           if (elect_one()) {                     // one election per 12 MMAs + commit (see tc_common.cuh)
             const uint32_t lo_off = PAIR ? B_BYTES / 2 : B_BYTES;       // B_lo follows B_hi (half-height images in a pair)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+              if (!PAIR && ks == 3) {
+                // Look ahead while the pipe still has the MMAs above queued: the tensor pipe's queue is shallow, so the issuing
+                // thread runs at pipe speed inside a batch and the pipe idled during the ~100-cycle barrier polls between
+                // batches.  A poll that already sees the NEXT batch's A slot (weight stage) full lets the next batch skip its wait.
+                peek_a = mbar_try_wait(&afull[(ac + 1) % NA], ((ac + 1) / NA) & 1) ? 1u : 0u;
+                if (h == nh - 1) peek_b = mbar_try_wait(&bfull[(bc + 1) % NB], ((bc + 1) / NB) & 1) ? 1u : 0u;
+              }
               const uint64_t bh = make_desc(sb + ks * 32);
               if (PAIR) {
                 mma2_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
@@ -297,7 +308,8 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
             }
             if (PAIR) mma2_commit_raw(&aempty[aslot]); else mma_commit_raw(&aempty[aslot]);
           }
-          __syncwarp();
+          a_ready = __any_sync(0xffffffffu, peek_a != 0);
+          if (h == nh - 1) b_ready = __any_sync(0xffffffffu, peek_b != 0);
           ++ac;
         }
         first = false;
