@@ -1,38 +1,49 @@
-// 2-D 32->32 stride-1 dilated 3x3 convolution on the tcgen05 tensor cores, "vertical walk" schedule.
-// Same GEMM formulation as conv_c32_tc.cu (M = 128 pixels of one image row, N = 96 = 3 kw x 32 cout folded, K = kh x 32
-// cin, TF32 operands with the 3xTF32 hi/lo split, fp32 accumulators in TMEM) but the tiles of one CTA walk DOWN a column
-// block in steps of `dil` rows, so consecutive tiles share two of their three input-row windows:
+// 2-D 32->32 stride-1 dilated 3x3 convolution on the tcgen05 tensor cores, "vertical walk" schedule with a TMA producer.
+// GEMM formulation: M = 128 pixels of one image row, N = 96 = 3 kw x 32 cout folded, K = kh x 32 cin, error-compensated
+// operand split (F16 = true: fp16 operands, kind::f16 K = 16, see conv3d_c32_tma.cu; F16 = false: 3xTF32), fp32 accumulators in
+// TMEM, A operand in TMEM.  The tiles of one CTA walk DOWN a column block in steps of `dil` rows, so consecutive tiles share
+// two of their three input-row windows:
 //
 //   window u  = A tile of input row r_u = rho + (j0 + u - 1)*dil, columns [x0, x0+128)          (loaded ONCE)
 //   tile j    = output row rho + (j0 + j)*dil, needs windows j (kh=0), j+1 (kh=1), j+2 (kh=2)
 //
 // The MMA warp is window-major: when window u lands it issues  acc[tile u] += A_u*B[0], acc[tile u-1] += A_u*B[1],
-// acc[tile u-2] += A_u*B[2]  and releases the A buffer at once; tile u-2 is then complete and goes to the epilogue.  Per
-// tile the loaders therefore move 1 window (16 KB) instead of 3, and smem store traffic / L2 traffic drop 3x — the
-// flat-tiled kernel was shared-memory-bandwidth bound (MMA operand fetch + loader stores + epilogue staging).
-// The three B images (one per kh, 24 KB each incl. hi/lo) stay resident in smem for the whole kernel.
+// acc[tile u-2] += A_u*B[2]  and releases the A slot at once; tile u-2 is then complete and goes to the epilogue.
+// A window = 128 consecutive pixels of one image row = 16 KB of contiguous channels-last memory: ONE 4-D TMA tile load (box
+// 32 ch x 128 px, SWIZZLE_128B, zero fill left/right of the row and above/below the image) issued by one producer thread —
+// round 1's three LDG->STS loader warps needed ~2070 cycles per window (latency-bound, two windows of register prefetch).
+// Warps: 0 producer, 1 MMA issuer (also fetches the three resident weight images), 2-9 converters (two per TMEM lane
+// quadrant, alternating windows: raw fp32 row -> hi/lo split -> tcgen05.st), 10-17 epilogue (two per quadrant).
+// smem: 6 x 16 KB raw window ring | 3 x 24 KB weight images (resident) | 48 KB epilogue tiles.
+// TMEM: 4 accumulators x 96 | A slots (F16: 4 x 32 columns, TF32: 2 x 64).
+#include <cuda.h>
 #include "tc_common.cuh"
 
 namespace tc2d {
 
 using namespace tc;
 
-constexpr int NA = 3;                                    // A-window ring depth (hi + lo = 32 KB each)
-constexpr int AWIN_BYTES = 2 * A_BYTES;
+constexpr int NR = 6;                                    // raw window ring depth
 constexpr int BWIN_BYTES = 2 * B_BYTES;
 constexpr int SY_BYTES = 3 * 128 * 128;
-constexpr int SMEM_BYTES2 = NA * AWIN_BYTES + 3 * BWIN_BYTES + SY_BYTES + 3072 + 1024;
+constexpr int SMEM_BYTES2 = NR * A_BYTES + 3 * BWIN_BYTES + SY_BYTES + 3072 + 1024;
+constexpr int NTHREADS2 = 18 * 32;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;
+template <bool F16> struct ASlots { static constexpr int N = F16 ? 4 : 2, COLS = F16 ? 32 : 64; };
+constexpr int ACC_STRIDE = 96, TA_BASE = NACC * 96;
 
 struct Params2 {
-  const float* x; const float* wimg; float* y;
+  const float* wimg; float* y;
   int B, H, W, dil;
   int step, ncb;            // output columns per tile (128 - 2*dil), column blocks per row
   int cmax, L, nseg;        // longest row chain ceil(H/dil), tiles per strip, segments per chain
   int nstrips;              // B * ncb * dil * nseg strip slots (some are empty)
   int passes;
   snb_conv_epilogue e;
-  long long* dbg;           // optional [grid][16] cycle counters (diagnostics, PROF kernels only), or NULL
+  long long* dbg;           // optional [grid][16] cycle counters (diagnostics), or NULL
 };
+
+#define T2WAIT(acc, call) do { const long long _t0 = p.dbg ? clock64() : 0; call; if (p.dbg) acc += clock64() - _t0; } while (0)
 
 struct Strip { int b, cb, row0, ntiles; };   // first output row, tiles (rows row0, row0+dil, ...)
 
@@ -48,39 +59,40 @@ __device__ __forceinline__ Strip decode_strip(const Params2& p, int sid) {
   return s;
 }
 
-// TA = true: the A window is copied ONCE from its smem image into TMEM (tcgen05.cp, 8 x 128x256b) and the 36 MMAs of the
-// window read A from TMEM — the per-MMA shared-memory operand fetch drops from 7 KB (A 4 KB + B 3 KB) to 3 KB; with A in
-// smem the kernel is bound by exactly that fetch (~110 cycles per M128 N96 K8 MMA instead of ~48).
-// TMEM columns: TA: 4 accumulators x 96 | 2 A slots x 64 (hi 32 | lo 32);  !TA: 4 accumulators x 128.
-template <bool TA, bool PROF>
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv2d_c32_tc_kernel(const Params2 p) {
-  pdl_launch();
-  constexpr int ACC_STRIDE = TA ? 96 : 128;
-  constexpr int TA_BASE = NACC * 96;
-  constexpr int TA_LOADERS = 3;              // TA: warps 0-2 load, warps 3-6 convert (one per TMEM lane quadrant)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar2() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+template <bool F16>
+__global__ void __launch_bounds__(NTHREADS2, 1)
+conv2d_c32_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params2 p) {
+  constexpr int NA = ASlots<F16>::N, ACOLS = ASlots<F16>::COLS;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
-  unsigned char* sB = base + NA * AWIN_BYTES;
+  unsigned char* sB = base + NR * A_BYTES;
   unsigned char* sYB = sB + 3 * BWIN_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sYB + SY_BYTES);
-  uint64_t* full = bars;                 // [NA]   loaders -> MMA
-  uint64_t* empty = bars + NA;           // [NA]   MMA commit -> loaders
-  uint64_t* tfull = bars + 2 * NA;       // [NACC] MMA commit -> epilogue
+  uint64_t* rfull = bars;                // [NR]   TMA (raw window) -> converters
+  uint64_t* rempty = rfull + NR;         // [NR]   converters -> producer
+  uint64_t* afull = rempty + NR;         // [NA]   converters -> MMA (A slot in TMEM)
+  uint64_t* aempty = afull + NA;         // [NA]   MMA commit -> converters
+  uint64_t* tfull = aempty + NA;         // [NACC] MMA commit -> epilogue
   uint64_t* tempty = tfull + NACC;       // [NACC] epilogue -> MMA
   uint64_t* wbar = tempty + NACC;
-  uint64_t* rfull = wbar + 1;            // [NA]   TA: loaders -> converters (raw fp32 window in smem)
-  uint64_t* rempty = rfull + NA;         // [NA]   TA: converters -> loaders
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + NA);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == NUM_LOADER_WARPS) {
+  if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < NA; ++i) { mbar_init(&full[i], TA ? 4 : NUM_LOADER_WARPS); mbar_init(&empty[i], 1); }
-      for (int i = 0; i < NA; ++i) { mbar_init(&rfull[i], TA_LOADERS); mbar_init(&rempty[i], 4); }
+      for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); }
+      for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
       for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
       mbar_init(wbar, 1);
       mbar_fence_init();
@@ -93,270 +105,166 @@ conv2d_c32_tc_kernel(const Params2 p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();                                    // only after this CTA owns its TMEM columns (see conv3d_c32_tma.cu)
   pdl_wait();                                      // everything above touched no global memory
 
-  if (TA && warp < TA_LOADERS) {
-    // =============================================================== TA loaders (warps 0-2): coalesced LDG.128 -> raw fp32 window in
-    // the smem ring (row = pixel, 16-B chunks XOR-swizzled by row & 7).  No hi/lo split here.
-    constexpr int PF = 2;
-    constexpr int LT_ROWS = TA_LOADERS * 4;                // rows covered by one pass of the loader threads (12)
-    constexpr int LT_N = (128 + LT_ROWS - 1) / LT_ROWS;    // rows per thread (11)
-    const int chunk = tid & 7, rgrp = tid >> 3;
-    int l_sid = blockIdx.x, l_u = 0;
-    Strip ls = decode_strip(p, l_sid < p.nstrips ? l_sid : 0);
-    auto l_skip_empty = [&]() {
-      while (l_sid < p.nstrips && ls.ntiles == 0) { l_sid += gridDim.x; if (l_sid < p.nstrips) ls = decode_strip(p, l_sid); }
-    };
-    l_skip_empty();
-    auto issue_loads = [&](float4 (&v)[LT_N]) {
-      const int r = ls.row0 + (l_u - 1) * p.dil;
-      const int x0 = ls.cb * p.step - p.dil;
-      const bool row_ok = (unsigned)r < (unsigned)p.H;
-      const float* rowp = p.x + ((size_t)ls.b * p.H + (row_ok ? r : 0)) * p.W * 32 + chunk * 4;
-#pragma unroll
-      for (int j = 0; j < LT_N; ++j) {
-        const int xx = x0 + rgrp + LT_ROWS * j;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok && rgrp + LT_ROWS * j < 128 && (unsigned)xx < (unsigned)p.W) v[j] = __ldcg(reinterpret_cast<const float4*>(rowp + (size_t)xx * 32));
+  if (warp == 0) {
+    // =============================================================== producer: one TMA tile load per window
+    if (lane == 0) {
+      uint32_t ac = 0;
+      long long w_r = 0; const long long t0 = clock64();
+      for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+        const Strip s = decode_strip(p, sid);
+        if (s.ntiles == 0) continue;
+        const int x0 = s.cb * p.step - p.dil;
+        for (int u = 0; u < s.ntiles + 2; ++u) {
+          const uint32_t sa = ac % NR;
+          T2WAIT(w_r, tc::mbar_wait(&rempty[sa], ((ac / NR) & 1) ^ 1));
+          mbar_expect_tx(&rfull[sa], A_BYTES);
+          tma_load_4d(base + sa * A_BYTES, &tmap, &rfull[sa], 0, x0, s.row0 + (u - 1) * p.dil, s.b);
+          ++ac;
+        }
       }
-      if (++l_u == ls.ntiles + 2) {
-        l_u = 0; l_sid += gridDim.x;
-        if (l_sid < p.nstrips) { ls = decode_strip(p, l_sid); l_skip_empty(); }
-      }
-    };
-    float4 v[PF][LT_N];
-#pragma unroll
-    for (int k = 0; k < PF; ++k)
-      if (l_sid < p.nstrips) issue_loads(v[k]);
-    long long n_items = 0;
+      if (p.dbg) { long long* dd = p.dbg + blockIdx.x * 16; dd[0] = w_r; dd[1] = clock64() - t0; }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (converged warp, elected lane), window-major
+    if (lane == 0) {
+      mbar_expect_tx(wbar, 3 * BWIN_BYTES);
+      for (int w = 0; w < 3; ++w)
+        bulk_g2s(sB + w * BWIN_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, BWIN_BYTES, wbar);
+    }
+    __syncwarp();
+    tc::mbar_wait_spin(wbar, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform copies for the uniform datapath
+    const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NR * A_BYTES;
+    long long tile_base = 0;                 // tiles issued so far by this CTA (TMEM accumulator = counter % NACC)
+    uint32_t win_count = 0;                  // windows consumed so far (TMEM A slot = counter % NA)
+    long long t_full = 0, t_tempty = 0; const long long t_mbegin = clock64();
     for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
       const Strip s = decode_strip(p, sid);
-      if (s.ntiles > 0) n_items += s.ntiles + 2;
-    }
-    uint32_t buf = 0, phase = 0;
-    long long t_lwait = 0; const long long t_lbegin = prof_clock<PROF>();
-    for (long long item0 = 0; item0 < n_items; item0 += PF) {
+      if (s.ntiles == 0) continue;
+      for (int u = 0; u < s.ntiles + 2; ++u) {
+        const uint32_t aslot = win_count % NA;
+        T2WAIT(t_full, mbar_wait_warp(&afull[aslot], (win_count / NA) & 1));
+        tc_fence_after();
+        const uint32_t ta = tmem_u + TA_BASE + aslot * ACOLS;
+        // accumulator bookkeeping first (waits are warp-uniform), then ONE election for the window's MMAs + commits
+        uint32_t tmem_d[3], sbw[3]; bool act[3]; int slot_done = -1;
 #pragma unroll
-      for (int k = 0; k < PF; ++k) {
-        if (item0 + k >= n_items) break;
-        unsigned char* st = base + buf * A_BYTES;
-        t_lwait += mbar_wait_timed<PROF>(&rempty[buf], phase ^ 1);
+        for (int kk = 0; kk < 3; ++kk) {
+          const int kh = 2 - kk;             // finish the oldest tile first so the epilogue can start on it
+          const int j = u - kh;
+          act[kk] = j >= 0 && j < s.ntiles;
+          const long long tcount = tile_base + (act[kk] ? j : 0);
+          const int slot = (int)(tcount & (NACC - 1));
+          if (act[kk] && kh == 0) {          // first touch of this tile's accumulator: the epilogue must have drained it
+            T2WAIT(t_tempty, mbar_wait_warp(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1)));
+            tc_fence_after();
+          }
+          if (act[kk] && kh == 2) slot_done = slot;
+          tmem_d[kk] = tmem_u + slot * ACC_STRIDE;
+          sbw[kk] = sb_u32 + kh * BWIN_BYTES;
+        }
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < LT_N; ++j) {
-          const int r = rgrp + LT_ROWS * j;
-          if (r < 128) *reinterpret_cast<float4*>(st + r * 128 + ((chunk ^ (r & 7)) << 4)) = v[k][j];
+          for (int kk = 0; kk < 3; ++kk) {
+            if (!act[kk]) continue;
+            const int kh = 2 - kk;
+            if (F16) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                mma_f16_ts_raw(tmem_d[kk], ta + ks * 8, make_desc(sbw[kk] + ks * 32), (kh | ks) != 0);
+                mma_f16_ts_raw(tmem_d[kk], ta + 16 + ks * 8, make_desc(sbw[kk] + B_BYTES + ks * 32), 1);
+                mma_f16_ts_raw(tmem_d[kk], ta + ks * 8, make_desc(sbw[kk] + 64 + ks * 32), 1);
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bh = make_desc(sbw[kk] + ks * 32);
+                mma_tf32_ts_raw(tmem_d[kk], ta + ks * 8, bh, (kh | ks) != 0);
+                if (p.passes == 3) {
+                  mma_tf32_ts_raw(tmem_d[kk], ta + 32 + ks * 8, bh, 1);
+                  mma_tf32_ts_raw(tmem_d[kk], ta + ks * 8, make_desc(sbw[kk] + B_BYTES + ks * 32), 1);
+                }
+              }
+            }
+            if (kh == 2) mma_commit_raw(&tfull[slot_done]);      // tile u-2 has received all three kh contributions
+          }
+          mma_commit_raw(&aempty[aslot]);                        // window u consumed: its TMEM slot is free
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&rfull[buf]);
-        if (++buf == NA) { buf = 0; phase ^= 1; }
-        if (l_sid < p.nstrips) issue_loads(v[k]);
+        ++win_count;
       }
+      tile_base += s.ntiles;
     }
-    if (PROF && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_lwait; p.dbg[blockIdx.x * 16 + 1] = prof_clock<PROF>() - t_lbegin; }
-  } else if (TA && warp < NUM_LOADER_WARPS) {
-    // =============================================================== TA converters (warps 3-6, TMEM lane quadrant = warp % 4):
-    // thread = pixel row: 8 conflict-free LDS.128 -> hi/lo split in registers -> tcgen05.st into the A slot in TMEM.  The
-    // MMAs then read A from TMEM: no per-MMA shared-memory fetch of the A operand.
+    if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[2] = t_full; dd[3] = t_tempty; dd[4] = clock64() - t_mbegin; }
+    __syncwarp();
+  } else if (warp < EPI_WARP0) {
+    // =============================================================== converters (TMEM lane quadrant = warp % 4, thread = pixel):
+    // 8 conflict-free LDS.128 -> hi/lo split in registers -> tcgen05.st into the A slot in TMEM.
     const int quad = warp & 3;
+    const uint32_t mine = (uint32_t)(warp - CONV_WARP0) >> 2;      // this warp converts the windows with cnt % 2 == mine
     const int m = quad * 32 + lane;                        // window row = TMEM lane
     long long n_items = 0;
     for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
       const Strip s = decode_strip(p, sid);
       if (s.ntiles > 0) n_items += s.ntiles + 2;
     }
-    uint32_t buf = 0, phase = 0;
-    for (long long it = 0; it < n_items; ++it) {
-      const uint32_t slot = (uint32_t)it & 1;
-      tc::mbar_wait(&rfull[buf], phase);
-      const unsigned char* st = base + buf * A_BYTES + m * 128;
+    long long w_rf = 0, w_ae = 0; const long long t0 = clock64();
+    for (uint32_t cnt = mine; cnt < (uint32_t)n_items; cnt += 2) {
+      const uint32_t sr = cnt % NR, aslot = cnt % NA;
+      T2WAIT(w_rf, tc::mbar_wait(&rfull[sr], (cnt / NR) & 1));
+      const unsigned char* st = base + sr * A_BYTES + m * 128;
       float4 v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(st + ((c ^ (m & 7)) << 4));
       __syncwarp();
-      if (lane == 0) mbar_arrive(&rempty[buf]);            // raw window consumed (values are in registers)
-      if (++buf == NA) { buf = 0; phase ^= 1; }
-      tc::mbar_wait(&empty[slot], (((uint32_t)it >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_arrive(&rempty[sr]);             // raw window consumed (values are in registers)
+      T2WAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
       tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + slot * 64;
-      {
-        uint32_t h[32];
+      const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * ACOLS;
+      if (F16) {
+        uint32_t hl[32];
+        split_f16(v, hl);
+        tmem_st32(ta, hl);
+      } else {
+        {
+          uint32_t h[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
-          h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
+          for (int c = 0; c < 8; ++c) {
+            h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
+            h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
+          }
+          tmem_st32(ta, h);
         }
-        tmem_st32(ta, h);
-      }
-      if (p.passes == 3) {
-        uint32_t l[32];
+        if (p.passes == 3) {
+          uint32_t l[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x4 = v[c];
-          l[4 * c] = __float_as_uint(x4.x - __uint_as_float(tc::tf32_hi_bits(x4.x)));
-          l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(tc::tf32_hi_bits(x4.y)));
-          l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(tc::tf32_hi_bits(x4.z)));
-          l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(tc::tf32_hi_bits(x4.w)));
+          for (int c = 0; c < 8; ++c) {
+            const float4 x4 = v[c];
+            l[4 * c] = __float_as_uint(x4.x - __uint_as_float(tc::tf32_hi_bits(x4.x)));
+            l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(tc::tf32_hi_bits(x4.y)));
+            l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(tc::tf32_hi_bits(x4.z)));
+            l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(tc::tf32_hi_bits(x4.w)));
+          }
+          tmem_st32(ta + 32, l);
         }
-        tmem_st32(ta + 32, l);
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[slot]);
+      if (lane == 0) mbar_arrive(&afull[aslot]);
     }
-  } else if (warp < NUM_LOADER_WARPS) {
-    // =============================================================== loaders (window items, register prefetch PF deep)
-    constexpr int PF = 3;
-    const int chunk = tid & 7, rgrp = tid >> 3;            // 8 lanes = one 128-B pixel; rows rgrp + LSTRIDE*j (< 128)
-    // load cursor
-    int l_sid = blockIdx.x, l_u = 0;
-    Strip ls = decode_strip(p, l_sid < p.nstrips ? l_sid : 0);
-    auto l_skip_empty = [&]() {
-      while (l_sid < p.nstrips && ls.ntiles == 0) { l_sid += gridDim.x; if (l_sid < p.nstrips) ls = decode_strip(p, l_sid); }
-    };
-    l_skip_empty();
-    auto issue_loads = [&](float4 (&v)[LROWS]) {
-      const int r = ls.row0 + (l_u - 1) * p.dil;
-      const int x0 = ls.cb * p.step - p.dil;
-      const bool row_ok = (unsigned)r < (unsigned)p.H;
-      const float* rowp = p.x + ((size_t)ls.b * p.H + (row_ok ? r : 0)) * p.W * 32 + chunk * 4;
-#pragma unroll
-      for (int j = 0; j < LROWS; ++j) {
-        const int xx = x0 + rgrp + LSTRIDE * j;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok && rgrp + LSTRIDE * j < 128 && (unsigned)xx < (unsigned)p.W) v[j] = __ldcg(reinterpret_cast<const float4*>(rowp + (size_t)xx * 32));
-      }
-      if (++l_u == ls.ntiles + 2) {
-        l_u = 0; l_sid += gridDim.x;
-        if (l_sid < p.nstrips) { ls = decode_strip(p, l_sid); l_skip_empty(); }
-      }
-    };
-    float4 v[PF][LROWS];
-#pragma unroll
-    for (int k = 0; k < PF; ++k)
-      if (l_sid < p.nstrips) issue_loads(v[k]);
-
-    // store cursor: only needs to know how many windows this CTA produces
-    long long n_items = 0;
-    for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
-      const Strip s = decode_strip(p, sid);
-      if (s.ntiles > 0) n_items += s.ntiles + 2;
-    }
-    uint32_t buf = 0, phase = 0;
-    long long t_lwait = 0; const long long t_lbegin = prof_clock<PROF>();
-    for (long long item0 = 0; item0 < n_items; item0 += PF) {
-#pragma unroll
-      for (int k = 0; k < PF; ++k) {
-        if (item0 + k >= n_items) break;
-        unsigned char* st = base + buf * AWIN_BYTES;
-        t_lwait += mbar_wait_timed<PROF>(&empty[buf], phase ^ 1);
-#pragma unroll
-        for (int j = 0; j < LROWS; ++j) {
-          const int r = rgrp + LSTRIDE * j;
-          if (r < 128) {
-            const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
-            float4 hi, lo;
-            split_tf32(v[k][j], hi, lo);
-            *reinterpret_cast<float4*>(st + off) = hi;
-            if (p.passes == 3) *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
-          }
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[buf]);
-        if (++buf == NA) { buf = 0; phase ^= 1; }
-        if (l_sid < p.nstrips) issue_loads(v[k]);
-      }
-    }
-    if (PROF && p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = t_lwait; p.dbg[blockIdx.x * 16 + 1] = prof_clock<PROF>() - t_lbegin; }
-  } else if (warp == NUM_LOADER_WARPS) {
-    // =============================================================== MMA issuer (converged warp, elected lane), window-major
-    {
-      if (lane == 0) {
-        mbar_expect_tx(wbar, 3 * BWIN_BYTES);
-        for (int w = 0; w < 3; ++w)
-          bulk_g2s(sB + w * BWIN_BYTES, p.wimg + (size_t)w * WIMG_FLOATS_PER_WINDOW, BWIN_BYTES, wbar);
-      }
-      __syncwarp();
-      tc::mbar_wait_spin(wbar, 0);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform copies for the uniform datapath
-      const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NA * AWIN_BYTES;
-      uint32_t buf = 0, phase = 0;
-      long long tile_base = 0;                 // tiles issued so far by this CTA (TMEM slot = counter % NACC)
-      uint32_t win_count = 0;                  // windows consumed so far (TMEM A slot = counter & 1)
-      long long t_full = 0, t_tempty = 0; const long long t_mbegin = prof_clock<PROF>();
-      for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
-        const Strip s = decode_strip(p, sid);
-        if (s.ntiles == 0) continue;
-        for (int u = 0; u < s.ntiles + 2; ++u) {
-          const uint32_t aslot = win_count & 1;
-          uint64_t* fbar = TA ? &full[aslot] : &full[buf];
-          const uint32_t fphase = TA ? ((win_count >> 1) & 1) : phase;
-          if (PROF) t_full += mbar_wait_timed<PROF>(fbar, fphase); else mbar_wait_warp(fbar, fphase);
-          tc_fence_after();
-          const uint32_t sa = base_u32 + buf * AWIN_BYTES;
-          const uint32_t ta = tmem_u + TA_BASE + aslot * 64;
-          // accumulator bookkeeping first (waits are warp-uniform), then ONE election for the window's 36 MMAs + commits
-          uint32_t tmem_d[3], sbw[3]; bool act[3]; int slot_done = -1;
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            const int kh = 2 - kk;             // finish the oldest tile first so the epilogue can start on it
-            const int j = u - kh;
-            act[kk] = j >= 0 && j < s.ntiles;
-            const long long tcount = tile_base + (act[kk] ? j : 0);
-            const int slot = (int)(tcount & (NACC - 1));
-            if (act[kk] && kh == 0) {          // first touch of this tile's accumulator: the epilogue must have drained it
-              if (PROF) t_tempty += mbar_wait_timed<PROF>(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
-              else mbar_wait_warp(&tempty[slot], (uint32_t)(((tcount / NACC) & 1) ^ 1));
-              tc_fence_after();
-            }
-            if (act[kk] && kh == 2) slot_done = slot;
-            tmem_d[kk] = tmem_u + slot * ACC_STRIDE;
-            sbw[kk] = sb_u32 + kh * BWIN_BYTES;
-          }
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-              if (!act[kk]) continue;
-              const int kh = 2 - kk;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t bh = make_desc(sbw[kk] + ks * 32);
-                if (TA) {
-                  mma_tf32_ts_raw(tmem_d[kk], ta + ks * 8, bh, (kh | ks) != 0);
-                  if (p.passes == 3) {
-                    mma_tf32_ts_raw(tmem_d[kk], ta + 32 + ks * 8, bh, 1);
-                    mma_tf32_ts_raw(tmem_d[kk], ta + ks * 8, make_desc(sbw[kk] + B_BYTES + ks * 32), 1);
-                  }
-                } else {
-                  const uint64_t ah = make_desc(sa + ks * 32);
-                  mma_tf32_raw(tmem_d[kk], ah, bh, (kh | ks) != 0);
-                  if (p.passes == 3) {
-                    mma_tf32_raw(tmem_d[kk], make_desc(sa + A_BYTES + ks * 32), bh, 1);
-                    mma_tf32_raw(tmem_d[kk], ah, make_desc(sbw[kk] + B_BYTES + ks * 32), 1);
-                  }
-                }
-              }
-              if (kh == 2) mma_commit_raw(&tfull[slot_done]);      // tile u-2 has received all three kh contributions
-            }
-            mma_commit_raw(TA ? &empty[aslot] : &empty[buf]);      // window u consumed (TA: its TMEM slot, else its smem buffer)
-          }
-          __syncwarp();
-          ++win_count;
-          if (++buf == NA) { buf = 0; phase ^= 1; }
-        }
-        tile_base += s.ntiles;
-      }
-      if (PROF && p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 2] = t_full; p.dbg[blockIdx.x * 16 + 3] = t_tempty; p.dbg[blockIdx.x * 16 + 4] = prof_clock<PROF>() - t_mbegin; }
-    }
-    __syncwarp();
+    if (p.dbg && warp == CONV_WARP0 && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[11] = w_rf; dd[12] = w_ae; dd[13] = clock64() - t0; }
   } else {
     // =============================================================== epilogue (8 warps; TMEM lane quadrant = warp % 4)
-    const int ew = warp - (NUM_LOADER_WARPS + 1);
+    const int ew = warp - EPI_WARP0;
     const int quad = warp & 3;
     const int half = ew >> 2;
     const int m = quad * 32 + lane;
-    const int et = tid - (NUM_LOADER_WARPS + 1) * 32;
+    const int et = tid - EPI_WARP0 * 32;
     const int chunk = et & 7, rg = et >> 3;          // rows rg + 32*j, 16-B chunk `chunk`
     float* sY = reinterpret_cast<float*>(sYB);
     const snb_conv_epilogue& e = p.e;
@@ -365,13 +273,14 @@ conv2d_c32_tc_kernel(const Params2 p) {
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
     const float slope = e.lrelu ? SNB_LRELU_SLOPE : 1.f;
+    const float winv = F16 ? __ldg(p.wimg + WIMG_SCALE_SLOT) : 1.f;    // 2^-s of the weight image (power of two: exact)
     long long tcount = 0;
-    long long t_tfull = 0, t_pre = 0, t_tmem = 0, t_out = 0, t_bar = 0; const long long t_ebegin = prof_clock<PROF>();
+    long long t_tfull = 0, t_pre = 0, t_tmem = 0, t_out = 0, t_bar = 0; const long long t_ebegin = clock64();
     for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
       const Strip s = decode_strip(p, sid);
       const int x0 = s.cb * p.step - p.dil;
       for (int j = 0; j < s.ntiles; ++j, ++tcount) {
-        const long long tA = prof_clock<PROF>();
+        const long long tA = p.dbg ? clock64() : 0;
         const int slot = (int)(tcount & (NACC - 1));
         const uint32_t accphase = (uint32_t)((tcount / NACC) & 1);
         const int h = s.row0 + j * p.dil;
@@ -389,10 +298,10 @@ conv2d_c32_tc_kernel(const Params2 p) {
           res[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has_res && okr[jj]) res[jj] = __ldcg(reinterpret_cast<const float4*>(e.residual + (rowbase + xs[jj]) * 32 + chunk * 4));
         }
-        t_pre += prof_clock<PROF>() - tA;
-        t_tfull += mbar_wait_timed<PROF>(&tfull[slot], accphase);
+        if (p.dbg) t_pre += clock64() - tA;
+        T2WAIT(t_tfull, tc::mbar_wait(&tfull[slot], accphase));
         tc_fence_after();
-        const long long tB = prof_clock<PROF>();
+        const long long tB = p.dbg ? clock64() : 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * ACC_STRIDE + half * 16;
         {
           float v0[16], v1[16], v2[16];
@@ -409,9 +318,9 @@ conv2d_c32_tc_kernel(const Params2 p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[slot]);
-        t_tmem += prof_clock<PROF>() - tB;
-        { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }
-        const long long tC = prof_clock<PROF>();
+        if (p.dbg) t_tmem += clock64() - tB;
+        T2WAIT(t_bar, epi_bar2());
+        const long long tC = p.dbg ? clock64() : 0;
         // Straight-line pointwise chain: absent stages are identities (scale 1 / shift 0, LeakyReLU slope 1, residual 0, stats
         // weight 0), so a tile costs no data-dependent branches — only the final store is predicated.
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -423,8 +332,13 @@ conv2d_c32_tc_kernel(const Params2 p) {
           const float4 a = *reinterpret_cast<const float4*>(sY + r0 * 32 + ((chunk ^ (r0 & 7)) << 2));
           const float4 b = *reinterpret_cast<const float4*>(sY + 128 * 32 + r * 32 + ((chunk ^ (r & 7)) << 2));
           const float4 c = *reinterpret_cast<const float4*>(sY + 2 * 128 * 32 + r2 * 32 + ((chunk ^ (r2 & 7)) << 2));
-          o[jj].x = (a.x + b.x) + c.x + bias4.x; o[jj].y = (a.y + b.y) + c.y + bias4.y;
-          o[jj].z = (a.z + b.z) + c.z + bias4.z; o[jj].w = (a.w + b.w) + c.w + bias4.w;
+          if (F16) {
+            o[jj].x = fmaf((a.x + b.x) + c.x, winv, bias4.x); o[jj].y = fmaf((a.y + b.y) + c.y, winv, bias4.y);
+            o[jj].z = fmaf((a.z + b.z) + c.z, winv, bias4.z); o[jj].w = fmaf((a.w + b.w) + c.w, winv, bias4.w);
+          } else {
+            o[jj].x = (a.x + b.x) + c.x + bias4.x; o[jj].y = (a.y + b.y) + c.y + bias4.y;
+            o[jj].z = (a.z + b.z) + c.z + bias4.z; o[jj].w = (a.w + b.w) + c.w + bias4.w;
+          }
         }
         if (has_stats) {                       // one warp-uniform branch per tile (train-mode BN only)
 #pragma unroll
@@ -454,7 +368,7 @@ conv2d_c32_tc_kernel(const Params2 p) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) { sRed[ew * 64 + lane * 4 + c] = s1[c]; sRed[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
           }
-          epi_bar();
+          epi_bar2();
           if (et < 64) {
             float a = 0.f;
 #pragma unroll
@@ -462,16 +376,16 @@ conv2d_c32_tc_kernel(const Params2 p) {
             e.stats[(((size_t)s.b * p.H + h) * p.ncb + s.cb) * 64 + et] = a;
           }
         }
-        t_out += prof_clock<PROF>() - tC;
-        { const long long tb = prof_clock<PROF>(); epi_bar(); t_bar += prof_clock<PROF>() - tb; }
+        if (p.dbg) t_out += clock64() - tC;
+        T2WAIT(t_bar, epi_bar2());
       }
     }
-    if (PROF && p.dbg && et == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = prof_clock<PROF>() - t_ebegin; d[7] = t_bar; d[8] = t_pre; d[9] = t_tmem; d[10] = t_out; }
+    if (p.dbg && et == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = clock64() - t_ebegin; d[7] = t_bar; d[8] = t_pre; d[9] = t_tmem; d[10] = t_out; }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == NUM_LOADER_WARPS) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
   }
@@ -533,28 +447,40 @@ extern "C" int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, floa
   return conv2d_tc_launch(x, wimg, y, g, e, passes, counters, stream);
 }
 
-template <bool TA, bool PROF>
-static int conv2d_tc_go(const tc2d::Params2& p, int grid, void* stream) {
-  SNB_CUDA(cudaFuncSetAttribute(tc2d::conv2d_c32_tc_kernel<TA, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2d::SMEM_BYTES2));
-  snb_launch(tc2d::conv2d_c32_tc_kernel<TA, PROF>, grid, tc::NTHREADS, tc2d::SMEM_BYTES2, stream, p);
-  SNB_LAUNCH_CHECK("conv2d_c32_tc_kernel");
-  return 0;
-}
-
 static int conv2d_tc_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                             int passes, long long* dbg, void* stream) {
   tc2d::Params2 p;
   if (int rc = tc2d_setup(g, p, "snb_conv2d_c32_tc")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv2d_c32_tc: null pointer");
-  const bool legacy = (passes & 0x100) != 0;      // diagnostics: A operand from shared memory instead of TMEM
-  passes &= 0xff;
+  SNB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "snb_conv2d_c32_tc: x must be 16-byte aligned");
+  const bool f16 = (passes & SNB_CONV_F16) != 0;       // weight image in the fp16-split format (snb_prep_conv_weights_tc mode | 0x10)
+  passes &= 0xf;
   SNB_REQUIRE(passes == 1 || passes == 3, "snb_conv2d_c32_tc: passes must be 1 or 3");
+  SNB_REQUIRE(!f16 || passes == 3, "snb_conv2d_c32_tc: the fp16 split has 3 passes");
   SNB_REQUIRE(!e->scale || e->shift, "snb_conv2d_c32_tc: scale without shift");
-  p.x = x; p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e; p.dbg = dbg;
+  p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e; p.dbg = dbg;
+  snb_encode_tiled_fn enc = snb_get_encode_tiled();
+  SNB_REQUIRE(enc != nullptr, "snb_conv2d_c32_tc: cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {32, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->B};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)g->W * 128, (cuuint64_t)g->W * g->H * 128};      // bytes, dims 1..3
+  const cuuint32_t box[4] = {32, 128, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv2d_c32_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nstrips < sms ? p.nstrips : sms;
-  if (dbg) return legacy ? conv2d_tc_go<false, true>(p, grid, stream) : conv2d_tc_go<true, true>(p, grid, stream);
-  return legacy ? conv2d_tc_go<false, false>(p, grid, stream) : conv2d_tc_go<true, false>(p, grid, stream);
+  if (f16) {
+    SNB_CUDA(cudaFuncSetAttribute(tc2d::conv2d_c32_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2d::SMEM_BYTES2));
+    snb_launch(tc2d::conv2d_c32_tc_kernel<true>, grid, tc2d::NTHREADS2, tc2d::SMEM_BYTES2, stream, tmap, p);
+  } else {
+    SNB_CUDA(cudaFuncSetAttribute(tc2d::conv2d_c32_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2d::SMEM_BYTES2));
+    snb_launch(tc2d::conv2d_c32_tc_kernel<false>, grid, tc2d::NTHREADS2, tc2d::SMEM_BYTES2, stream, tmap, p);
+  }
+  SNB_LAUNCH_CHECK("conv2d_c32_tc_kernel");
+  return 0;
 }

@@ -15,17 +15,14 @@
 // A CTA works on SUPER-TILES of two consecutive tiles of one slice: every (kd,kh) weight image is fetched once per pair, which
 // halves the dominant L2->smem stream (24 KB of weights against 16 KB of activations per window) and doubles the MMA work
 // behind each in-flight weight stage (the single-tile version was bound by exactly that stream / its latency).
-// PAIR = true (experimental, SNB200_CONV3D=pair): the same kernel as a cluster of two CTAs driving tcgen05.mma.cta_group::2 (M = 256: each CTA's TMEM
-// holds the A rows / accumulator of ITS tile, each CTA's smem holds HALF of the weight tile's N = 96 rows).  One CTA per tile
-// fetches the full 3 KB B operand per MMA and the kernel is bound by the 128 B/clk shared-memory port (725 cycles of smem
-// traffic per window against 581 cycles of MMA math); in a pair the B fetch and the streamed weight
-// image are halved per SM.  The leader (cluster rank 0) issues all MMAs; converters / epilogue warps of the peer arrive
-// remotely on the leader's barriers, the peer's otherwise idle MMA warp forwards "my weight half has landed", and every
-// tcgen05.commit is multicast to both CTAs.  A pair works on two consecutive super-tiles of one slice (same kd windows);
-// missing tiles at the end of a slice are dummies (TMA zero fill, no stores).  Parity-green but 20 % SLOWER than one CTA per tile
-// (255 vs 203 us at batch 4): an A slot now turns around through commit -> multicast arrive -> convert -> tcgen05.st -> REMOTE
-// arrive, longer than the two 12-MMA batches the other slots cover, and the pair runs in lock step.  Kept for the next round
-// (needs A slots / accumulators decoupled per CTA), not the default.
+// F16 = true (the product path): the error-compensated split uses fp16 operands (tcgen05.mma.kind::f16, K = 16) instead of TF32
+// (K = 8): x = xh + 2^-11 xl', xh = fp16(x), xl' = fp16((x - xh) * 2^11); w' = w * 2^s (per-layer power of two, exact), wh = fp16(w'),
+// wl = fp16(w' - wh); out = 2^-s (xh.wh + xl'.(2^-11 wh) + xh.wl).  Same three products and the same ~2^-22 relative error as
+// 3xTF32 (both formats carry an 11-bit significand; the 2^11 pre-scaling of xl' keeps it out of the fp16 subnormals), but an
+// M128 N96 K16 fp16 MMA does twice the work of the K8 TF32 one in the same 48 cycles: 6 instead of 12 MMAs per window, half
+// the B-operand fetch, half the tcgen05.st traffic (A slot = 32 TMEM columns, 6 slots).  Range: |x| < 65504 (saturating
+// conversion; activations behind BatchNorm are O(1..100)).  (A cta_group::2 variant of the TF32 kernel was built in round 1,
+// measured 20 % slower and removed.)
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,8 +36,10 @@ constexpr int NR = 6;                                    // raw A ring depth (TM
 constexpr int NB = 3;                                    // B ring depth (one weight image serves both tiles of a pair)
 constexpr int NTHREADS3 = 18 * 32;
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;                // 8 converter warps: two per quadrant, alternating windows
-constexpr int NACC3 = 3, NA = 3;                           // TMEM: 3 accumulators x 96 columns | 3 A slots x 64 columns (the A-slot turnaround
-                                                           // commit -> convert -> tcgen05.st -> arrive is longer than one 12-MMA batch: 2 slots starve the MMA warp)
+constexpr int NACC3 = 3;                                 // TMEM accumulators x 96 columns
+// A slots in TMEM behind the accumulators.  TF32: 3 x 64 columns (hi 32 | lo 32).  F16: 6 x 32 columns (hi 16 | lo' 16): the
+// slot turnaround commit -> convert -> tcgen05.st -> arrive is longer than one MMA batch, and an fp16 batch is half as long.
+template <bool F16> struct ASlots { static constexpr int N = F16 ? 6 : 3, COLS = F16 ? 32 : 64; };
 constexpr int ACC_STRIDE = 96, TA_BASE = NACC3 * 96;
 constexpr int SMEM_BYTES3 = NR * A_BYTES + NB * 2 * B_BYTES + OUT_BYTES + 3072 /*barriers, stats scratch*/ + 1024 /*alignment slack*/;
 
@@ -63,70 +62,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
-  asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n"
-               :: "r"(smem_u32(bar)), "r"(cta) : "memory");
-}
-template <bool PAIR> __device__ __forceinline__ void arrive_on_leader(uint64_t* bar, uint32_t rank) {
-  if (PAIR && rank != 0) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// warp-uniform wait (see tc::mbar_wait_warp) with cluster-scope acquire: barriers that receive remote arrivals
-__device__ __forceinline__ void mbar_wait_warp_cluster(uint64_t* bar, uint32_t parity) {
-  if (__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) return;
-  const long long t0 = clock64();
-  while (!__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) {
-    __nanosleep(20);
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-constexpr uint32_t IDESC_M256 = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((256u >> 4) << 24);
-__device__ __forceinline__ void mma2_tf32_ts_raw(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC_M256), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma2_commit_raw(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
-               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
-// work decomposition shared by all roles.  PAIR: unit = two consecutive super-tiles of one slice, this CTA takes the one with
-// its cluster rank; always two tiles per super-tile (missing ones are dummies).  Single: unit = one super-tile.
+// work decomposition shared by all roles: unit = one super-tile (two consecutive tiles of one slice, the last may be single)
 struct Unit { int slice, sst, nh; };
-template <bool PAIR> __device__ __forceinline__ int unit_first(uint32_t rank) { return PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
-template <bool PAIR> __device__ __forceinline__ int unit_step() { return PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
-template <bool PAIR> __device__ __forceinline__ Unit unit_of(int u, int spt, int tiles_per_slice, uint32_t rank) {
+__device__ __forceinline__ Unit unit_of(int u, int spt, int tiles_per_slice) {
   Unit r;
-  if (PAIR) {
-    const int ppu = (spt + 1) >> 1;
-    r.slice = u / ppu; r.sst = 2 * (u - r.slice * ppu) + (int)rank; r.nh = 2;
-  } else {
-    r.slice = u / spt; r.sst = u - r.slice * spt; r.nh = (2 * r.sst + 1 < tiles_per_slice) ? 2 : 1;
-  }
+  r.slice = u / spt; r.sst = u - r.slice * spt; r.nh = (2 * r.sst + 1 < tiles_per_slice) ? 2 : 1;
   return r;
 }
 
 __device__ __forceinline__ void epi_bar3() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
-template <bool PAIR>
+template <bool F16>
 __global__ void __launch_bounds__(NTHREADS3, 1)
 conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p) {
-  pdl_launch();
+  constexpr int NA = ASlots<F16>::N, ACOLS = ASlots<F16>::COLS;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -141,37 +90,31 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
   uint64_t* aempty = afull + NA;         // [NA]    MMA commit -> converters
   uint64_t* tfull = aempty + NA;         // [NACC3] MMA commit -> epilogue
   uint64_t* tempty = tfull + NACC3;      // [NACC3] epilogue -> MMA
-  uint64_t* bpeer = tempty + NACC3;       // [NB]    PAIR: the peer's weight half has landed (remote arrive) -> leader's MMA warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bpeer + NB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC3);
   float* sRed = reinterpret_cast<float*>(tmem_slot + 2);   // [8 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = PAIR ? cluster_rank() : 0u;
-  const int nunits = PAIR ? p.B * p.D * ((p.spt + 1) >> 1) : p.nsuper;
+  const int nunits = p.nsuper;
 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); }
       for (int i = 0; i < NB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-      for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], PAIR ? 8 : 4); mbar_init(&aempty[i], 1); }
-      for (int i = 0; i < NACC3; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
-      for (int i = 0; i < NB; ++i) mbar_init(&bpeer[i], 1);
+      for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+      for (int i = 0; i < NACC3; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NUM_EPI_WARPS); }
       mbar_fence_init();
     }
     __syncwarp();
-    if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Dependents may be scheduled only now that this CTA owns its TMEM columns: a dependent CTA that became co-resident and
+  // allocated first would spin in griddepcontrol.wait while this one blocks in tcgen05.alloc.
+  pdl_launch();
   pdl_wait();                                      // everything above touched no global memory
   const int HW = p.H * p.W;
 
@@ -182,8 +125,8 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     if (lane == 0) {
       uint32_t ac = 0;
       long long w_r = 0; const long long t0 = clock64();
-      for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
-        const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const Unit un = unit_of(u, p.spt, p.tiles_per_slice);
         const int slice = un.slice, sst = un.sst, nh = un.nh;
         const int b = slice / p.D, d = slice - b * p.D;
         for (int widx = 0; widx < 9; ++widx) {
@@ -194,8 +137,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
             const uint32_t sa = ac % NR;
             T3WAIT(w_r, tc::mbar_wait(&rempty[sa], ((ac / NR) & 1) ^ 1));
             mbar_expect_tx(&rfull[sa], A_BYTES);
-            int q = (2 * sst + h) * p.step - 1 + (kh - 1) * p.W;
-            if (2 * sst + h >= p.tiles_per_slice) q = HW + 1024;          // dummy tile of a pair: everything out of bounds -> zero fill
+            const int q = (2 * sst + h) * p.step - 1 + (kh - 1) * p.W;
             tma_load_4d(base + sa * A_BYTES, &tmap, &rfull[sa], 0, q, dd, b);
             ++ac;
           }
@@ -205,23 +147,16 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     } else if (lane == 1) {
       uint32_t bc = 0;
       long long w_b = 0;
-      for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
-        const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const Unit un = unit_of(u, p.spt, p.tiles_per_slice);
         const int d = un.slice % p.D;
         for (int widx = 0; widx < 9; ++widx) {
           const int dd = d + widx / 3 - 1;
           if ((unsigned)dd >= (unsigned)p.D) continue;
           const uint32_t sb = bc % NB;
           T3WAIT(w_b, tc::mbar_wait(&bempty[sb], ((bc / NB) & 1) ^ 1));
-          if (PAIR) {       // this CTA's half of the N = 96 weight rows: rows [48 rank, 48 rank + 48) of B_hi and of B_lo
-            mbar_expect_tx(&bfull[sb], B_BYTES);
-            const float* wsrc = p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW + rank * (48 * 32);
-            bulk_g2s(sBring + sb * 2 * B_BYTES, wsrc, B_BYTES / 2, &bfull[sb]);
-            bulk_g2s(sBring + sb * 2 * B_BYTES + B_BYTES / 2, wsrc + B_BYTES / 4, B_BYTES / 2, &bfull[sb]);
-          } else {
-            mbar_expect_tx(&bfull[sb], 2 * B_BYTES);
-            bulk_g2s(sBring + sb * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[sb]);
-          }
+          mbar_expect_tx(&bfull[sb], 2 * B_BYTES);
+          bulk_g2s(sBring + sb * 2 * B_BYTES, p.wimg + (size_t)widx * WIMG_FLOATS_PER_WINDOW, 2 * B_BYTES, &bfull[sb]);
           ++bc;
         }
       }
@@ -236,31 +171,13 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     uint32_t a_ready = 0, b_ready = 0;           // the next A slot / weight stage was already seen full by a look-ahead poll
     long long w_a = 0, w_bf = 0, w_t = 0; const long long t0 = clock64();
     int it = 0;
-    if (PAIR && rank != 0) {
-      // peer CTA: no MMA issue; forward "my half of the weight stage has landed" to the leader
-      for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
-        const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
-        const int d = un.slice % p.D;
-        for (int widx = 0; widx < 9; ++widx) {
-          const int dd = d + widx / 3 - 1;
-          if ((unsigned)dd >= (unsigned)p.D) continue;
-          const uint32_t sbi = bc % NB;
-          T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
-          if (lane == 0) mbar_arrive_remote(&bpeer[sbi], 0);
-          __syncwarp();
-          ++bc;
-        }
-      }
-    } else
-    for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>(), ++it) {
-      const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++it) {
+      const Unit un = unit_of(u, p.spt, p.tiles_per_slice);
       const int d = un.slice % p.D;
       const int nh = un.nh;
       const int accs[2] = {(2 * it) % NACC3, (2 * it + 1) % NACC3};
-      for (int h = 0; h < nh; ++h) {
-        if (PAIR) T3WAIT(w_t, mbar_wait_warp_cluster(&tempty[accs[h]], ((accpar >> accs[h]) & 1) ^ 1));
-        else      T3WAIT(w_t, mbar_wait_warp(&tempty[accs[h]], ((accpar >> accs[h]) & 1) ^ 1));
-      }
+      for (int h = 0; h < nh; ++h)
+        T3WAIT(w_t, mbar_wait_warp(&tempty[accs[h]], ((accpar >> accs[h]) & 1) ^ 1));
       tc_fence_after();
       bool first = true;
       for (int widx = 0; widx < 9; ++widx) {
@@ -269,56 +186,60 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         const uint32_t sbi = bc % NB;
         if (!b_ready) T3WAIT(w_bf, mbar_wait_warp(&bfull[sbi], (bc / NB) & 1));
         b_ready = 0;
-        if (PAIR) T3WAIT(w_bf, mbar_wait_warp_cluster(&bpeer[sbi], (bc / NB) & 1));
         const uint32_t sb = smem_u + NR * A_BYTES + sbi * 2 * B_BYTES;
         for (int h = 0; h < nh; ++h) {
           const uint32_t aslot = ac % NA;
-          if (PAIR) T3WAIT(w_a, mbar_wait_warp_cluster(&afull[aslot], (ac / NA) & 1));
-          else if (!a_ready) T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
+          if (!a_ready) T3WAIT(w_a, mbar_wait_warp(&afull[aslot], (ac / NA) & 1));
           a_ready = 0;
           tc_fence_after();
           uint32_t peek_a = 0, peek_b = 0;       // look-ahead polls of the elected lane (see below)
-          const uint32_t ta = tmem_u + TA_BASE + aslot * 64;
+          const uint32_t ta = tmem_u + TA_BASE + aslot * ACOLS;
           const uint32_t tmem_d = tmem_u + accs[h] * ACC_STRIDE;
-          if (elect_one()) {                     // one election per 12 MMAs + commit (see tc_common.cuh)
-            const uint32_t lo_off = PAIR ? B_BYTES / 2 : B_BYTES;       // B_lo follows B_hi (half-height images in a pair)
+          if (elect_one()) {                     // one election per batch of MMAs + commit (see tc_common.cuh)
+            if (F16) {
+              // B stage: image P rows = [wh 64 B | wl 64 B], image Q rows = [2^-11 wh 64 B | unused]; A slot = [xh 16 cols | xl' 16 cols]
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (!PAIR && ks == 3) {
-                // Look ahead while the pipe still has the MMAs above queued: the tensor pipe's queue is shallow, so the issuing
-                // thread runs at pipe speed inside a batch and the pipe idled during the ~100-cycle barrier polls between
-                // batches.  A poll that already sees the NEXT batch's A slot (weight stage) full lets the next batch skip its wait.
-                peek_a = mbar_try_wait(&afull[(ac + 1) % NA], ((ac + 1) / NA) & 1) ? 1u : 0u;
-                if (h == nh - 1) peek_b = mbar_try_wait(&bfull[(bc + 1) % NB], ((bc + 1) / NB) & 1) ? 1u : 0u;
-              }
-              const uint64_t bh = make_desc(sb + ks * 32);
-              if (PAIR) {
-                mma2_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
-                if (p.passes == 3) {
-                  mma2_tf32_ts_raw(tmem_d, ta + 32 + ks * 8, bh, 1);
-                  mma2_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + lo_off + ks * 32), 1);
+              for (int ks = 0; ks < 2; ++ks) {
+                if (ks == 1) {
+                  // Look ahead while the pipe still has the MMAs above queued (the tensor pipe's queue is shallow: it idled during
+                  // the ~100-cycle barrier polls between batches); a poll that already sees the NEXT batch's operands ready lets
+                  // that batch skip its wait.
+                  peek_a = mbar_try_wait(&afull[(ac + 1) % NA], ((ac + 1) / NA) & 1) ? 1u : 0u;
+                  if (h == nh - 1) peek_b = mbar_try_wait(&bfull[(bc + 1) % NB], ((bc + 1) / NB) & 1) ? 1u : 0u;
                 }
-              } else {
+                const uint64_t bh = make_desc(sb + ks * 32);
+                mma_f16_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
+                mma_f16_ts_raw(tmem_d, ta + 16 + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
+                mma_f16_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + 64 + ks * 32), 1);
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks == 3) {
+                  peek_a = mbar_try_wait(&afull[(ac + 1) % NA], ((ac + 1) / NA) & 1) ? 1u : 0u;
+                  if (h == nh - 1) peek_b = mbar_try_wait(&bfull[(bc + 1) % NB], ((bc + 1) / NB) & 1) ? 1u : 0u;
+                }
+                const uint64_t bh = make_desc(sb + ks * 32);
                 mma_tf32_ts_raw(tmem_d, ta + ks * 8, bh, !(first && ks == 0));
                 if (p.passes == 3) {
                   mma_tf32_ts_raw(tmem_d, ta + 32 + ks * 8, bh, 1);
-                  mma_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + lo_off + ks * 32), 1);
+                  mma_tf32_ts_raw(tmem_d, ta + ks * 8, make_desc(sb + B_BYTES + ks * 32), 1);
                 }
               }
             }
-            if (PAIR) mma2_commit_raw(&aempty[aslot]); else mma_commit_raw(&aempty[aslot]);
+            mma_commit_raw(&aempty[aslot]);
           }
           a_ready = __any_sync(0xffffffffu, peek_a != 0);
           if (h == nh - 1) b_ready = __any_sync(0xffffffffu, peek_b != 0);
           ++ac;
         }
         first = false;
-        if (elect_one()) { if (PAIR) mma2_commit_raw(&bempty[sbi]); else mma_commit_raw(&bempty[sbi]); }
+        if (elect_one()) mma_commit_raw(&bempty[sbi]);
         __syncwarp();
         ++bc;
       }
       for (int h = 0; h < nh; ++h) {
-        if (elect_one()) { if (PAIR) mma2_commit_raw(&tfull[accs[h]]); else mma_commit_raw(&tfull[accs[h]]); }
+        if (elect_one()) mma_commit_raw(&tfull[accs[h]]);
         __syncwarp();
         accpar ^= 1u << accs[h];
       }
@@ -331,8 +252,8 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     const int m = quad * 32 + lane;
     uint32_t cnt = 0;                                              // A items: (window, tile of the pair)
     long long w_rf = 0, w_ae = 0, w_st = 0; const long long t0 = clock64();
-    for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>()) {
-      const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const Unit un = unit_of(u, p.spt, p.tiles_per_slice);
       const int d = un.slice % p.D;
       const int nh = un.nh;
       for (int item = 0; item < 9 * nh; ++item) {
@@ -350,32 +271,38 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         if (lane == 0) mbar_arrive(&rempty[s]);            // raw window consumed (values are in registers)
         T3WAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * 64;
-        {
-          uint32_t h[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * ACOLS;
+        if (F16) {
+          uint32_t hl[32];
+          split_f16(v, hl);
+          tmem_st32(ta, hl);
+        } else {
+          {
+            uint32_t h[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
-            h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
+            for (int c = 0; c < 8; ++c) {
+              h[4 * c] = tc::tf32_hi_bits(v[c].x); h[4 * c + 1] = tc::tf32_hi_bits(v[c].y);
+              h[4 * c + 2] = tc::tf32_hi_bits(v[c].z); h[4 * c + 3] = tc::tf32_hi_bits(v[c].w);
+            }
+            tmem_st32(ta, h);
           }
-          tmem_st32(ta, h);
-        }
-        if (p.passes == 3) {
-          uint32_t l[32];
+          if (p.passes == 3) {
+            uint32_t l[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 x4 = v[c];
-            l[4 * c] = __float_as_uint(x4.x - __uint_as_float(tc::tf32_hi_bits(x4.x)));
-            l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(tc::tf32_hi_bits(x4.y)));
-            l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(tc::tf32_hi_bits(x4.z)));
-            l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(tc::tf32_hi_bits(x4.w)));
+            for (int c = 0; c < 8; ++c) {
+              const float4 x4 = v[c];
+              l[4 * c] = __float_as_uint(x4.x - __uint_as_float(tc::tf32_hi_bits(x4.x)));
+              l[4 * c + 1] = __float_as_uint(x4.y - __uint_as_float(tc::tf32_hi_bits(x4.y)));
+              l[4 * c + 2] = __float_as_uint(x4.z - __uint_as_float(tc::tf32_hi_bits(x4.z)));
+              l[4 * c + 3] = __float_as_uint(x4.w - __uint_as_float(tc::tf32_hi_bits(x4.w)));
+            }
+            tmem_st32(ta + 32, l);
           }
-          tmem_st32(ta + 32, l);
         }
         T3WAIT(w_st, tmem_wait_st());
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_on_leader<PAIR>(&afull[aslot], rank);
+        if (lane == 0) mbar_arrive(&afull[aslot]);
         ++cnt;
       }
     }
@@ -396,20 +323,20 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bias4;
     if (e.bias) bias4 = reinterpret_cast<const float4*>(e.bias)[chunk];
     if (e.scale) { sc4 = reinterpret_cast<const float4*>(e.scale)[chunk]; sh4 = reinterpret_cast<const float4*>(e.shift)[chunk]; }
+    const float winv = F16 ? __ldg(p.wimg + WIMG_SCALE_SLOT) : 1.f;    // 2^-s of the weight image (power of two: exact)
     int it = 0;
     long long w_tf = 0; const long long t0 = clock64();
     uint32_t accpar = 0;                             // same bookkeeping as the MMA warp (a single-tile pair skips one accumulator)
-    for (int u = unit_first<PAIR>(rank); u < nunits; u += unit_step<PAIR>(), ++it) {
-     const Unit un = unit_of<PAIR>(u, p.spt, p.tiles_per_slice, rank);
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++it) {
+     const Unit un = unit_of(u, p.spt, p.tiles_per_slice);
      const int slice = un.slice, sst = un.sst, nh = un.nh;
      for (int hh2 = 0; hh2 < nh; ++hh2) {
       const int acc = (2 * it + hh2) % NACC3;
       const uint32_t accphase = (accpar >> acc) & 1;
       accpar ^= 1u << acc;
       const int tt = 2 * sst + hh2;
-      const bool real_tile = tt < p.tiles_per_slice;      // false: dummy tile of a pair (nothing is stored)
       const int tile = slice * p.tiles_per_slice + tt;
-      const int q0 = real_tile ? tt * p.step - 1 : HW;
+      const int q0 = tt * p.step - 1;
       int ww[4]; bool okr[4]; size_t goff[4];
       {
         const int q = q0 + rg;
@@ -449,7 +376,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) arrive_on_leader<PAIR>(&tempty[acc], rank);
+      if (lane == 0) mbar_arrive(&tempty[acc]);
       epi_bar3();
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -463,8 +390,13 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         if (ww[j] == 0) a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ww[j] == p.W - 1) c = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 o;
-        o.x = (a.x + bb.x) + c.x + bias4.x; o.y = (a.y + bb.y) + c.y + bias4.y;
-        o.z = (a.z + bb.z) + c.z + bias4.z; o.w = (a.w + bb.w) + c.w + bias4.w;
+        if (F16) {
+          o.x = fmaf((a.x + bb.x) + c.x, winv, bias4.x); o.y = fmaf((a.y + bb.y) + c.y, winv, bias4.y);
+          o.z = fmaf((a.z + bb.z) + c.z, winv, bias4.z); o.w = fmaf((a.w + bb.w) + c.w, winv, bias4.w);
+        } else {
+          o.x = (a.x + bb.x) + c.x + bias4.x; o.y = (a.y + bb.y) + c.y + bias4.y;
+          o.z = (a.z + bb.z) + c.z + bias4.z; o.w = (a.w + bb.w) + c.w + bias4.w;
+        }
         if (has_stats && okr[j]) {
           s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
           s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
@@ -485,7 +417,7 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
           for (int c = 0; c < 4; ++c) { sRed[ew * 64 + lane * 4 + c] = s1[c]; sRed[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
         }
         epi_bar3();
-        if (et < 64 && real_tile) {
+        if (et < 64) {
           float a = 0.f;
 #pragma unroll
           for (int wq = 0; wq < NUM_EPI_WARPS; ++wq) a += sRed[wq * 64 + et];
@@ -500,31 +432,15 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
 
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();            // the peer may still be reading its accumulators / receiving multicast arrivals
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
-    else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
   }
 }
 
 }  // namespace tc3
 
 // ---- host side
-typedef CUresult (*snb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static snb_encode_tiled_fn snb_get_encode_tiled() {
-  static snb_encode_tiled_fn fn = []() -> snb_encode_tiled_fn {       // thread-safe one-time lookup of a driver entry point
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult st;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return nullptr;
-    return reinterpret_cast<snb_encode_tiled_fn>(p);
-  }();
-  return fn;
-}
-
 int snb_conv3d_tma_setup(const snb_conv_geom* g, tc3::Params3& p, const char* who) {
   SNB_REQUIRE(g != nullptr, "%s: null geometry", who);
   SNB_REQUIRE(g->transposed == 0 && g->stride == 1 && g->KD == 3 && g->KH == 3 && g->KW == 3 && g->dil == 1, "%s: needs a stride-1 3x3x3 conv", who);
@@ -551,6 +467,8 @@ int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb
   tc3::Params3 p;
   if (int rc = snb_conv3d_tma_setup(g, p, "snb_conv_c32_tc")) return rc;
   SNB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "snb_conv_c32_tc: x must be 16-byte aligned");
+  const bool f16 = (passes & SNB_CONV_F16) != 0;       // weight image in the fp16-split format (snb_prep_conv_weights_tc mode | 0x10)
+  passes &= 0xf;
   p.wimg = wimg; p.y = y; p.passes = passes; p.e = *e; p.dbg = dbg;
   snb_encode_tiled_fn enc = snb_get_encode_tiled();
   SNB_REQUIRE(enc != nullptr, "snb_conv_c32_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -567,17 +485,13 @@ int snb_conv3d_tma_launch(const float* x, const float* wimg, float* y, const snb
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // SNB200_CONV3D=pair selects the experimental cta_group::2 variant (measured slower, see the header comment)
-  static const bool single = []() { const char* s = getenv("SNB200_CONV3D"); return !(s != nullptr && strcmp(s, "pair") == 0); }();
-  if (single || sms < 2) {
-    const int grid = p.nsuper < sms ? p.nsuper : sms;
+  const int grid = p.nsuper < sms ? p.nsuper : sms;
+  if (f16) {
+    SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
+    snb_launch(tc3::conv3d_c32_tma_kernel<true>, grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
+  } else {
     SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
     snb_launch(tc3::conv3d_c32_tma_kernel<false>, grid, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
-  } else {
-    const int npu = g->B * g->D * ((p.spt + 1) / 2);            // pair units
-    const int ncl = npu < sms / 2 ? npu : sms / 2;
-    SNB_CUDA(cudaFuncSetAttribute(tc3::conv3d_c32_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES3));
-    snb_launch_cluster2(tc3::conv3d_c32_tma_kernel<true>, 2 * ncl, tc3::NTHREADS3, tc3::SMEM_BYTES3, stream, tmap, p);
   }
   SNB_LAUNCH_CHECK("conv3d_c32_tma_kernel");
   return 0;

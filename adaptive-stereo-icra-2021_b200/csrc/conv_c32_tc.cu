@@ -323,10 +323,65 @@ conv_c32_tc_kernel(const Params p) {
   }
 }
 
+// ---- fp16-split weight image (SNB_CONV_F16).  Per (kd,kh) window two 12 KB blocks of 96 rows x 128 B, SWIZZLE_128B K-major:
+//   P: row n = [wh(n, cin 0..31) 64 B | wl(n, cin 0..31) 64 B]      Q: row n = [2^-11 wh 64 B | unused]
+// with w' = w * 2^s, wh = fp16(w'), wl = fp16(w' - wh).  2^-s sits in the spare slot WIMG_SCALE_SLOT of the image (written by
+// weight_scale_kernel, which must run before the prep kernel on the same stream).
+__device__ __forceinline__ void store_f16_split(float* __restrict__ out, int win, int n, int k, float v, float scale) {
+  const float vs = v * scale;
+  const __half wh = __float2half_rn(vs);
+  const float whf = __half2float(wh);
+  const __half wl = __float2half_rn(vs - whf);
+  const __half whs = __float2half_rn(whf * (1.f / 2048.f));
+  __half* img = reinterpret_cast<__half*>(out + (size_t)win * WIMG_FLOATS_PER_WINDOW);
+  const int sw = n & 7;
+  img[n * 64 + ((((k >> 3)) ^ sw) << 3) + (k & 7)] = wh;                       // logical 16-B chunks 0..3
+  img[n * 64 + ((((k >> 3) + 4) ^ sw) << 3) + (k & 7)] = wl;                   // logical chunks 4..7
+  img[B_BYTES / 2 + n * 64 + ((((k >> 3)) ^ sw) << 3) + (k & 7)] = whs;
+  if (win != 0 || n != 0 || k >= 2)                                            // the other half of Q is never an operand; keep it
+    img[B_BYTES / 2 + n * 64 + ((((k >> 3) + 4) ^ sw) << 3) + (k & 7)] = __float2half_rn(0.f);   // defined (halfs 32,33 of row 0 = the 2^-s slot)
+}
+
+// 2^-s for one weight tensor of `numel` floats: s = 13 - floor(log2 max|w|), i.e. max|w * 2^s| in [2^13, 2^14) — far from the
+// fp16 overflow (65504) and with the low parts wl ~ 2^-11 w' of everything above 2^-16 max|w| still normal fp16 numbers.
+__device__ __forceinline__ void weight_scale_block(const float* __restrict__ w, int numel, float* __restrict__ slot) {
+  __shared__ float smax[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < numel; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, smax[i]);
+    int s = 0;
+    if (m > 0.f && m <= 3.0e38f) s = 13 - ilogbf(m);
+    s = s < -20 ? -20 : (s > 40 ? 40 : s);
+    *slot = ldexpf(1.f, -s);
+  }
+}
+__global__ void weight_scale_kernel(const float* __restrict__ w, int numel, float* __restrict__ slot) {
+  pdl_launch(); pdl_wait();
+  weight_scale_block(w, numel, slot);
+}
+__global__ void weight_scale_batch_kernel(const long long* __restrict__ table) {
+  pdl_launch(); pdl_wait();
+  const long long* e = table + 4 * blockIdx.x;
+  const int cfg = (int)e[2];
+  if (((cfg >> 8) & SNB_CONV_F16) == 0) return;
+  const int nwin = cfg & 0xff, kind = (cfg >> 16) & 0xff;
+  weight_scale_block(reinterpret_cast<const float*>(e[0]), kind == 0 ? 1024 * nwin * 3 : 1024 * 25,
+                     reinterpret_cast<float*>(e[1]) + WIMG_SCALE_SLOT);
+}
+
 // w [32 cout][32 cin][kd*kh*kw taps] -> per (kd,kh) window: B_hi[n = kw*32 + cout][k = cin] then B_lo, each in the
 // SWIZZLE_128B K-major smem image (row n = 128 B, 16-B chunk c stored at c ^ (n & 7)).  mode 1: data-gradient weights.
+// mode | SNB_CONV_F16: the fp16-split format above.
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int nwin, int mode) {
   pdl_launch(); pdl_wait();
+  const bool f16 = (mode & SNB_CONV_F16) != 0;
+  mode &= 0xf;
+  const float scale = f16 ? 1.f / out[WIMG_SCALE_SLOT] : 1.f;
   const int taps = nwin * 3;
   const int total = nwin * 96 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -338,6 +393,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
     float v;
     if (mode == 0) v = w[((size_t)co * 32 + k) * taps + tap];
     else           v = w[((size_t)k * 32 + co) * taps + (taps - 1 - tap)];   // dgrad: swap channels, flip taps
+    if (f16) { store_f16_split(out, win, n, k, v, scale); continue; }
     const float hi = __uint_as_float(tc::tf32_hi_bits(v));
     const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
     out[o] = hi;
@@ -352,7 +408,9 @@ __global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table
   const float* __restrict__ w = reinterpret_cast<const float*>(e[0]);
   float* __restrict__ out = reinterpret_cast<float*>(e[1]);
   const int cfg = (int)e[2];
-  const int nwin = cfg & 0xff, mode = (cfg >> 8) & 0xff, kind = (cfg >> 16) & 0xff, pa = (cfg >> 24) & 0xf, pb = (cfg >> 28) & 0xf;
+  const int nwin = cfg & 0xff, mode = (cfg >> 8) & 0xf, kind = (cfg >> 16) & 0xff, pa = (cfg >> 24) & 0xf, pb = (cfg >> 28) & 0xf;
+  const bool f16 = ((cfg >> 8) & SNB_CONV_F16) != 0;
+  const float scale = f16 ? 1.f / out[WIMG_SCALE_SLOT] : 1.f;
   const int taps = nwin * 3;
   const int total = nwin * 96 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -370,6 +428,7 @@ __global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table
       const int y5 = 2 * (tap / 3) + pa, x5 = 2 * (tap % 3) + pb;
       v = (y5 < 5 && x5 < 5) ? w[((size_t)oc * 32 + ic) * 25 + y5 * 5 + x5] : 0.f;
     }
+    if (f16) { store_f16_split(out, win, n, k, v, scale); continue; }
     const float hi = __uint_as_float(tc::tf32_hi_bits(v));
     const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
     out[o] = hi;
@@ -411,8 +470,12 @@ extern "C" int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g) {
 extern "C" int snb_conv_weights_tc_floats(int kd) { return kd * 3 * tc::WIMG_FLOATS_PER_WINDOW; }
 
 extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream) {
-  SNB_REQUIRE(w && out && (kd == 1 || kd == 3) && (mode == 0 || mode == 1), "snb_prep_conv_weights_tc: bad args");
+  SNB_REQUIRE(w && out && (kd == 1 || kd == 3) && ((mode & ~SNB_CONV_F16) == 0 || (mode & ~SNB_CONV_F16) == 1), "snb_prep_conv_weights_tc: bad args");
   const int nwin = kd * 3;
+  if (mode & SNB_CONV_F16) {
+    snb_launch(tc::weight_scale_kernel, 1, 256, 0, stream, w, 1024 * nwin * 3, out + tc::WIMG_SCALE_SLOT);
+    SNB_LAUNCH_CHECK("weight_scale_kernel");
+  }
   snb_launch(tc::prep_weights_tc_kernel, snb_ceil_div(nwin * 96 * 32, 256), 256, 0, stream, w, out, nwin, mode);
   SNB_LAUNCH_CHECK("prep_weights_tc_kernel");
   return 0;
@@ -420,6 +483,8 @@ extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int 
 
 extern "C" int snb_prep_conv_weights_tc_batch(const long long* table, int n, void* stream) {
   SNB_REQUIRE(table && n > 0 && n <= 65535, "snb_prep_conv_weights_tc_batch: bad args");
+  snb_launch(tc::weight_scale_batch_kernel, n, 256, 0, stream, table);       // no-op blocks for TF32-format entries
+  SNB_LAUNCH_CHECK("weight_scale_batch_kernel");
   snb_launch(tc::prep_weights_tc_batch_kernel, dim3(36, n), 256, 0, stream, table);
   SNB_LAUNCH_CHECK("prep_weights_tc_batch_kernel");
   return 0;
@@ -445,7 +510,8 @@ static int conv_c32_tc_launch(const float* x, const float* wimg, float* y, const
   if (int rc = tc_setup(g, p, "snb_conv_c32_tc")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv_c32_tc: null pointer");
   if (g->KD == 3 && (passes & 0x400) == 0) {                            // 3-D product path (dbg: per-role wait counters)
-    SNB_REQUIRE((passes & 0xff) == 1 || (passes & 0xff) == 3, "snb_conv_c32_tc: passes must be 1 or 3");
+    SNB_REQUIRE((passes & 0xef) == 1 || (passes & 0xef) == 3, "snb_conv_c32_tc: passes must be 1 or 3");
+    SNB_REQUIRE((passes & SNB_CONV_F16) == 0 || (passes & 0xf) == 3, "snb_conv_c32_tc: the fp16 split has 3 passes");
     SNB_REQUIRE(!e->scale || e->shift, "snb_conv_c32_tc: scale without shift");
     return snb_conv3d_tma_launch(x, wimg, y, g, e, passes & 0xff, dbg, stream);
   }

@@ -1,6 +1,24 @@
 // Shared tcgen05 / TMEM / mbarrier helpers of the tensor-core convolution kernels (sm_100a).
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda.h>
+
+// ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*snb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline snb_encode_tiled_fn snb_get_encode_tiled() {
+  static snb_encode_tiled_fn fn = []() -> snb_encode_tiled_fn {       // thread-safe one-time lookup of a driver entry point
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<snb_encode_tiled_fn>(p);
+  }();
+  return fn;
+}
+
 
 namespace tc {
 
@@ -145,6 +163,41 @@ __device__ __forceinline__ void mma_tf32_raw(uint32_t tmem_d, uint64_t adesc, ui
 }
 __device__ __forceinline__ void mma_commit_raw(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- fp16-split operands (kind::f16, M128 N96 K16, fp32 accumulate): instruction descriptor with A = B = f16 (format 0),
+// D = f32, K-major A and B.  The A operand sits in TMEM as packed pairs: 32-bit column j of lane m = {k = 2j (low half), 2j + 1}.
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void mma_f16_ts_raw(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC_F16), "r"(accumulate) : "memory");
+}
+// Float index (from the start of a weight image) of the spare slot that carries 2^-s, the inverse of the power-of-two scale the
+// fp16-split weights were multiplied with: image Q (second 12 KB block of window 0), row 0, logical 16-B chunk 4 (never an operand).
+constexpr int WIMG_SCALE_SLOT = B_BYTES / 4 + 16;
+// {lo, hi} -> packed f16x2 (lo in the low half), round to nearest, saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+// 32 fp32 channels of one position -> 16 packed xh words | 16 packed xl' words, xh = fp16(x), xl' = fp16((x - xh) * 2^11)
+__device__ __forceinline__ void split_f16(const float4 (&v)[8], uint32_t (&hl)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t h0 = pack_f16x2(v[c].x, v[c].y), h1 = pack_f16x2(v[c].z, v[c].w);
+    const float2 f0 = unpack_f16x2(h0), f1 = unpack_f16x2(h1);
+    hl[2 * c] = h0; hl[2 * c + 1] = h1;
+    hl[16 + 2 * c] = pack_f16x2((v[c].x - f0.x) * 2048.f, (v[c].y - f0.y) * 2048.f);
+    hl[16 + 2 * c + 1] = pack_f16x2((v[c].z - f1.x) * 2048.f, (v[c].w - f1.y) * 2048.f);
+  }
 }
 
 // M128 N32 K8 variant (small-Cin im2col convolutions, 32->1 tap contractions), A from TMEM; call inside one elected region

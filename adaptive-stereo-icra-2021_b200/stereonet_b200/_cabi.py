@@ -44,6 +44,7 @@ SIGNATURES = {
   "snb_refine_in_conv_num_tiles": (_I, [_I, _I, _I]),
   "snb_conv_c32_taps": (_I, [_P, _P, _P, _LL, _I, _I, _P]),
   "snb_tapsum_softargmin": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+  "snb_conv3d_out_softargmin": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
   "snb_tapsum_refine_out": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
   "snb_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
   "snb_upsample_bilinear_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),

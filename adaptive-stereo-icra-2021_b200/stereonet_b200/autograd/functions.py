@@ -112,13 +112,13 @@ class Conv3dOutSoftargmin(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w, b):
-    taps = ops.conv_c32_taps(x, w, 27)
-    cost, pred = ops.tapsum_softargmin(taps, b, True)
+    cost, pred, fcs = ops.conv3d_out_softargmin(x, w, b, want_cost=True, want_fcs=x.shape[1] > 2)
     ctx.save_for_backward(x, w, cost, pred)
-    return cost, pred
+    ctx.mark_non_differentiable(fcs) if fcs is not None else None
+    return cost, pred, fcs
 
   @staticmethod
-  def backward(ctx, dcost_out, dpred):
+  def backward(ctx, dcost_out, dpred, _dfcs=None):
     x, w, cost, pred = ctx.saved_tensors
     dcost = ops.softargmin_bwd(cost, pred, _c(dpred), _c(dcost_out))
     dx, dw, db = ops.conv_c32_taps_bwd(x, w, dcost, 27)
@@ -126,7 +126,9 @@ class Conv3dOutSoftargmin(torch.autograd.Function):
 
 
 def conv3d_out_softargmin_autograd(x, conv, want_cost):
-  cost, pred = Conv3dOutSoftargmin.apply(x, conv.weight, conv.bias)
+  cost, pred, fcs = Conv3dOutSoftargmin.apply(x, conv.weight, conv.bias)
+  if want_cost and fcs is not None:
+    cost._snb_fcs = fcs
   return (cost if want_cost else None), pred
 
 

@@ -49,28 +49,35 @@ def clear_cache(module):
 
 import os
 
-# Convolution backend for the stride-1 3x3 / 3x3x3 32->32 layers: "tc3" = tcgen05 3xTF32 (fp32-grade, default),
-# "tc1" = tcgen05 single-pass TF32 (faster, ~1e-3 relative), "ffma" = fp32 CUDA-core kernel.  All three are this
-# library's own kernels; the switch exists for measurement and cross-checking, not as a fallback.
-CONV_BACKEND = os.environ.get("SNB200_CONV", "tc3")
+# Operand format of the stride-1 3x3 / 3x3x3 32->32 tensor-core layers.  "h3" (the product path): error-compensated fp16 split
+# (tcgen05 kind::f16, fp32-grade results).  The other values exist for the parity tests and A/B measurements only (set with
+# set_conv_backend, never from the environment): "tc3" = 3xTF32 split, "tc1" = single-pass TF32 (~1e-3 relative),
+# "ffma" = fp32 CUDA-core kernel.
+CONV_BACKEND = "h3"
 
 
 def set_conv_backend(name):
   global CONV_BACKEND
-  if name not in ("tc3", "tc1", "ffma"):
+  if name not in ("h3", "tc3", "tc1", "ffma"):
     raise ValueError(name)
   CONV_BACKEND = name
+  bump_epoch()                 # cached weight images are in the previous backend's format
+
+
+def _tc_kw():
+  return dict(f16=True, passes=3) if CONV_BACKEND == "h3" else dict(f16=False, passes=3 if CONV_BACKEND == "tc3" else 1)
 
 
 def wprep_tc(conv, mode=0):
-  return _cached(conv, ("wtc", mode), [conv.weight], lambda: ops.prep_conv_weights_tc(conv.weight, mode))
+  f16 = CONV_BACKEND == "h3"
+  return _cached(conv, ("wtc", mode, f16), [conv.weight], lambda: ops.prep_conv_weights_tc(conv.weight, mode, f16=f16))
 
 
 def conv3x3_c32(x, conv, g, **kw):
   """Backend dispatch for the 'same' 3x3(x3) convolution + fused epilogue."""
   if CONV_BACKEND == "ffma":
     return ops.conv_c32(x, wprep(conv), g, **kw)
-  return ops.conv_c32_tc(x, wprep_tc(conv), g, passes=3 if CONV_BACKEND == "tc3" else 1, **kw)
+  return ops.conv_c32_tc(x, wprep_tc(conv), g, **_tc_kw(), **kw)
 
 
 def wprep(conv, mode=0):
@@ -98,14 +105,14 @@ def conv3x3_c32_dgrad(dy, conv, g, residual=None):
   """Data gradient of a stride-1 'same' 3x3(x3) conv: the same convolution kernels with flipped/transposed weights."""
   if CONV_BACKEND == "ffma":
     return ops.conv_c32(dy, wprep(conv, 1), g, residual=residual)
-  return ops.conv_c32_tc(dy, wprep_tc(conv, 1), g, residual=residual, passes=3 if CONV_BACKEND == "tc3" else 1)
+  return ops.conv_c32_tc(dy, wprep_tc(conv, 1), g, residual=residual, **_tc_kw())
 
 
 def conv3x3_c32_wgrad(x, dz, g, wshape):
   """Weight gradient of a stride-1 'same' 3x3(x3) conv: tensor-core kernel unless the FFMA backend is selected."""
   if CONV_BACKEND == "ffma":
     return ops.conv_c32_wgrad(x, dz, g, wshape)
-  return ops.conv_c32_wgrad_tc(x, dz, g, wshape, passes=3 if CONV_BACKEND == "tc3" else 1)
+  return ops.conv_c32_wgrad_tc(x, dz, g, wshape, passes=1 if CONV_BACKEND == "tc1" else 3)
 
 
 def _needs_grad(*tensors_or_modules):
@@ -136,6 +143,8 @@ def conv5x5s2_first(img, conv):
 
 def wprep_tc_phases(conv, mode):
   """Tensor-core weight images of the four polyphase 3x3 sub-kernels of a 5x5 stride-2 conv (csrc/phase.cu)."""
+  f16 = CONV_BACKEND == "h3"
+
   def make():
     w = conv.weight.detach()
     imgs = []
@@ -143,9 +152,9 @@ def wprep_tc_phases(conv, mode):
       for b in (0, 1):
         sub = w[:, :, a::2, b::2]                                  # [32,32,3|2,3|2]  (layout ops only)
         sub = torch.nn.functional.pad(sub, (0, 3 - sub.shape[3], 0, 3 - sub.shape[2])).contiguous()
-        imgs.append(ops.prep_conv_weights_tc(sub, mode))
+        imgs.append(ops.prep_conv_weights_tc(sub, mode, f16=f16))
     return imgs
-  return _cached(conv, ("wtc_phase", mode), [conv.weight], make)
+  return _cached(conv, ("wtc_phase", mode, f16), [conv.weight], make)
 
 
 class WeightPrepBatch:
@@ -156,6 +165,9 @@ class WeightPrepBatch:
 
   def __init__(self, nets, modes=(0, 1)):
     self.items = []                      # (conv, cache key, views, source pointer)
+    self.backend = CONV_BACKEND
+    f16 = CONV_BACKEND == "h3"
+    fbit = ops.CONV_F16 if f16 else 0
     rows = []
     plan = []
     for net in nets:
@@ -168,10 +180,10 @@ class WeightPrepBatch:
         if tuple(w.shape[2:]) in ((3, 3), (3, 3, 3)) and m.stride[0] == 1:
           kd = 3 if w.dim() == 5 else 1
           for mode in modes:
-            plan.append((m, ("wtc", mode), [(kd * 3, mode, 0, 0, 0)]))
+            plan.append((m, ("wtc", mode, f16), [(kd * 3, mode | fbit, 0, 0, 0)]))
         elif tuple(w.shape[2:]) == (5, 5) and m.stride[0] == 2:
           for mode in modes:
-            plan.append((m, ("wtc_phase", mode), [(3, mode, 1, a, b) for a in (0, 1) for b in (0, 1)]))
+            plan.append((m, ("wtc_phase", mode, f16), [(3, mode | fbit, 1, a, b) for a in (0, 1) for b in (0, 1)]))
     per_win = ops.conv_weights_tc_floats(1) // 3
     total = sum(cfg[0] * per_win for _, _, cfgs in plan for cfg in cfgs)
     dev = plan[0][0].weight.device
@@ -189,7 +201,7 @@ class WeightPrepBatch:
     self.n = len(rows)
 
   def valid(self):
-    return all(m.weight.data_ptr() == ptr and m.weight.is_contiguous() for m, _, _, ptr in self.items)
+    return self.backend == CONV_BACKEND and all(m.weight.data_ptr() == ptr and m.weight.is_contiguous() for m, _, _, ptr in self.items)
 
   def refresh(self):
     ops.prep_conv_weights_tc_batch(self.table, self.n)
@@ -207,10 +219,9 @@ def conv5x5s2_c32(x, conv, bias, phases=None):
     return y
   ph = phases if phases is not None else ops.phase_split(x)
   g3 = ops.geom(ph[0].shape, 3, stride=1, dil=1)
-  passes = 3 if CONV_BACKEND == "tc3" else 1
   y = None
   for i, wimg in enumerate(wprep_tc_phases(conv, 0)):
-    y, _ = ops.conv_c32_tc(ph[i], wimg, g3, bias=bias if i == 0 else None, residual=y, passes=passes)
+    y, _ = ops.conv_c32_tc(ph[i], wimg, g3, bias=bias if i == 0 else None, residual=y, **_tc_kw())
   return y
 
 
@@ -221,10 +232,9 @@ def conv5x5s2_c32_dgrad(dy, conv, H, W):
     dx, _ = ops.conv_c32(dy, wprep(conv, 2), ops.geom_transposed(g))
     return dx
   g3 = ops.geom(dy.shape, 3, stride=1, dil=1)
-  passes = 3 if CONV_BACKEND == "tc3" else 1
   ph = torch.empty((4,) + tuple(dy.shape), device=dy.device, dtype=torch.float32)
   for i, wimg in enumerate(wprep_tc_phases(conv, 1)):
-    ops.conv_c32_tc(dy, wimg, g3, passes=passes, out=ph[i])
+    ops.conv_c32_tc(dy, wimg, g3, out=ph[i], **_tc_kw())
   return ops.phase_merge(ph, H, W)
 
 
@@ -280,11 +290,16 @@ def cost_volume(left, right, D):
 
 
 def conv3d_out_softargmin(x, conv, want_cost):
+  """conv3d_alone + softmax + DisparityRegression (stereo_net.py:187-198): one kernel.  When the cost volume is requested its
+  feature-contrast map comes out of the same epilogue and rides along as `cost._snb_fcs` (losses.feature_contrast_mean)."""
   if _needs_grad(x, conv):
     from . import functions
     return functions.conv3d_out_softargmin_autograd(x, conv, want_cost)
-  taps = ops.conv_c32_taps(x, conv.weight, 27)
-  return ops.tapsum_softargmin(taps, conv.bias, want_cost)
+  cost, pred, fcs = ops.conv3d_out_softargmin(x, conv.weight, conv.bias, want_cost=want_cost,
+                                              want_fcs=want_cost and x.shape[1] > 2)
+  if fcs is not None:
+    cost._snb_fcs = fcs
+  return cost, pred
 
 
 def upsample(pred, H, W, mul):

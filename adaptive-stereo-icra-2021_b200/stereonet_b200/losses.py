@@ -127,6 +127,9 @@ def feature_contrast_mean(cost_volume):
   the reference formulation (kept for CPU tensors in tests)."""
   if cost_volume.is_cuda:
     from . import ops
+    fcs = getattr(cost_volume, "_snb_fcs", None)          # written by the fused head kernel next to this cost volume
+    if fcs is not None and fcs.shape == cost_volume.shape[:1] + cost_volume.shape[2:]:
+      return fcs
     with torch.no_grad():
       return ops.feature_contrast(cost_volume.detach().contiguous())
   with torch.no_grad():

@@ -116,15 +116,19 @@ def conv_c32(x, wprep, g, bias=None, scale=None, shift=None, residual=None, lrel
   return y, stats
 
 
-def prep_conv_weights_tc(w, mode=0):
-  """[32,32,(3,)3,3] -> tensor-core B-operand image (see snb_prep_conv_weights_tc)."""
+CONV_F16 = 0x10      # SNB_CONV_F16: fp16-split operand format (weight image and `passes` flag must match)
+
+
+def prep_conv_weights_tc(w, mode=0, f16=True):
+  """[32,32,(3,)3,3] -> tensor-core B-operand image (see snb_prep_conv_weights_tc); f16: the fp16-split format."""
   w = _req(w.detach().contiguous(), "weight")
   if w.shape[0] != 32 or w.shape[1] != 32 or tuple(w.shape[-2:]) != (3, 3):
     raise RuntimeError(f"stereonet_b200: tensor-core conv needs a [32,32,(3,)3,3] weight, got {tuple(w.shape)}")
   kd = 3 if w.dim() == 5 else 1
   out = torch.empty((_cabi.lib().snb_conv_weights_tc_floats(kd),), device=w.device, dtype=torch.float32)
-  check(_cabi.lib().snb_prep_conv_weights_tc(_p(w), _p(out), kd, mode, _stream(w)), "snb_prep_conv_weights_tc")
-  _count()
+  check(_cabi.lib().snb_prep_conv_weights_tc(_p(w), _p(out), kd, mode | (CONV_F16 if f16 else 0), _stream(w)),
+        "snb_prep_conv_weights_tc")
+  _count(2 if f16 else 1)
   return out
 
 
@@ -135,13 +139,14 @@ def conv_weights_tc_floats(kd):
 def prep_conv_weights_tc_batch(table, n):
   """One launch for n weight images; `table` is an int64 device tensor [n,4] (see snb_prep_conv_weights_tc_batch)."""
   check(_cabi.lib().snb_prep_conv_weights_tc_batch(_p(table), n, _stream(table)), "snb_prep_conv_weights_tc_batch")
-  _count()
+  _count(2)
 
 
 def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
-                flat=False, a_smem=False, out=None, legacy3d=False):
-  """Tensor-core (tcgen05, TF32) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.
-  2-D inputs use the vertical-walk kernel (snb_conv2d_c32_tc) unless flat=True; 3-D inputs the flat-tiled one."""
+                flat=False, out=None, legacy3d=False, f16=True):
+  """Tensor-core (tcgen05) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.  f16 (default):
+  error-compensated fp16 operand split (kind::f16), else TF32 (passes = 3: 3xTF32, 1: plain); `wimg` must be in the same format.
+  2-D inputs use the vertical-walk kernel (snb_conv2d_c32_tc) unless flat=True; 3-D inputs the TMA kernel."""
   three_d = x.dim() == 5
   _req(x, "x"); _req(wimg, "wimg")
   lib = _cabi.lib()
@@ -161,10 +166,12 @@ def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lr
     if residual.shape != y.shape:
       raise RuntimeError("stereonet_b200: residual shape mismatch")
   e = ConvEpilogue(_p(bias), _p(scale), _p(shift), _p(residual), _p(stats), 1 if lrelu else 0)
-  if a_smem and use2d:
-    passes |= 0x100                      # diagnostics: 2-D kernel with the A operand from shared memory instead of TMEM
+  if f16:
+    if passes != 3 or (flat and not three_d) or legacy3d:
+      raise RuntimeError("stereonet_b200: the fp16 operand split has 3 passes and runs on the product kernels only")
+    passes |= CONV_F16
   if three_d and legacy3d:
-    passes |= 0x400                      # diagnostics: 3-D flat-tiled kernel with loader warps instead of the TMA kernel                      # diagnostics: A operand from shared memory instead of TMEM
+    passes |= 0x400                      # diagnostics: 3-D flat-tiled kernel with loader warps instead of the TMA kernel
   check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
   _count()
   return y, stats
@@ -253,6 +260,20 @@ def tapsum_softargmin(taps, bias, want_cost):
         "snb_tapsum_softargmin")
   _count()
   return cost, pred
+
+
+def conv3d_out_softargmin(x, w, bias, want_cost=True, want_fcs=False):
+  """conv3d_alone + softmax + expectation in one kernel (snb_conv3d_out_softargmin).  x [B,D,H,W,32] -> (cost [B,D,H,W] or
+  None, pred [B,H,W], fcs [B,H,W] or None)."""
+  _req(x, "x", 5)
+  B, D, H, W, _ = x.shape
+  pred = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+  cost = torch.empty((B, D, H, W), device=x.device, dtype=torch.float32) if want_cost else None
+  fcs = torch.empty((B, H, W), device=x.device, dtype=torch.float32) if want_fcs else None
+  check(_cabi.lib().snb_conv3d_out_softargmin(_p(x), _p(_req(w.detach(), "w")), _p(bias.detach()), _p(cost), _p(pred), _p(fcs),
+                                              B, D, H, W, _stream(x)), "snb_conv3d_out_softargmin")
+  _count()
+  return cost, pred, fcs
 
 
 def tapsum_refine_out(taps, bias, up, relu=True):

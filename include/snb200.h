@@ -31,6 +31,10 @@ extern "C" {
 #endif
 
 #define SNB_C 32 /* channel width of every hidden activation (stereo_net.py:59,64,155) */
+/* OR-ed into `passes` of the tensor-core convolutions / `mode` of snb_prep_conv_weights_tc: error-compensated split with fp16
+ * operands (tcgen05.mma.kind::f16, K = 16, power-of-two weight scaling) instead of 3xTF32 — same three products, same
+ * fp32-grade result, half the MMA count.  The weight image must have been prepared in the matching format. */
+#define SNB_CONV_F16 0x10
 
 /* Geometry of one convolution over channels-last tensors. 2-D convs use D = OD = KD = 1, pd = 0. */
 typedef struct {
@@ -144,6 +148,15 @@ SNB_API int snb_conv_c32_taps(const float* x, const float* w /*[1][32][ntaps]*/,
  * cost_out may be NULL (stereo_net.py:197-198 returns it when requested). */
 SNB_API int snb_tapsum_softargmin(const float* taps /*[B,D,27,H,W]*/, const float* bias /*[1]*/, float* cost_out /*[B,D,H,W]*/,
                           float* pred /*[B,H,W]*/, int B, int D, int H, int W, void* stream);
+
+/* conv3d_alone + softmax + DisparityRegression as ONE kernel (stereo_net.py:187-198, :124-134) — the product path; the two
+ * entry points above remain as the independent cross-check.  x [B,D,H,W,32] channels-last, w [1][32][3][3][3], bias [1] ->
+ * pred [B,H,W] = sum_d d * softmax_d(cost), optional cost_out [B,D,H,W] (the pre-softmax cost volume adapt.py:73 asks for)
+ * and optional fcs_out [B,H,W] = feature-contrast score of that cost (feature_contrast.py:12-23; same value as
+ * snb_feature_contrast(cost_out)).  A CTA streams the input rows of its output band once: each activation leaves HBM once,
+ * the tap sums never leave the chip; softmax / expectation / top-2 over D are warp-shuffle reductions.  D <= 64. */
+SNB_API int snb_conv3d_out_softargmin(const float* x, const float* w /*[1][32][3][3][3]*/, const float* bias /*[1]*/,
+                              float* cost_out, float* pred, float* fcs_out, int B, int D, int H, int W, void* stream);
 
 /* Second half of conv2d_out fused with the residual add + ReLU (stereo_net.py:121): out = relu(up + bias + sum taps).
  * bias / up may be NULL and relu = 0 turns it into a plain 3x3 tap gather (used by the refinement-head data gradient). */

@@ -1,0 +1,112 @@
+"""Round-2 kernel timings (CUDA events, L2 flushed before every launch unless stated): 32->32 convolutions in the fp16-split and
+3xTF32 operand formats, the fused head against the two-kernel head, the cost volume (cold single launches and back-to-back over
+rotating output buffers).  Usage: python scripts/time_r2.py [out.json]"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "adaptive-stereo-icra-2021_b200")); sys.path.insert(0, ROOT)
+import torch
+from stereonet_b200 import ops
+from bench import time_kernel
+dev = "cuda:0"
+torch.manual_seed(0)
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+stream = torch.cuda.current_stream()
+out = {}
+
+
+def warm_chain(fn, n=20):
+  """n back-to-back launches between two events (no flush: the way the kernel runs inside the captured forward)."""
+  for _ in range(3):
+    fn()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record(stream)
+  for _ in range(n):
+    fn()
+  b.record(stream)
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / n
+
+
+for shape, dil in [((1, 376, 1248, 32), 1), ((1, 376, 1248, 32), 4), ((1, 376, 1248, 32), 8), ((2, 47, 156, 32), 1)]:
+  x = torch.randn(shape, device=dev)
+  w = torch.randn(32, 32, 3, 3, device=dev) * 0.1
+  b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
+  g = ops.geom(shape, 3, dil=dil)
+  ref, _ = ops.conv_c32(x, ops.prep_conv_weights(w), g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True)
+  flops = 2 * 9 * 32 * 32 * x.numel() / 32
+  for fmt in ("h", 3, 1):
+    kw = dict(f16=True, passes=3) if fmt == "h" else dict(f16=False, passes=fmt)
+    wimg = ops.prep_conv_weights_tc(w, f16=fmt == "h")
+    fn = lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True, **kw)
+    y, _ = fn()
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    ms, _ = time_kernel(fn, 10, flush, stream)
+    wm = warm_chain(fn)
+    out[f"conv2d_{shape[1]}x{shape[2]}_dil{dil}_{fmt}"] = dict(cold_us=ms * 1e3, warm_us=wm * 1e3, tflops_cold=flops / ms / 1e9, rel_err=err)
+    print(f"conv2d {shape} dil{dil} fmt {fmt}: cold {ms*1e3:7.1f} us warm {wm*1e3:7.1f} us {flops/ms/1e9:6.1f} TFLOP/s rel err {err:.2e}", flush=True)
+
+for shape in [(1, 24, 47, 156, 32), (4, 24, 47, 156, 32)]:
+  x = torch.randn(shape, device=dev)
+  w = torch.randn(32, 32, 3, 3, 3, device=dev) * 0.05
+  b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
+  g = ops.geom(shape, 3)
+  ref, _ = ops.conv_c32(x, ops.prep_conv_weights(w), g, bias=b, scale=sc, shift=sh, lrelu=True)
+  flops = 2 * 27 * 32 * 32 * x.numel() / 32
+  for fmt in ("h", 3, 1):
+    kw = dict(f16=True, passes=3) if fmt == "h" else dict(f16=False, passes=fmt)
+    wimg = ops.prep_conv_weights_tc(w, f16=fmt == "h")
+    fn = lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, lrelu=True, **kw)
+    y, _ = fn()
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    ms, _ = time_kernel(fn, 10, flush, stream)
+    wm = warm_chain(fn)
+    out[f"conv3d_B{shape[0]}_{fmt}"] = dict(cold_us=ms * 1e3, warm_us=wm * 1e3, tflops_cold=flops / ms / 1e9, rel_err=err)
+    print(f"conv3d {shape} fmt {fmt}: cold {ms*1e3:7.1f} us warm {wm*1e3:7.1f} us {flops/ms/1e9:6.1f} TFLOP/s rel err {err:.2e}", flush=True)
+
+# ---- head: one fused kernel vs contraction + gather
+for B in (1, 4):
+  x = torch.randn(B, 24, 47, 156, 32, device=dev)
+  w = torch.randn(1, 32, 3, 3, 3, device=dev) * 0.5
+  bias = torch.randn(1, device=dev)
+  alg = 4 * B * 47 * 156 * (32 * 24 + 1 + 24 + 1)
+  f1 = lambda: ops.conv3d_out_softargmin(x, w, bias, want_cost=True, want_fcs=True)
+  def f2():
+    taps = ops.conv_c32_taps(x, w, 27)
+    return ops.tapsum_softargmin(taps, bias, True)
+  c1, p1, _ = f1(); c2, p2 = f2()
+  for name, fn in (("fused", f1), ("two_kernel", f2)):
+    ms, _ = time_kernel(fn, 20, flush, stream)
+    wm = warm_chain(fn)
+    out[f"head_{name}_B{B}"] = dict(cold_us=ms * 1e3, warm_us=wm * 1e3, gbs_cold=alg / ms / 1e6, gbs_warm=alg / wm / 1e6)
+    print(f"head {name} B={B}: cold {ms*1e3:6.1f} us ({alg/ms/1e6:6.0f} GB/s) warm {wm*1e3:6.1f} us ({alg/wm/1e6:6.0f} GB/s)  "
+          f"max|dcost| {(c1-c2).abs().max().item():.2e} max|dpred| {(p1-p2).abs().max().item():.2e}", flush=True)
+
+# ---- cost volume
+for B in (1, 8):
+  fl = torch.randn(B, 47, 156, 32, device=dev); fr = torch.randn(B, 47, 156, 32, device=dev)
+  alg = 4 * B * 32 * 47 * 156 * (2 + 24)
+  ms, _ = time_kernel(lambda: ops.cost_volume(fl, fr, 24), 20, flush, stream)
+  # back to back over rotating output buffers totalling > 2x L2 (every launch writes memory no earlier launch left in L2)
+  nbuf = max(2, (300 * 1024 * 1024) // (alg) + 1)
+  outs = [torch.empty((B, 24, 47, 156, 32), device=dev) for _ in range(nbuf)]
+  from stereonet_b200 import _cabi
+  import ctypes as C
+  def launch(i):
+    _cabi.check(_cabi.lib().snb_cost_volume_fwd(ops._p(fl), ops._p(fr), ops._p(outs[i % nbuf]), B, 24, 47, 156, ops._stream(fl)), "cv")
+  for i in range(nbuf):
+    launch(i)
+  torch.cuda.synchronize()
+  a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  n = 4 * nbuf
+  a.record(stream)
+  for i in range(n):
+    launch(i)
+  b2.record(stream)
+  torch.cuda.synchronize()
+  rot = a.elapsed_time(b2) / n
+  out[f"cost_volume_B{B}"] = dict(cold_us=ms * 1e3, rotating_us=rot * 1e3, gbs_cold=alg / ms / 1e6, gbs_rotating=alg / rot / 1e6, nbuf=nbuf)
+  print(f"cost volume B={B}: cold {ms*1e3:6.1f} us ({alg/ms/1e6:6.0f} GB/s)  rotating x{nbuf} {rot*1e3:6.1f} us ({alg/rot/1e6:6.0f} GB/s)", flush=True)
+
+if len(sys.argv) > 1:
+  json.dump(out, open(sys.argv[1], "w"), indent=1)

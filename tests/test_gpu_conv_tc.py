@@ -1,5 +1,6 @@
-"""GPU parity of the tcgen05 (tensor-core, TF32) 32->32 convolution against plain fp32 torch on the CPU.
-passes=3 (error-compensated 3xTF32) must be fp32-grade: 1e-5 of the output magnitude; passes=1 is plain TF32: 3e-3."""
+"""GPU parity of the tcgen05 (tensor-core) 32->32 convolution against plain fp32 torch on the CPU.  Operand formats:
+"h" = error-compensated fp16 split (kind::f16, the product path) and 3 = 3xTF32 must be fp32-grade: 1e-5 of the output
+magnitude; 1 = plain single-pass TF32: 3e-3."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -8,38 +9,58 @@ from stereonet_b200 import ops
 from test_gpu_kernels import cl, uncl, rnd, close, DEV
 
 pytestmark = pytest.mark.gpu
-TOL = {3: 1e-5, 1: 3e-3}
+TOL = {"h": 1e-5, 3: 1e-5, 1: 3e-3}
 
 
-@pytest.mark.parametrize("flat", [False, True])
-@pytest.mark.parametrize("passes", [3, 1])
+def kw(fmt):
+  return dict(f16=True, passes=3) if fmt == "h" else dict(f16=False, passes=fmt)
+
+
+def wimg(w, fmt, mode=0):
+  return ops.prep_conv_weights_tc(w.to(DEV), mode=mode, f16=fmt == "h")
+
+
+@pytest.mark.parametrize("fmt", ["h", 3, 1])
 @pytest.mark.parametrize("B,H,W,dil", [(1, 19, 45, 1), (2, 23, 37, 2), (1, 40, 50, 4), (1, 33, 41, 8), (1, 8, 128, 1),
                                        (1, 47, 156, 1), (1, 130, 260, 2), (2, 5, 300, 8), (1, 1, 7, 1)])
-def test_conv_tc_2d(B, H, W, dil, passes, flat):
-  """flat=False: vertical-walk 2-D kernel (snb_conv2d_c32_tc); flat=True: the flat-tiled kernel (snb_conv_c32_tc)."""
+def test_conv_tc_2d(B, H, W, dil, fmt):
+  """Vertical-walk 2-D kernel (snb_conv2d_c32_tc), TMA producer."""
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
   ref = F.conv2d(x, w, b, padding=dil, dilation=dil)
   g = ops.geom((B, H, W, 32), 3, dil=dil)
-  y, _ = ops.conv_c32_tc(cl(x), ops.prep_conv_weights_tc(w.to(DEV)), g, bias=b.to(DEV), passes=passes, flat=flat)
-  close(uncl(y), ref, TOL[passes], f"tc conv2d dil={dil} passes={passes} flat={flat}")
+  y, _ = ops.conv_c32_tc(cl(x), wimg(w, fmt), g, bias=b.to(DEV), **kw(fmt))
+  close(uncl(y), ref, TOL[fmt], f"tc conv2d dil={dil} fmt={fmt}")
 
 
+@pytest.mark.parametrize("wscale,xscale", [(1e-4, 1.0), (3.0, 1.0), (0.1, 1e-3), (0.1, 300.0), (0.02, 1e-6)])
+def test_conv_tc_f16_split_dynamic_range(wscale, xscale):
+  """The fp16 split must stay fp32-grade whatever the magnitude of weights (power-of-two scaling in the weight image) and
+  activations (the low part is pre-scaled by 2^11, so it never falls into the fp16 subnormals) — within |x| < 65504."""
+  x, w, b = rnd(1, 32, 21, 150, seed=1) * xscale, rnd(32, 32, 3, 3, seed=2, scale=wscale), rnd(32, seed=3) * (wscale * xscale)
+  x[0, :, 3, 5] = 0.0                                           # exact zeros and a few large outliers
+  x[0, 7, 10, 20] = 6.0e4 if xscale >= 1.0 else x[0, 7, 10, 20]
+  ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).float()
+  y, _ = ops.conv_c32_tc(cl(x), wimg(w, "h"), ops.geom((1, 21, 150, 32), 3), bias=b.to(DEV))
+  close(uncl(y), ref, 1e-5, f"f16 split wscale={wscale} xscale={xscale}")
+
+
+@pytest.mark.parametrize("fmt", ["h", 3])
 @pytest.mark.parametrize("B,H,W,dil", [(2, 23, 37, 2), (1, 47, 156, 1), (1, 64, 300, 4)])
-def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil):
+def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil, fmt):
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
   scale, shift = rnd(32, seed=4).abs() + 0.5, rnd(32, seed=5)
   z = F.conv2d(x, w, b, padding=dil, dilation=dil)
   ref = F.leaky_relu(z * scale.view(1, 32, 1, 1) + shift.view(1, 32, 1, 1), 0.2) + x
   xc = cl(x)
-  y, stats = ops.conv_c32_tc(xc, ops.prep_conv_weights_tc(w.to(DEV)), ops.geom((B, H, W, 32), 3, dil=dil), bias=b.to(DEV),
-                             scale=scale.to(DEV), shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True)
+  y, stats = ops.conv_c32_tc(xc, wimg(w, fmt), ops.geom((B, H, W, 32), 3, dil=dil), bias=b.to(DEV),
+                             scale=scale.to(DEV), shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True, **kw(fmt))
   close(uncl(y), ref, 1e-5, "conv2d tc epilogue")
   s = stats.double().sum(0).cpu()
   close(s[0], z.double().sum((0, 2, 3)), 1e-4, "sum z")
   close(s[1], (z.double() ** 2).sum((0, 2, 3)), 1e-4, "sum z^2")
 
 
-@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("passes", ["h", 3, 1])
 @pytest.mark.parametrize("B,D,H,W", [(1, 24, 9, 20), (2, 6, 7, 33), (1, 12, 17, 16), (1, 24, 47, 156)])
 def test_conv_tc_3d_full_epilogue(B, D, H, W, passes):
   x, w, b = rnd(B, 32, D, H, W, seed=1), rnd(32, 32, 3, 3, 3, seed=2, scale=0.05), rnd(32, seed=3)
@@ -48,8 +69,8 @@ def test_conv_tc_3d_full_epilogue(B, D, H, W, passes):
   ref = F.leaky_relu(z * scale.view(1, 32, 1, 1, 1) + shift.view(1, 32, 1, 1, 1), 0.2) + x
   g = ops.geom((B, D, H, W, 32), 3)
   xc = cl(x)
-  y, stats = ops.conv_c32_tc(xc, ops.prep_conv_weights_tc(w.to(DEV)), g, bias=b.to(DEV), scale=scale.to(DEV),
-                             shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True, passes=passes)
+  y, stats = ops.conv_c32_tc(xc, wimg(w, passes), g, bias=b.to(DEV), scale=scale.to(DEV),
+                             shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True, **kw(passes))
   close(uncl(y), ref, TOL[passes], f"tc conv3d passes={passes}")
   s = stats.double().sum(0).cpu()
   close(s[0], z.double().sum((0, 2, 3, 4)), 10 * TOL[passes], "sum z")
@@ -60,20 +81,21 @@ def test_conv_tc_kitti_refinement_size():
   x, w, b = rnd(1, 32, 376, 1248, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
   for dil in (1, 8):
     ref = F.conv2d(x, w, b, padding=dil, dilation=dil)
-    y, _ = ops.conv_c32_tc(cl(x), ops.prep_conv_weights_tc(w.to(DEV)), ops.geom((1, 376, 1248, 32), 3, dil=dil), bias=b.to(DEV))
+    y, _ = ops.conv_c32_tc(cl(x), wimg(w, "h"), ops.geom((1, 376, 1248, 32), 3, dil=dil), bias=b.to(DEV))
     close(uncl(y), ref, 1e-5, f"tc conv2d 376x1248 dil={dil}")
 
 
-def test_conv_tc_dgrad_weights():
+@pytest.mark.parametrize("fmt", ["h", 3])
+def test_conv_tc_dgrad_weights(fmt):
   x = rnd(1, 32, 14, 27, seed=1).requires_grad_()
   w = rnd(32, 32, 3, 3, seed=2, scale=0.1)
   gy = rnd(1, 32, 14, 27, seed=3)
   F.conv2d(x, w, None, padding=2, dilation=2).backward(gy)
-  dx, _ = ops.conv_c32_tc(cl(gy), ops.prep_conv_weights_tc(w.to(DEV), mode=1), ops.geom((1, 14, 27, 32), 3, dil=2))
+  dx, _ = ops.conv_c32_tc(cl(gy), wimg(w, fmt, mode=1), ops.geom((1, 14, 27, 32), 3, dil=2), **kw(fmt))
   close(uncl(dx), x.grad, 1e-5, "tc dgrad 2d")
   x = rnd(1, 32, 6, 9, 11, seed=1).requires_grad_()
   w = rnd(32, 32, 3, 3, 3, seed=2, scale=0.05)
   gy = rnd(1, 32, 6, 9, 11, seed=3)
   F.conv3d(x, w, None, padding=1).backward(gy)
-  dx, _ = ops.conv_c32_tc(cl(gy), ops.prep_conv_weights_tc(w.to(DEV), mode=1), ops.geom((1, 6, 9, 11, 32), 3))
+  dx, _ = ops.conv_c32_tc(cl(gy), wimg(w, fmt, mode=1), ops.geom((1, 6, 9, 11, 32), 3), **kw(fmt))
   close(uncl(dx), x.grad, 1e-5, "tc dgrad 3d")

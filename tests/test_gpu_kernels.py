@@ -141,6 +141,25 @@ def test_conv3d_out_softargmin(B, D, H, W, sharp):
   assert torch.equal(pred, pred2)
 
 
+@pytest.mark.parametrize("B,D,H,W,sharp", [(1, 24, 9, 20, 1.0), (2, 12, 7, 33, 30.0), (1, 6, 5, 70, 30.0), (1, 24, 47, 156, 10.0),
+                                           (1, 24, 40, 120, 10.0), (1, 12, 20, 60, 20.0), (1, 24, 1, 9, 10.0), (1, 24, 2, 3, 10.0),
+                                           (1, 48, 11, 50, 5.0), (3, 24, 68, 120, 10.0), (1, 24, 5, 8, 30.0)])
+def test_conv3d_out_softargmin_fused(B, D, H, W, sharp):
+  """The ONE-kernel head (snb_conv3d_out_softargmin: conv3d_alone + softmax + expectation + cost + FCS, stereo_net.py:187-198)
+  against fp32 torch / the oracle's soft-argmin / the sort-based feature-contrast score (feature_contrast.py:12-23)."""
+  x, w, b = rnd(B, 32, D, H, W, seed=1), rnd(1, 32, 3, 3, 3, seed=2, scale=0.05 * sharp), rnd(1, seed=3)
+  cost_ref = F.conv3d(x, w, b, padding=1).squeeze(1)
+  pred_ref = O.soft_argmin(cost_ref)
+  s = torch.sort(cost_ref, dim=1, descending=True)[0]
+  fcs_ref = s[:, 0] - s[:, 2:].mean(dim=1)
+  cost, pred, fcs = ops.conv3d_out_softargmin(cl(x), w.to(DEV), b.to(DEV), want_cost=True, want_fcs=True)
+  close(cost.cpu(), cost_ref, 1e-5, "cost")
+  assert (pred.cpu() - pred_ref).abs().max().item() <= 2e-4, "soft-argmin (coarse px)"
+  close(fcs.cpu(), fcs_ref, 2e-5, "feature contrast")
+  _, pred2, none = ops.conv3d_out_softargmin(cl(x), w.to(DEV), b.to(DEV), want_cost=False)
+  assert none is None and torch.equal(pred, pred2)
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 20, 33), (2, 64, 300)])
 def test_refine_out(B, H, W):
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(1, 32, 3, 3, seed=2, scale=0.1), rnd(1, seed=3)

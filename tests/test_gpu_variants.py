@@ -1,7 +1,8 @@
 """The A/B switches of the library select between kernels of this library (never a fallback).  Each variant must give the
-same results as the default path: the CUDA-core cross-check kernels (SNB200_SMALL_CONV=ffma, SNB200_TAPS=ffma), the
-experimental cta_group::2 3-D filter kernel (SNB200_CONV3D=pair) and launches without programmatic dependent launch
-(SNB200_PDL=0).  The switches are read once per process, so every variant runs in its own interpreter."""
+same results as the default path: the CUDA-core cross-check kernels (SNB200_SMALL_CONV=ffma), launches without programmatic
+dependent launch (SNB200_PDL=0) and — selected by the test itself through fused.set_conv_backend, not the environment — the
+3xTF32 operand split and the fp32 FFMA kernel instead of the fp16 split of the 32->32 convolutions.  The switches are read once
+per process, so every variant runs in its own interpreter."""
 import os
 import subprocess
 import sys
@@ -29,6 +30,10 @@ for p in (ROOT, os.path.join(ROOT, "adaptive-stereo-icra-2021_b200"), os.path.jo
 import stereonet_oracle as O
 import stereonet_b200 as S
 from stereonet_b200 import ops
+from stereonet_b200.autograd import fused
+if os.environ.get("SNB_TEST_BACKEND"):
+  fused.set_conv_backend(os.environ["SNB_TEST_BACKEND"])
+h16 = fused.CONV_BACKEND == "h3"
 dev = "cuda:0"
 k = 3
 f = S.FeatureExtractorNetwork(k).to(dev).eval(); s = S.StereoNet(k, 1, 0).to(dev).eval()
@@ -39,7 +44,7 @@ with torch.no_grad():
   out = s(l, f(l), f(r), "l", output_cost_volume=True)
   x3 = torch.randn(1, 6, 9, 150, 32, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
   w3 = torch.randn(32, 32, 3, 3, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) * 0.05
-  y3, st3 = ops.conv_c32_tc(x3, ops.prep_conv_weights_tc(w3), ops.geom(tuple(x3.shape), 3), lrelu=True, want_stats=True)
+  y3, st3 = ops.conv_c32_tc(x3, ops.prep_conv_weights_tc(w3, f16=h16), ops.geom(tuple(x3.shape), 3), lrelu=True, want_stats=True, f16=h16)
 torch.cuda.synchronize()
 np.savez(sys.argv[2], disp=out["pred_disp_l/0"].cpu().numpy(), coarse=out["pred_disp_l/3"].cpu().numpy(),
          cost=out["cost_volume_l/3"].cpu().numpy(), y3=y3.cpu().numpy(), st3=st3.double().sum(0).cpu().numpy())
@@ -59,8 +64,8 @@ def default_run():
   return _run({})
 
 
-@pytest.mark.parametrize("env", [{"SNB200_SMALL_CONV": "ffma"}, {"SNB200_TAPS": "ffma"}, {"SNB200_CONV3D": "pair"}, {"SNB200_PDL": "0"},
-                                 {"SNB200_SMALL_CONV": "ffma", "SNB200_TAPS": "ffma", "SNB200_PDL": "0"}])
+@pytest.mark.parametrize("env", [{"SNB200_SMALL_CONV": "ffma"}, {"SNB200_PDL": "0"}, {"SNB_TEST_BACKEND": "tc3"},
+                                 {"SNB_TEST_BACKEND": "ffma", "SNB200_SMALL_CONV": "ffma", "SNB200_PDL": "0"}])
 def test_variant_matches_default(default_run, env):
   got = _run(env)
   exact = env == {"SNB200_PDL": "0"}                     # same kernels, only the launch attribute differs
@@ -88,6 +93,7 @@ def test_weight_prep_batch_matches_per_layer_prep():
     if key[0] == "wtc":
       ref = ops.prep_conv_weights_tc(conv.weight, mode)
       assert torch.equal(views[0], ref), (key, tuple(conv.weight.shape))
+      assert float(views[0][ops.conv_weights_tc_floats(1) // 6 + 16]) in [2.0 ** -e for e in range(-20, 41)]    # the 2^-s slot
       n3x3 += 1
     else:
       w = conv.weight.detach()
@@ -96,7 +102,13 @@ def test_weight_prep_batch_matches_per_layer_prep():
         for b in (0, 1):
           sub = w[:, :, a::2, b::2]
           sub = torch.nn.functional.pad(sub, (0, 3 - sub.shape[3], 0, 3 - sub.shape[2])).contiguous()
-          assert torch.equal(views[i], ops.prep_conv_weights_tc(sub, mode)), (key, a, b)
+          # the batched prep scales by max|w| of the whole 5x5 kernel, the per-layer prep by max|sub-kernel|: both are exact
+          # power-of-two scalings, so the images may differ but the convolutions they drive must not
+          xs = torch.randn(1, 9, 40, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(a * 2 + b))
+          g3 = ops.geom(tuple(xs.shape), 3)
+          y_b, _ = ops.conv_c32_tc(xs, views[i], g3)
+          y_l, _ = ops.conv_c32_tc(xs, ops.prep_conv_weights_tc(sub, mode), g3)
+          assert float((y_b - y_l).abs().max()) <= 2e-6 * max(1.0, float(y_l.abs().max())), (key, a, b)
           i += 1
       n5x5 += 1
     # the per-module cache now serves these images
