@@ -220,8 +220,9 @@ conv2d_c32_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params2 p) 
       float4 v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(st + ((c ^ (m & 7)) << 4));
+      const uint32_t dep = xor_all(v);                     // every lane's loads have RETURNED before the slot is released
       __syncwarp();
-      if (lane == 0) mbar_arrive(&rempty[sr]);             // raw window consumed (values are in registers)
+      if (lane == 0) mbar_arrive_after(&rempty[sr], dep);   // (the scoreboard is per warp register: lane 0 waits for the whole warp-wide load)
       T2WAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
       tc_fence_after();
       const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * ACOLS;

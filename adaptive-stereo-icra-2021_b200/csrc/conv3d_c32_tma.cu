@@ -267,8 +267,9 @@ conv3d_c32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params3 p)
         float4 v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (m & 7)) << 4));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rempty[s]);            // raw window consumed (values are in registers)
+      const uint32_t dep = xor_all(v);                     // every lane's loads have RETURNED before the slot is released
+      __syncwarp();
+      if (lane == 0) mbar_arrive_after(&rempty[s], dep);   // (the scoreboard is per warp register: lane 0 waits for the whole warp-wide load)
         T3WAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + TA_BASE + aslot * ACOLS;

@@ -200,6 +200,22 @@ __device__ __forceinline__ void split_f16(const float4 (&v)[8], uint32_t (&hl)[3
   }
 }
 
+// mbarrier.arrive that is data-dependent on `dep`: the arrive cannot ISSUE before the instructions that produced `dep` have
+// their operands, i.e. before the shared-memory loads feeding them have returned.  A consumer that releases a TMA-filled smem
+// slot right after issuing its LDS instructions (values "in registers" only once they arrive) lets the producer's next TMA
+// write race the loads still in flight — seen as rare, large errors in back-to-back launches of the 2-D kernel.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0x7fc12345;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+               "@!p mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" :: "r"(smem_u32(bar)), "r"(dep) : "memory");
+}
+__device__ __forceinline__ uint32_t xor_all(const float4 (&v)[8]) {
+  uint32_t x = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    x ^= __float_as_uint(v[c].x) ^ __float_as_uint(v[c].y) ^ __float_as_uint(v[c].z) ^ __float_as_uint(v[c].w);
+  return x;
+}
+
 // M128 N32 K8 variant (small-Cin im2col convolutions, 32->1 tap contractions), A from TMEM; call inside one elected region
 constexpr uint32_t IDESC_N32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 

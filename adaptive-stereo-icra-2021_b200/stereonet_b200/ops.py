@@ -143,15 +143,21 @@ def prep_conv_weights_tc_batch(table, n):
 
 
 def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
-                flat=False, out=None, legacy3d=False, f16=True):
+                flat=False, out=None, legacy3d=False, f16=True, walk96=False):
   """Tensor-core (tcgen05) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.  f16 (default):
   error-compensated fp16 operand split (kind::f16), else TF32 (passes = 3: 3xTF32, 1: plain); `wimg` must be in the same format.
-  2-D inputs use the vertical-walk kernel (snb_conv2d_c32_tc) unless flat=True; 3-D inputs the TMA kernel."""
+  2-D inputs: f16 -> snb_conv2d_c32_ws (the product kernel; walk96=True selects the older N = 96 walk kernel in the fp16 format),
+  TF32 -> snb_conv2d_c32_tc, flat=True -> the flat-tiled loader-warp kernel; 3-D inputs the TMA kernel."""
   three_d = x.dim() == 5
   _req(x, "x"); _req(wimg, "wimg")
   lib = _cabi.lib()
   use2d = (not three_d) and (not flat)
+  use_ws = use2d and f16 and not walk96               # 2-D product kernel: shifted operand copies, N = 32 (conv2d_c32_ws.cu)
+  if use_ws and want_stats and (scale is not None or lrelu or residual is not None):
+    raise RuntimeError("stereonet_b200: snb_conv2d_c32_ws takes BN statistics of the plain conv + bias output only")
   fn, fn_tiles = (lib.snb_conv2d_c32_tc, lib.snb_conv2d_c32_tc_num_tiles) if use2d else (lib.snb_conv_c32_tc, lib.snb_conv_c32_tc_num_tiles)
+  if use_ws:
+    fn_tiles = lib.snb_conv2d_c32_ws_num_tiles
   y = out if out is not None else torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
   if out is not None:
     _req(out, "out")
@@ -172,7 +178,10 @@ def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lr
     passes |= CONV_F16
   if three_d and legacy3d:
     passes |= 0x400                      # diagnostics: 3-D flat-tiled kernel with loader warps instead of the TMA kernel
-  check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
+  if use_ws:
+    check(lib.snb_conv2d_c32_ws(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), _stream(x)), "snb_conv2d_c32_ws")
+  else:
+    check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
   _count()
   return y, stats
 

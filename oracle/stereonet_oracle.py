@@ -218,6 +218,40 @@ def epe(pred, gt):
   return torch.abs(pred - gt)[gt > 0].mean()
 
 
+def khamis_robust_loss(pred_disp: torch.Tensor, gt_disp: torch.Tensor) -> torch.Tensor:
+  """khamis_robust_loss loss_functions.py:6-15 (the experience-replay term of adapt.py:343-345):
+  sum over gt > 0 of sqrt((gt - pred)^2 + 4) / 2 - 1, divided by max(#valid, 1)."""
+  mask = (gt_disp > 0).detach()
+  num_valid = max(mask.sum(), 1)
+  return torch.sum(torch.sqrt(torch.pow(gt_disp[mask] - pred_disp[mask], 2) + 4) / 2 - 1) / num_valid
+
+
+D1_THRESHOLDS = (2, 3, 4, 5)          # train.py:106
+
+
+def eval_metrics(pred_disp: torch.Tensor, gt_disp: torch.Tensor, cost: Optional[torch.Tensor] = None) -> Dict[str, float]:
+  """The per-batch body of train.evaluate, train.py:98-110: EPE over gt > 0, D1-all at 2/3/4/5 px, mean FCS."""
+  valid = gt_disp > 0
+  err = torch.abs(pred_disp - gt_disp)
+  m = {"EPE": err[valid].mean().item()}
+  for t in D1_THRESHOLDS:
+    m[f"D1_all_{t}px"] = ((valid * (err > t)).sum() / float(valid.sum())).item()
+  if cost is not None:
+    m["FCS"] = feature_contrast_mean(cost).mean().item()
+  return m
+
+
+def validate_ovs(fsd, ssd, pairs, k: int, input_scale: int = 0, maxdisp: int = 192):
+  """StateMachine.validate adapt.py:122-142: eval mode, no grad, ONE pair at a time, single-image Monodepth loss.
+  `pairs` = iterable of (left [1,3,H,W], right [1,3,H,W]).  Returns the list of per-pair losses."""
+  out = []
+  with torch.no_grad():
+    for left, right in pairs:
+      o = predict_disparity_left(fsd, ssd, left, right, k, input_scale, maxdisp, training=False)
+      out.append(monodepth_single_loss(left, right, o[f"pred_disp_l/{input_scale}"]).item())
+  return out
+
+
 # --------------------------------------------------------------------------------------
 # deterministic weights / inputs shared by golden generation, tests and bench
 # --------------------------------------------------------------------------------------
@@ -320,13 +354,20 @@ def unused_param(key: str) -> bool:
   return ".conv2." in key
 
 
-def adapt_step(fsd, ssd, left, right, k, adam_state, lr=5e-5, input_scale=0, maxdisp=192, clip=True):
+def adapt_step(fsd, ssd, left, right, k, adam_state, lr=5e-5, input_scale=0, maxdisp=192, clip=True, replay=None,
+               er_loss_weight=0.05):
   """One gradient update of the adaptation loop: adapt.py:313-314 (train mode), :328-337 (forward + loss),
   :381-394 (zero_grad, backward, clip_grad_norm_ on stereo_net only, Adam step; params = stereo_net then
   feature_net, :208-210).  Adam restated from torch.optim.Adam defaults (betas .9/.999, eps 1e-8).
+  `replay` = (left, right, gt_disp) adds the experience-replay term of the ER / VS+ER modes, adapt.py:339-349,386-388: a SECOND
+  full train-mode pass on the replay sample (so BatchNorm running statistics are updated twice) and
+  loss += er_loss_weight * khamis_robust_loss(pred_er, gt_er).
   `fsd`/`ssd` hold leaf tensors with requires_grad; updated in place.  Returns (loss, outputs, grads)."""
   outputs = predict_disparity_left(fsd, ssd, left, right, k, input_scale, maxdisp, training=True)
   loss = monodepth_single_loss(left, right, outputs[f"pred_disp_l/{input_scale}"])
+  if replay is not None:
+    out_er = predict_disparity_left(fsd, ssd, replay[0], replay[1], k, input_scale, maxdisp, training=True)
+    loss = loss + er_loss_weight * khamis_robust_loss(out_er[f"pred_disp_l/{input_scale}"], replay[2])
   params = [(("s", n), p) for n, p in ssd.items() if p.requires_grad and not unused_param(n)] + \
            [(("f", n), p) for n, p in fsd.items() if p.requires_grad and not unused_param(n)]
   grads = torch.autograd.grad(loss, [p for _, p in params], allow_unused=True)

@@ -111,7 +111,7 @@ def test_head_backward():
   gp, gc = rnd(B, H, W, seed=2), rnd(B, D, H, W, seed=3) * 0.1
   ((pred * gp).sum() + (cost * gc).sum()).backward()
   xg = cl(x.detach()).requires_grad_()
-  cg, pg = Fn.Conv3dOutSoftargmin.apply(xg, gconv.weight, gconv.bias)
+  cg, pg, _fcs = Fn.Conv3dOutSoftargmin.apply(xg, gconv.weight, gconv.bias)
   ((pg * gp.to(DEV)).sum() + (cg * gc.to(DEV)).sum()).backward()
   close(uncl(xg.grad), x.grad, 3e-5, "dx")
   close(gconv.weight.grad.cpu(), conv.weight.grad, 3e-5, "dw")

@@ -9,20 +9,25 @@ from stereonet_b200 import ops
 from test_gpu_kernels import cl, uncl, rnd, close, DEV
 
 pytestmark = pytest.mark.gpu
-TOL = {"h": 1e-5, 3: 1e-5, 1: 3e-3}
+TOL = {"h": 1e-5, "h96": 1e-5, 3: 1e-5, 1: 3e-3}
 
 
 def kw(fmt):
-  return dict(f16=True, passes=3) if fmt == "h" else dict(f16=False, passes=fmt)
+  """"h": the product kernels (2-D: shifted-operand N = 32 kernel, 3-D: TMA kernel) in the fp16 format; "h96": the 2-D N = 96
+  walk kernel in the fp16 format; 3 / 1: TF32 with that many passes."""
+  if fmt in ("h", "h96"):
+    return dict(f16=True, passes=3, walk96=fmt == "h96")
+  return dict(f16=False, passes=fmt)
 
 
 def wimg(w, fmt, mode=0):
-  return ops.prep_conv_weights_tc(w.to(DEV), mode=mode, f16=fmt == "h")
+  return ops.prep_conv_weights_tc(w.to(DEV), mode=mode, f16=fmt in ("h", "h96"))
 
 
-@pytest.mark.parametrize("fmt", ["h", 3, 1])
+@pytest.mark.parametrize("fmt", ["h", "h96", 3, 1])
 @pytest.mark.parametrize("B,H,W,dil", [(1, 19, 45, 1), (2, 23, 37, 2), (1, 40, 50, 4), (1, 33, 41, 8), (1, 8, 128, 1),
-                                       (1, 47, 156, 1), (1, 130, 260, 2), (2, 5, 300, 8), (1, 1, 7, 1)])
+                                       (1, 47, 156, 1), (1, 130, 260, 2), (2, 5, 300, 8), (1, 1, 7, 1), (1, 9, 129, 1),
+                                       (1, 70, 256, 16), (3, 3, 128, 2)])
 def test_conv_tc_2d(B, H, W, dil, fmt):
   """Vertical-walk 2-D kernel (snb_conv2d_c32_tc), TMA producer."""
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
@@ -44,7 +49,7 @@ def test_conv_tc_f16_split_dynamic_range(wscale, xscale):
   close(uncl(y), ref, 1e-5, f"f16 split wscale={wscale} xscale={xscale}")
 
 
-@pytest.mark.parametrize("fmt", ["h", 3])
+@pytest.mark.parametrize("fmt", ["h", "h96", 3])
 @pytest.mark.parametrize("B,H,W,dil", [(2, 23, 37, 2), (1, 47, 156, 1), (1, 64, 300, 4)])
 def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil, fmt):
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
@@ -52,6 +57,21 @@ def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil, fmt):
   z = F.conv2d(x, w, b, padding=dil, dilation=dil)
   ref = F.leaky_relu(z * scale.view(1, 32, 1, 1) + shift.view(1, 32, 1, 1), 0.2) + x
   xc = cl(x)
+  if fmt == "h":      # snb_conv2d_c32_ws: statistics of conv + bias only (the train-mode call), the full epilogue separately
+    g = ops.geom((B, H, W, 32), 3, dil=dil)
+    zc, stats = ops.conv_c32_tc(xc, wimg(w, fmt), g, bias=b.to(DEV), want_stats=True)
+    close(uncl(zc), z, 1e-5, "conv2d ws z")
+    s = stats.double().sum(0).cpu()
+    close(s[0], z.double().sum((0, 2, 3)), 1e-4, "sum z")
+    close(s[1], (z.double() ** 2).sum((0, 2, 3)), 1e-4, "sum z^2")
+    y, _ = ops.conv_c32_tc(xc, wimg(w, fmt), g, bias=b.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV), residual=xc, lrelu=True)
+    close(uncl(y), ref, 1e-5, "conv2d ws epilogue, residual = input (on-chip)")
+    other = rnd(B, 32, H, W, seed=9)
+    y2, _ = ops.conv_c32_tc(xc, wimg(w, fmt), g, bias=b.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV), residual=cl(other), lrelu=True)
+    close(uncl(y2), ref - x + other, 1e-5, "conv2d ws epilogue, residual from global memory")
+    y3, _ = ops.conv_c32_tc(xc, wimg(w, fmt), g)
+    close(uncl(y3), z - b.view(1, 32, 1, 1), 1e-5, "conv2d ws, no epilogue")
+    return
   y, stats = ops.conv_c32_tc(xc, wimg(w, fmt), ops.geom((B, H, W, 32), 3, dil=dil), bias=b.to(DEV),
                              scale=scale.to(DEV), shift=shift.to(DEV), residual=xc, lrelu=True, want_stats=True, **kw(fmt))
   close(uncl(y), ref, 1e-5, "conv2d tc epilogue")
