@@ -17,8 +17,9 @@
 //               memory in the coalesced pass.
 // Every tile yields 128 valid outputs (the halo is in the raw window, not in the tile): 3 % fewer tiles than the N = 96 kernel
 // at dilation 1, 14 % fewer at dilation 8.
-// Warps: 0 producer, 1 MMA issuer (+ resident weight images), 2-9 converters (two per TMEM lane quadrant, alternating windows),
-// 10-13 epilogue.  smem: 4 x 20 KB raw ring | 72 KB weights | 2 x 16 KB output staging.
+// Warps: 0 producer, 1 MMA issuer (+ resident weight images), 2-9 converters (two groups of four, alternating windows), 10-17
+// epilogue (two groups of four, alternating tiles; a staged tile leaves through one TMA tile store).
+// smem: 4 x 20 KB raw ring | 4 x 16 KB staging | 72 KB weights.
 // TMEM: 4 accumulators x 32 | 3 residual slots x 32 | 3 A slots x 96 (= 3 kw x (xh 16 | xl' 16)).
 #include <cuda.h>
 #include "tc_common.cuh"
@@ -31,9 +32,10 @@ constexpr int NR = 4;                                    // raw window ring dept
 constexpr int RAW_BYTES = 160 * 128;                     // up to 128 + 2*16 pixel rows of 128 B
 constexpr int BWIN_BYTES = 2 * B_BYTES;                  // one kh window: image P [wh | wl] + image Q [2^-11 wh | -], 96 rows each
 constexpr int STG_BYTES = 128 * 128;                     // one output tile, fp32
-constexpr int SMEM_BYTES = NR * RAW_BYTES + 3 * BWIN_BYTES + 2 * STG_BYTES + 4096 + 1024;
-constexpr int NTHREADS_WS = 14 * 32;
-constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;
+// raw ring | weights | two staging tiles per epilogue group | barriers, params
+constexpr int SMEM_BYTES = NR * RAW_BYTES + 3 * BWIN_BYTES + 4 * STG_BYTES + 4096 + 1024;
+constexpr int NTHREADS_WS = 18 * 32;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 10;             // 2 converter groups x 4 warps (alternating windows), 2 epilogue groups x 4 warps (alternating tiles)
 constexpr int NACCW = 4, NRES = 3, NA = 3;
 constexpr int ACC_BASE = 0, RES_BASE = NACCW * 32, A_BASE = RES_BASE + NRES * 32, A_COLS = 96;
 static_assert(A_BASE + NA * A_COLS <= 512, "TMEM budget");
@@ -71,7 +73,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void epi_bar_ws() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;\n" :: "r"(id) : "memory"); }     // 4 warps of one group
 
 // M128 N32 K16 kind::f16 (A from TMEM)
 constexpr uint32_t IDESC_F16_N32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
@@ -85,13 +87,13 @@ __device__ __forceinline__ void mma_f16_n32(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 
 __global__ void __launch_bounds__(NTHREADS_WS, 1)
-conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const Params p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
-  unsigned char* sB = base + NR * RAW_BYTES;
-  unsigned char* sStg = sB + 3 * BWIN_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * STG_BYTES);
+  unsigned char* sStg = base + NR * RAW_BYTES;              // [2 epilogue groups][2] output tiles (1024-B aligned: TMA store source)
+  unsigned char* sB = sStg + 4 * STG_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 3 * BWIN_BYTES);
   uint64_t* rfull = bars;                // [NR]    TMA (raw window) -> converters
   uint64_t* rempty = rfull + NR;         // [NR]    converters -> producer
   uint64_t* afull = rempty + NR;         // [NA]    converters -> MMA (A slot in TMEM)
@@ -101,8 +103,8 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* rsempty = tempty + NACCW;    // [NRES]  epilogue -> converters (residual slot drained)
   uint64_t* wbar = rsempty + NRES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-  float* sPar = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);    // [96] bias | scale | shift (16-B aligned)
-  float* sRed = sPar + 96;                                  // [4 warps][64]
+  float* sPar = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);    // [64] alpha | beta (16-B aligned)
+  float* sRed = sPar + 96;                                  // [2 groups][4 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int RW = 128 + 2 * p.dil;                           // rows of a raw window
@@ -111,7 +113,7 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     if (lane == 0) {
       for (int i = 0; i < NR; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 4); }
       for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
-      for (int i = 0; i < NACCW; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+      for (int i = 0; i < NACCW; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }      // a tile is drained by ONE epilogue group
       for (int i = 0; i < NRES; ++i) mbar_init(&rsempty[i], 4);
       mbar_init(wbar, 1);
       mbar_fence_init();
@@ -126,10 +128,13 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch();                                    // only after this CTA owns its TMEM columns
   pdl_wait();                                      // everything above touched no global memory
-  if (tid >= EPI_WARP0 * 32 && tid < EPI_WARP0 * 32 + 96) {
-    const int i = tid - EPI_WARP0 * 32, c = i & 31, which = i >> 5;
+  if (tid >= EPI_WARP0 * 32 && tid < EPI_WARP0 * 32 + 32) {
+    // y = lrelu(scale * (acc * 2^-s + bias) + shift) = lrelu(acc * alpha + beta): two broadcast reads per channel quad instead of three
+    const int c = tid - EPI_WARP0 * 32;
     const snb_conv_epilogue& e = p.e;
-    sPar[i] = which == 0 ? (e.bias ? e.bias[c] : 0.f) : which == 1 ? (e.scale ? e.scale[c] : 1.f) : (e.scale ? e.shift[c] : 0.f);
+    const float bias = e.bias ? e.bias[c] : 0.f, sc = e.scale ? e.scale[c] : 1.f, sh = e.scale ? e.shift[c] : 0.f;
+    sPar[c] = sc * __ldg(p.wimg + WIMG_SCALE_SLOT);
+    sPar[32 + c] = fmaf(sc, bias, sh);
   }
 
   if (warp == 0) {
@@ -163,7 +168,7 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     __syncwarp();
     tc::mbar_wait_spin(wbar, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NR * RAW_BYTES;
+    const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NR * RAW_BYTES + 4 * STG_BYTES;
     long long tile_base = 0;
     uint32_t win_count = 0;
     long long t_full = 0, t_tempty = 0; const long long t_mbegin = clock64();
@@ -218,9 +223,12 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[2] = t_full; dd[3] = t_tempty; dd[4] = clock64() - t_mbegin; }
     __syncwarp();
   } else if (warp < EPI_WARP0) {
-    // =============================================================== converters (TMEM lane quadrant = warp % 4, thread = output pixel)
+    // =============================================================== converters: 2 groups of 4 warps, alternating windows (TMEM lane
+    // quadrant = warp % 4, thread = output pixel m).  For kw = 0,1,2: row m + kw*dil of the raw window -> (xh | xl') -> A slot [kw].
+    // The kernel is bound by shared-memory wavefronts (B-operand fetch 432 + TMA write 144 + these reads 384 + epilogue per tile):
+    // converting every row once into a packed smem copy was measured and costs 800 wavefronts instead of 384.
     const int quad = warp & 3;
-    const uint32_t mine = (uint32_t)(warp - CONV_WARP0) >> 2;      // this warp converts the windows with cnt % 2 == mine
+    const uint32_t grp = (uint32_t)(warp - CONV_WARP0) >> 2;
     const int m = quad * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     long long w_rf = 0, w_ae = 0, w_rs = 0; const long long t0 = clock64();
@@ -230,7 +238,7 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       const Strip s = decode_strip(p, sid);
       if (s.ntiles == 0) continue;
       for (int u = 0; u < s.ntiles + 2; ++u, ++cnt) {
-        if ((cnt & 1) != mine) continue;
+        if ((cnt & 1) != grp) continue;
         const uint32_t sr = cnt % NR, aslot = cnt % NA;
         WSWAIT(w_rf, tc::mbar_wait(&rfull[sr], (cnt / NR) & 1));
         const unsigned char* rawp = base + sr * RAW_BYTES;
@@ -281,49 +289,64 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     }
     if (p.dbg && warp == CONV_WARP0 && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[11] = w_rf; dd[12] = w_ae; dd[13] = clock64() - t0; dd[14] = w_rs; }
   } else {
-    // =============================================================== epilogue (4 warps; TMEM lane quadrant = warp % 4, thread = pixel)
-    const int ew = warp - EPI_WARP0;
+    // =============================================================== epilogue: 2 groups of 4 warps, alternating tiles (TMEM lane
+    // quadrant = warp % 4, thread = pixel).  One tile per group at a time: its latency chain (tcgen05.ld -> pointwise -> smem
+    // transpose -> coalesced stores) is ~2500 cycles, more than the MMAs of a tile.
+    const int egrp = (warp - EPI_WARP0) >> 2;
+    const int ew = (warp - EPI_WARP0) & 3;
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
-    const int et = tid - EPI_WARP0 * 32;
+    const int et = (tid - EPI_WARP0 * 32) & 127;
     const int chunk = et & 7, rg = et >> 3;          // coalesced pass: rows rg + 16*i, 16-B chunk `chunk`
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const snb_conv_epilogue& e = p.e;
     const bool has_stats = e.stats != nullptr;
     const float slope = e.lrelu ? SNB_LRELU_SLOPE : 1.f;
-    const float winv = __ldg(p.wimg + WIMG_SCALE_SLOT);       // 2^-s of the weight image (power of two: exact)
-    epi_bar_ws();                                             // sPar is visible
+    float* red = sRed + egrp * 256;
+    // Output paths.  res_mode 0 / 1: the staged tile (SWIZZLE_128B image of 128 pixels x 32 ch) leaves through ONE TMA tile store
+    // (columns >= W are clipped by the tensor map) — no read-back pass.  res_mode 2 (a residual that is not the input): the coalesced
+    // pass below adds it from global memory and stores.  Train-mode statistics are a read-only column pass over the staged tile.
+    const bool tma_out = p.res_mode != 2;
+    uint32_t ntile_g = 0;                                     // tiles this group has staged so far (staging buffer = parity)
+    const int bar_id = 4 + egrp;
+    asm volatile("bar.sync 6, 256;\n" ::: "memory");          // sPar (written by the first epilogue warp) is visible
     long long tcount = 0;
-    long long t_tfull = 0, t_px = 0, t_out = 0, t_bar = 0; const long long t_ebegin = clock64();
+    long long t_tfull = 0, t_px = 0, t_out = 0, t_bar = 0, t_ld = 0, t_bar2 = 0; const long long t_ebegin = clock64();
     for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
       const Strip s = decode_strip(p, sid);
       const int x0 = s.cb * 128;
       for (int j = 0; j < s.ntiles; ++j, ++tcount) {
+        if ((int)(tcount & 1) != egrp) continue;
         const int slot = (int)(tcount & (NACCW - 1));
         const uint32_t accphase = (uint32_t)((tcount / NACCW) & 1);
         const int rslot = (int)(tcount % NRES);
         const int h = s.row0 + j * p.dil;
         const size_t rowbase = ((size_t)s.b * p.H + h) * p.W;
-        float* stg = reinterpret_cast<float*>(sStg + (tcount & 1) * STG_BYTES);
+        float* stg = reinterpret_cast<float*>(sStg + (egrp * 2 + (ntile_g & 1)) * STG_BYTES);
+        if (tma_out && ntile_g >= 2) {                // the TMA store that read this buffer two tiles ago must have drained it
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+          group_bar(bar_id);
+        }
+        ++ntile_g;
         WSWAIT(t_tfull, tc::mbar_wait(&tfull[slot], accphase));
         tc_fence_after();
         const long long tB = p.dbg ? clock64() : 0;
         {
           float acc[32], res[32];
-          tmem_ld32(tlane + ACC_BASE + slot * 32, acc);
-          if (p.res_mode == 1) tmem_ld32(tlane + RES_BASE + rslot * 32, res);
+          if (p.res_mode == 1) tmem_ld32x2(tlane + ACC_BASE + slot * 32, tlane + RES_BASE + rslot * 32, acc, res);
+          else tmem_ld32(tlane + ACC_BASE + slot * 32, acc);
+          if (p.dbg) t_ld += clock64() - tB;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { mbar_arrive(&tempty[slot]); if (p.res_mode == 1) mbar_arrive(&rsempty[rslot]); }
           float* row = stg + m * 32;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sPar + 4 * c);
-            const float4 s4 = *reinterpret_cast<const float4*>(sPar + 32 + 4 * c);
-            const float4 h4 = *reinterpret_cast<const float4*>(sPar + 64 + 4 * c);
+            const float4 a4 = *reinterpret_cast<const float4*>(sPar + 4 * c);
+            const float4 b4 = *reinterpret_cast<const float4*>(sPar + 32 + 4 * c);
             float4 o;
-            o.x = fmaf(fmaf(acc[4 * c], winv, b4.x), s4.x, h4.x); o.y = fmaf(fmaf(acc[4 * c + 1], winv, b4.y), s4.y, h4.y);
-            o.z = fmaf(fmaf(acc[4 * c + 2], winv, b4.z), s4.z, h4.z); o.w = fmaf(fmaf(acc[4 * c + 3], winv, b4.w), s4.w, h4.w);
+            o.x = fmaf(acc[4 * c], a4.x, b4.x); o.y = fmaf(acc[4 * c + 1], a4.y, b4.y);
+            o.z = fmaf(acc[4 * c + 2], a4.z, b4.z); o.w = fmaf(acc[4 * c + 3], a4.w, b4.w);
             o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
             o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
             if (p.res_mode == 1) { o.x += res[4 * c]; o.y += res[4 * c + 1]; o.z += res[4 * c + 2]; o.w += res[4 * c + 3]; }
@@ -331,9 +354,16 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           }
         }
         if (p.dbg) t_px += clock64() - tB;
-        WSWAIT(t_bar, epi_bar_ws());                  // tile staged; everyone is also done reading the other buffer (tile - 1)
+        if (tma_out) fence_async_smem();              // generic-proxy writes of the tile -> visible to the TMA (async proxy)
+        WSWAIT(t_bar, group_bar(bar_id));             // tile staged
         const long long tC = p.dbg ? clock64() : 0;
+        if (tma_out && et == 0) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n"
+                       :: "l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stg)), "r"(0), "r"(x0), "r"(h), "r"(s.b) : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!tma_out || has_stats)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = rg + 16 * i;
@@ -349,7 +379,7 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
               s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
               s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
             }
-            __stcg(reinterpret_cast<float4*>(p.y + off), o);
+            if (!tma_out) __stcg(reinterpret_cast<float4*>(p.y + off), o);
           }
         }
         if (has_stats) {      // stats row = (image row, column block): [(b*H + h)*ncb + cb][2][32]
@@ -360,21 +390,22 @@ conv2d_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           }
           if (lane < 8) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { sRed[ew * 64 + lane * 4 + c] = s1[c]; sRed[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
+            for (int c = 0; c < 4; ++c) { red[ew * 64 + lane * 4 + c] = s1[c]; red[ew * 64 + 32 + lane * 4 + c] = s2[c]; }
           }
-          epi_bar_ws();
+          group_bar(bar_id);
           if (et < 64) {
             float a = 0.f;
 #pragma unroll
-            for (int wq = 0; wq < 4; ++wq) a += sRed[wq * 64 + et];
+            for (int wq = 0; wq < 4; ++wq) a += red[wq * 64 + et];
             e.stats[(((size_t)s.b * p.H + h) * p.ncb + s.cb) * 64 + et] = a;
           }
-          epi_bar_ws();                               // sRed is rewritten by the next tile
         }
         if (p.dbg) t_out += clock64() - tC;
+        if (!tma_out || has_stats) WSWAIT(t_bar2, group_bar(bar_id));       // staging tile / stats scratch may be rewritten
       }
     }
-    if (p.dbg && et == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = clock64() - t_ebegin; d[7] = t_bar; d[9] = t_px; d[10] = t_out; }
+    if (tma_out && et == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");    // all stores complete before the CTA exits
+    if (p.dbg && et == 0 && egrp == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = clock64() - t_ebegin; d[7] = t_bar; d[9] = t_px; d[10] = t_out; d[8] = t_ld; d[15] = t_bar2; }
   }
 
   tc_fence_before();
@@ -445,12 +476,18 @@ static int ws2_launch(const float* x, const float* wimg, float* y, const snb_con
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv2d_c32_ws: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  CUtensorMap tmap_out;
+  const cuuint32_t box_out[4] = {32, 128, 1, 1};
+  const CUresult cr2 = enc(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box_out, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SNB_REQUIRE(cr2 == CUDA_SUCCESS, "snb_conv2d_c32_ws: cuTensorMapEncodeTiled (output) failed (%d)", (int)cr2);
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nstrips < sms ? p.nstrips : sms;
   SNB_CUDA(cudaFuncSetAttribute(ws2::conv2d_c32_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws2::SMEM_BYTES));
-  snb_launch(ws2::conv2d_c32_ws_kernel, grid, ws2::NTHREADS_WS, ws2::SMEM_BYTES, stream, tmap, p);
+  snb_launch(ws2::conv2d_c32_ws_kernel, grid, ws2::NTHREADS_WS, ws2::SMEM_BYTES, stream, tmap, tmap_out, p);
   SNB_LAUNCH_CHECK("conv2d_c32_ws_kernel");
   return 0;
 }

@@ -39,25 +39,30 @@ __device__ __forceinline__ void ffma2_acc(unsigned long long& acc, unsigned long
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
-// one kernel row kh of one channel quad for one position: 9 taps = 5 packed FMAs (the 10th lane multiplies a zero weight)
-template <int KH>
-__device__ __forceinline__ void fma_khrow(unsigned long long (&acc)[5], const float* __restrict__ wrow, unsigned long long xp) {
-  const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(wrow + KH * 12);
-  const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(wrow + KH * 12 + 4);
-  const unsigned long long w4 = *reinterpret_cast<const unsigned long long*>(wrow + KH * 12 + 8);
-  ffma2_acc(acc[0], xp, w01.x); ffma2_acc(acc[1], xp, w01.y);
-  ffma2_acc(acc[2], xp, w23.x); ffma2_acc(acc[3], xp, w23.y);
-  ffma2_acc(acc[4], xp, w4);
+// the 9 (kd,kw) weights of one kernel row kh for one channel, as 5 packed pairs (the 10th lane is a zero weight)
+struct WRow { ulonglong2 a, b; unsigned long long c; };
+__device__ __forceinline__ WRow load_wrow(const float* __restrict__ wrow, int kh) {
+  WRow w;
+  w.a = *reinterpret_cast<const ulonglong2*>(wrow + kh * 12);
+  w.b = *reinterpret_cast<const ulonglong2*>(wrow + kh * 12 + 4);
+  w.c = *reinterpret_cast<const unsigned long long*>(wrow + kh * 12 + 8);
+  return w;
+}
+__device__ __forceinline__ void fma_khrow(unsigned long long (&acc)[5], const WRow& w, unsigned long long xp) {
+  ffma2_acc(acc[0], xp, w.a.x); ffma2_acc(acc[1], xp, w.a.y);
+  ffma2_acc(acc[2], xp, w.b.x); ffma2_acc(acc[3], xp, w.b.y);
+  ffma2_acc(acc[4], xp, w.c);
 }
 
-// contraction of one staged input row: MASK bit kh set = this row feeds kernel row kh of an output row inside the band
+// contraction of one staged input row: MASK bit kh set = this row feeds kernel row kh of an output row inside the band.
+// The weights of a channel are loaded ONCE per thread (broadcast LDS) and serve its HF_P positions; positions past the end of
+// the segment read as zeros (no per-position branch, which would also keep the compiler from sharing the weight loads).
 template <int MASK>
 __device__ __forceinline__ void contract_row(const unsigned char* __restrict__ row, const float* __restrict__ sW, int npos,
                                              unsigned long long (&accN)[HF_P][5], unsigned long long (&accC)[HF_P][5],
                                              unsigned long long (&accP)[HF_P][5]) {
   const int t = threadIdx.x;
-  const int nround = (npos + HF_THREADS - 1) / HF_THREADS;        // rounds of HF_THREADS positions that hold any work (CTA-uniform)
-#pragma unroll 1
+#pragma unroll 2
   for (int c4 = 0; c4 < 8; ++c4) {
     float4 xv[HF_P];
 #pragma unroll
@@ -69,14 +74,17 @@ __device__ __forceinline__ void contract_row(const unsigned char* __restrict__ r
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float* wrow = sW + (c4 * 4 + kk) * HF_WROW;
+      WRow w0, w1, w2;
+      if (MASK & 1) w0 = load_wrow(wrow, 0);
+      if (MASK & 2) w1 = load_wrow(wrow, 1);
+      if (MASK & 4) w2 = load_wrow(wrow, 2);
 #pragma unroll
       for (int i = 0; i < HF_P; ++i) {
-        if (i >= nround) continue;
         const float xs = kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w;
         const unsigned long long xp = pack2(xs, xs);
-        if (MASK & 1) fma_khrow<0>(accN[i], wrow, xp);
-        if (MASK & 2) fma_khrow<1>(accC[i], wrow, xp);
-        if (MASK & 4) fma_khrow<2>(accP[i], wrow, xp);
+        if (MASK & 1) fma_khrow(accN[i], w0, xp);
+        if (MASK & 2) fma_khrow(accC[i], w1, xp);
+        if (MASK & 4) fma_khrow(accP[i], w2, xp);
       }
     }
   }

@@ -99,6 +99,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 32-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t t0, uint32_t t1, float (&a)[32], float (&b)[32]) {
+  uint32_t r[64];
+#define SNB_LD32(OFF, ADDR) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n" \
+      : "=r"(r[OFF+0]), "=r"(r[OFF+1]), "=r"(r[OFF+2]), "=r"(r[OFF+3]), "=r"(r[OFF+4]), "=r"(r[OFF+5]), "=r"(r[OFF+6]), "=r"(r[OFF+7]), \
+        "=r"(r[OFF+8]), "=r"(r[OFF+9]), "=r"(r[OFF+10]), "=r"(r[OFF+11]), "=r"(r[OFF+12]), "=r"(r[OFF+13]), "=r"(r[OFF+14]), "=r"(r[OFF+15]), \
+        "=r"(r[OFF+16]), "=r"(r[OFF+17]), "=r"(r[OFF+18]), "=r"(r[OFF+19]), "=r"(r[OFF+20]), "=r"(r[OFF+21]), "=r"(r[OFF+22]), "=r"(r[OFF+23]), \
+        "=r"(r[OFF+24]), "=r"(r[OFF+25]), "=r"(r[OFF+26]), "=r"(r[OFF+27]), "=r"(r[OFF+28]), "=r"(r[OFF+29]), "=r"(r[OFF+30]), "=r"(r[OFF+31]) \
+      : "r"(ADDR) : "memory")
+  SNB_LD32(0, t0); SNB_LD32(32, t1);
+#undef SNB_LD32
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[32 + i]); }
+}
+
 // registers -> TMEM: lane (32*quadrant + laneid) gets 32 consecutive 32-bit columns starting at taddr's column
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

@@ -8,7 +8,7 @@ from stereonet_b200._cabi import ConvEpilogue
 dev = "cuda:0"
 torch.manual_seed(0)
 names = ["prod_wait_rempty", "prod_total", "mma_wait_afull", "mma_wait_tempty", "mma_total", "epi_wait_tfull", "epi_total", "epi_bar",
-         "epi_pre", "epi_tmem2smem", "epi_out", "cv_wait_rfull", "cv_wait_aempty", "cv_total", "cv_wait_res"]
+         "epi_tmem_ld", "epi_tmem2smem", "epi_out", "cv_wait_rfull", "cv_wait_aempty", "cv_total", "cv_wait_res", "epi_bar2"]
 x = torch.randn(1, 376, 1248, 32, device=dev)
 w = torch.randn(32, 32, 3, 3, device=dev) * 0.1
 b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
