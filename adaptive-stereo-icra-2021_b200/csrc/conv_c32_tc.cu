@@ -342,6 +342,35 @@ __device__ __forceinline__ void store_f16_split(float* __restrict__ out, int win
     img[B_BYTES / 2 + n * 64 + ((((k >> 3) + 4) ^ sw) << 3) + (k & 7)] = __float2half_rn(0.f);   // defined (halfs 32,33 of row 0 = the 2^-s slot)
 }
 
+// ---- weight images of conv_c32_ws.cu (SNB_CONV_WS): one image per (window, kw), rows = [kz = 2 | kz = 1 | kz = 0] x 32 cout, where
+// kz is the kernel axis the CTA walks along (2-D: kh, one window; 3-D: kd, window = kh).  2-D image = P [wh | wl] + Q [2^-11 wh | -]
+// (24 KB, 2^-s in the same spare slot as above); 3-D image = [wh | wl''] with wl'' = 2^11 (w' - wh) (12 KB; 2^-s after the 9 images).
+__device__ __forceinline__ void store_ws_split(float* __restrict__ out, bool d3, int win, int n, int k, float v, float scale) {
+  const int kw = n >> 5, co = n & 31;
+  const float vs = v * scale;
+  const __half wh = __float2half_rn(vs);
+  const float whf = __half2float(wh);
+  const int sw = co & 7;                                  // row = blk * 32 + co: row & 7 == co & 7
+  const int c0 = ((((k >> 3)) ^ sw) << 3) + (k & 7), c1 = ((((k >> 3) + 4) ^ sw) << 3) + (k & 7);
+  if (d3) {
+    const int kd = win / 3, kh = win - kd * 3;
+    __half* img = reinterpret_cast<__half*>(out) + (size_t)(kh * 3 + kw) * (B_BYTES / 2);
+    const int row = (2 - kd) * 32 + co;
+    img[row * 64 + c0] = wh;
+    img[row * 64 + c1] = __float2half_rn((vs - whf) * 2048.f);
+  } else {
+    __half* img = reinterpret_cast<__half*>(out) + (size_t)kw * B_BYTES;        // 24 KB per image = B_BYTES halfs
+    const int row = (2 - win) * 32 + co;
+    img[row * 64 + c0] = wh;
+    img[row * 64 + c1] = __float2half_rn(vs - whf);
+    img[B_BYTES / 2 + row * 64 + c0] = __float2half_rn(whf * (1.f / 2048.f));
+    if (kw != 0 || row != 0 || k >= 2) img[B_BYTES / 2 + row * 64 + c1] = __float2half_rn(0.f);
+  }
+}
+__device__ __forceinline__ int scale_slot_of(int mode_bits, int nwin) {
+  return ((mode_bits & SNB_CONV_WS) && nwin == 9) ? 9 * (B_BYTES / 4) : WIMG_SCALE_SLOT;
+}
+
 // 2^-s for one weight tensor of `numel` floats: s = 13 - floor(log2 max|w|), i.e. max|w * 2^s| in [2^13, 2^14) — far from the
 // fp16 overflow (65504) and with the low parts wl ~ 2^-11 w' of everything above 2^-16 max|w| still normal fp16 numbers.
 __device__ __forceinline__ void weight_scale_block(const float* __restrict__ w, int numel, float* __restrict__ slot) {
@@ -368,10 +397,10 @@ __global__ void weight_scale_batch_kernel(const long long* __restrict__ table) {
   pdl_launch(); pdl_wait();
   const long long* e = table + 4 * blockIdx.x;
   const int cfg = (int)e[2];
-  if (((cfg >> 8) & SNB_CONV_F16) == 0) return;
+  if (((cfg >> 8) & (SNB_CONV_F16 | SNB_CONV_WS)) == 0) return;
   const int nwin = cfg & 0xff, kind = (cfg >> 16) & 0xff;
   weight_scale_block(reinterpret_cast<const float*>(e[0]), kind == 0 ? 1024 * nwin * 3 : 1024 * 25,
-                     reinterpret_cast<float*>(e[1]) + WIMG_SCALE_SLOT);
+                     reinterpret_cast<float*>(e[1]) + scale_slot_of(cfg >> 8, nwin));
 }
 
 // w [32 cout][32 cin][kd*kh*kw taps] -> per (kd,kh) window: B_hi[n = kw*32 + cout][k = cin] then B_lo, each in the
@@ -379,9 +408,9 @@ __global__ void weight_scale_batch_kernel(const long long* __restrict__ table) {
 // mode | SNB_CONV_F16: the fp16-split format above.
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int nwin, int mode) {
   pdl_launch(); pdl_wait();
-  const bool f16 = (mode & SNB_CONV_F16) != 0;
+  const bool f16 = (mode & SNB_CONV_F16) != 0, ws = (mode & SNB_CONV_WS) != 0;
+  const float scale = (f16 || ws) ? 1.f / out[scale_slot_of(mode, nwin)] : 1.f;
   mode &= 0xf;
-  const float scale = f16 ? 1.f / out[WIMG_SCALE_SLOT] : 1.f;
   const int taps = nwin * 3;
   const int total = nwin * 96 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -393,6 +422,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
     float v;
     if (mode == 0) v = w[((size_t)co * 32 + k) * taps + tap];
     else           v = w[((size_t)k * 32 + co) * taps + (taps - 1 - tap)];   // dgrad: swap channels, flip taps
+    if (ws) { store_ws_split(out, nwin == 9, win, n, k, v, scale); continue; }
     if (f16) { store_f16_split(out, win, n, k, v, scale); continue; }
     const float hi = __uint_as_float(tc::tf32_hi_bits(v));
     const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
@@ -409,8 +439,8 @@ __global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table
   float* __restrict__ out = reinterpret_cast<float*>(e[1]);
   const int cfg = (int)e[2];
   const int nwin = cfg & 0xff, mode = (cfg >> 8) & 0xf, kind = (cfg >> 16) & 0xff, pa = (cfg >> 24) & 0xf, pb = (cfg >> 28) & 0xf;
-  const bool f16 = ((cfg >> 8) & SNB_CONV_F16) != 0;
-  const float scale = f16 ? 1.f / out[WIMG_SCALE_SLOT] : 1.f;
+  const bool f16 = ((cfg >> 8) & SNB_CONV_F16) != 0, ws = ((cfg >> 8) & SNB_CONV_WS) != 0;
+  const float scale = (f16 || ws) ? 1.f / out[scale_slot_of(cfg >> 8, nwin)] : 1.f;
   const int taps = nwin * 3;
   const int total = nwin * 96 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -428,6 +458,7 @@ __global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table
       const int y5 = 2 * (tap / 3) + pa, x5 = 2 * (tap % 3) + pb;
       v = (y5 < 5 && x5 < 5) ? w[((size_t)oc * 32 + ic) * 25 + y5 * 5 + x5] : 0.f;
     }
+    if (ws) { store_ws_split(out, nwin == 9, win, n, k, v, scale); continue; }
     if (f16) { store_f16_split(out, win, n, k, v, scale); continue; }
     const float hi = __uint_as_float(tc::tf32_hi_bits(v));
     const size_t o = (size_t)win * WIMG_FLOATS_PER_WINDOW + n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
@@ -470,10 +501,12 @@ extern "C" int snb_conv_c32_tc_num_tiles(const snb_conv_geom* g) {
 extern "C" int snb_conv_weights_tc_floats(int kd) { return kd * 3 * tc::WIMG_FLOATS_PER_WINDOW; }
 
 extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream) {
-  SNB_REQUIRE(w && out && (kd == 1 || kd == 3) && ((mode & ~SNB_CONV_F16) == 0 || (mode & ~SNB_CONV_F16) == 1), "snb_prep_conv_weights_tc: bad args");
+  SNB_REQUIRE(w && out && (kd == 1 || kd == 3) && ((mode & 0xf) == 0 || (mode & 0xf) == 1) && (mode & ~0x3f) == 0 &&
+              (mode & (SNB_CONV_F16 | SNB_CONV_WS)) != (SNB_CONV_F16 | SNB_CONV_WS), "snb_prep_conv_weights_tc: bad args");
   const int nwin = kd * 3;
-  if (mode & SNB_CONV_F16) {
-    snb_launch(tc::weight_scale_kernel, 1, 256, 0, stream, w, 1024 * nwin * 3, out + tc::WIMG_SCALE_SLOT);
+  if (mode & (SNB_CONV_F16 | SNB_CONV_WS)) {
+    const int slot = ((mode & SNB_CONV_WS) && kd == 3) ? 9 * (tc::B_BYTES / 4) : tc::WIMG_SCALE_SLOT;
+    snb_launch(tc::weight_scale_kernel, 1, 256, 0, stream, w, 1024 * nwin * 3, out + slot);
     SNB_LAUNCH_CHECK("weight_scale_kernel");
   }
   snb_launch(tc::prep_weights_tc_kernel, snb_ceil_div(nwin * 96 * 32, 256), 256, 0, stream, w, out, nwin, mode);

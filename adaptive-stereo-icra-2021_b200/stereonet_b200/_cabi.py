@@ -33,9 +33,10 @@ SIGNATURES = {
   "snb_conv2d_c32_tc_num_tiles": (_I, [_GP]),
   "snb_conv2d_c32_tc_profile": (_I, [_P, _P, _P, _GP, _EP, _I, _P, _P]),
   "snb_conv_c32_tc_profile": (_I, [_P, _P, _P, _GP, _EP, _I, _P, _P]),
-  "snb_conv2d_c32_ws": (_I, [_P, _P, _P, _GP, _EP, _P]),
-  "snb_conv2d_c32_ws_num_tiles": (_I, [_GP]),
-  "snb_conv2d_c32_ws_profile": (_I, [_P, _P, _P, _GP, _EP, _P, _P]),
+  "snb_conv_c32_ws": (_I, [_P, _P, _P, _GP, _EP, _P]),
+  "snb_conv_c32_ws_num_tiles": (_I, [_GP]),
+  "snb_conv_weights_ws_floats": (_I, [_I]),
+  "snb_conv_c32_ws_profile": (_I, [_P, _P, _P, _GP, _EP, _P, _P]),
   "snb_prep_conv_weights_tc": (_I, [_P, _P, _I, _I, _P]),
   "snb_conv_weights_tc_floats": (_I, [_I]),
   "snb_prep_conv_weights_tc_batch": (_I, [_P, _I, _P]),

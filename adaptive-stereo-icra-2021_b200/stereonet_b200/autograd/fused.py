@@ -49,28 +49,29 @@ def clear_cache(module):
 
 import os
 
-# Operand format of the stride-1 3x3 / 3x3x3 32->32 tensor-core layers.  "h3" (the product path): error-compensated fp16 split
-# (tcgen05 kind::f16, fp32-grade results).  The other values exist for the parity tests and A/B measurements only (set with
-# set_conv_backend, never from the environment): "tc3" = 3xTF32 split, "tc1" = single-pass TF32 (~1e-3 relative),
-# "ffma" = fp32 CUDA-core kernel.
-CONV_BACKEND = "h3"
+# Kernel / operand format of the stride-1 3x3 / 3x3x3 32->32 tensor-core layers.  "ws" (the product path): snb_conv_c32_ws,
+# error-compensated fp16 split (tcgen05 kind::f16, fp32-grade results).  The other values exist for the parity tests and A/B
+# measurements only (set with set_conv_backend, never from the environment): "h3" = the fp16 split on the round-1 kernels,
+# "tc3" = 3xTF32 split, "tc1" = single-pass TF32 (~1e-3 relative), "ffma" = fp32 CUDA-core kernel.
+CONV_BACKEND = "ws"
+_FMT = {"ws": "ws", "h3": "h", "tc3": 3, "tc1": 1}
 
 
 def set_conv_backend(name):
   global CONV_BACKEND
-  if name not in ("h3", "tc3", "tc1", "ffma"):
+  if name not in ("ws", "h3", "tc3", "tc1", "ffma"):
     raise ValueError(name)
   CONV_BACKEND = name
   bump_epoch()                 # cached weight images are in the previous backend's format
 
 
 def _tc_kw():
-  return dict(f16=True, passes=3) if CONV_BACKEND == "h3" else dict(f16=False, passes=3 if CONV_BACKEND == "tc3" else 1)
+  return dict(fmt=_FMT[CONV_BACKEND])
 
 
 def wprep_tc(conv, mode=0):
-  f16 = CONV_BACKEND == "h3"
-  return _cached(conv, ("wtc", mode, f16), [conv.weight], lambda: ops.prep_conv_weights_tc(conv.weight, mode, f16=f16))
+  fmt = _FMT[CONV_BACKEND]
+  return _cached(conv, ("wtc", mode, fmt), [conv.weight], lambda: ops.prep_conv_weights_tc(conv.weight, mode, fmt=fmt))
 
 
 def conv3x3_c32(x, conv, g, **kw):
@@ -143,7 +144,7 @@ def conv5x5s2_first(img, conv):
 
 def wprep_tc_phases(conv, mode):
   """Tensor-core weight images of the four polyphase 3x3 sub-kernels of a 5x5 stride-2 conv (csrc/phase.cu)."""
-  f16 = CONV_BACKEND == "h3"
+  fmt = _FMT[CONV_BACKEND]
 
   def make():
     w = conv.weight.detach()
@@ -152,9 +153,9 @@ def wprep_tc_phases(conv, mode):
       for b in (0, 1):
         sub = w[:, :, a::2, b::2]                                  # [32,32,3|2,3|2]  (layout ops only)
         sub = torch.nn.functional.pad(sub, (0, 3 - sub.shape[3], 0, 3 - sub.shape[2])).contiguous()
-        imgs.append(ops.prep_conv_weights_tc(sub, mode, f16=f16))
+        imgs.append(ops.prep_conv_weights_tc(sub, mode, fmt=fmt))
     return imgs
-  return _cached(conv, ("wtc_phase", mode, f16), [conv.weight], make)
+  return _cached(conv, ("wtc_phase", mode, fmt), [conv.weight], make)
 
 
 class WeightPrepBatch:
@@ -166,8 +167,8 @@ class WeightPrepBatch:
   def __init__(self, nets, modes=(0, 1)):
     self.items = []                      # (conv, cache key, views, source pointer)
     self.backend = CONV_BACKEND
-    f16 = CONV_BACKEND == "h3"
-    fbit = ops.CONV_F16 if f16 else 0
+    fmt = _FMT[CONV_BACKEND]
+    fbit = ops._fmt_of(fmt)[0]
     rows = []
     plan = []
     for net in nets:
@@ -180,20 +181,20 @@ class WeightPrepBatch:
         if tuple(w.shape[2:]) in ((3, 3), (3, 3, 3)) and m.stride[0] == 1:
           kd = 3 if w.dim() == 5 else 1
           for mode in modes:
-            plan.append((m, ("wtc", mode, f16), [(kd * 3, mode | fbit, 0, 0, 0)]))
+            plan.append((m, ("wtc", mode, fmt), [(kd * 3, mode | fbit, 0, 0, 0)]))
         elif tuple(w.shape[2:]) == (5, 5) and m.stride[0] == 2:
           for mode in modes:
-            plan.append((m, ("wtc_phase", mode, f16), [(3, mode | fbit, 1, a, b) for a in (0, 1) for b in (0, 1)]))
-    per_win = ops.conv_weights_tc_floats(1) // 3
-    total = sum(cfg[0] * per_win for _, _, cfgs in plan for cfg in cfgs)
+            plan.append((m, ("wtc_phase", mode, fmt), [(3, mode | fbit, 1, a, b) for a in (0, 1) for b in (0, 1)]))
+    size = lambda nwin: ops.conv_weights_tc_floats(nwin // 3, fmt)
+    total = sum(size(cfg[0]) for _, _, cfgs in plan for cfg in cfgs)
     dev = plan[0][0].weight.device
     self.buf = torch.empty((total,), device=dev, dtype=torch.float32)
     off = 0
     for m, key, cfgs in plan:
       views = []
       for nwin, mode, kind, a, b in cfgs:
-        v = self.buf[off:off + nwin * per_win]
-        off += nwin * per_win
+        v = self.buf[off:off + size(nwin)]
+        off += size(nwin)
         views.append(v)
         rows.append([m.weight.data_ptr(), v.data_ptr(), nwin | (mode << 8) | (kind << 16) | (a << 24) | (b << 28), 0])
       self.items.append((m, key, views, m.weight.data_ptr()))

@@ -116,24 +116,40 @@ def conv_c32(x, wprep, g, bias=None, scale=None, shift=None, residual=None, lrel
   return y, stats
 
 
-CONV_F16 = 0x10      # SNB_CONV_F16: fp16-split operand format (weight image and `passes` flag must match)
+CONV_F16 = 0x10      # SNB_CONV_F16: fp16-split operands on the round-1 kernels (3-D TMA kernel, 2-D N = 96 walk kernel)
+CONV_WS = 0x20       # SNB_CONV_WS: weight image layout of snb_conv_c32_ws, the product kernel
 
 
-def prep_conv_weights_tc(w, mode=0, f16=True):
-  """[32,32,(3,)3,3] -> tensor-core B-operand image (see snb_prep_conv_weights_tc); f16: the fp16-split format."""
+def _fmt_of(fmt):
+  """Operand format of the tensor-core convolutions -> (prep mode bits, passes argument).  "ws": snb_conv_c32_ws (product);
+  "h": fp16 split on the round-1 kernels; 3: 3xTF32 split; 1: single-pass TF32."""
+  if fmt == "ws":
+    return CONV_WS, 3
+  if fmt == "h":
+    return CONV_F16, 3 | CONV_F16
+  if fmt in (3, 1):
+    return 0, fmt
+  raise ValueError(f"unknown tensor-core operand format {fmt!r}")
+
+
+def prep_conv_weights_tc(w, mode=0, fmt="ws"):
+  """[32,32,(3,)3,3] -> tensor-core B-operand image for operand format `fmt` (see _fmt_of / snb_prep_conv_weights_tc)."""
   w = _req(w.detach().contiguous(), "weight")
   if w.shape[0] != 32 or w.shape[1] != 32 or tuple(w.shape[-2:]) != (3, 3):
     raise RuntimeError(f"stereonet_b200: tensor-core conv needs a [32,32,(3,)3,3] weight, got {tuple(w.shape)}")
   kd = 3 if w.dim() == 5 else 1
-  out = torch.empty((_cabi.lib().snb_conv_weights_tc_floats(kd),), device=w.device, dtype=torch.float32)
-  check(_cabi.lib().snb_prep_conv_weights_tc(_p(w), _p(out), kd, mode | (CONV_F16 if f16 else 0), _stream(w)),
-        "snb_prep_conv_weights_tc")
-  _count(2 if f16 else 1)
+  bits, _ = _fmt_of(fmt)
+  lib = _cabi.lib()
+  n = lib.snb_conv_weights_ws_floats(kd) if bits == CONV_WS else lib.snb_conv_weights_tc_floats(kd)
+  out = torch.empty((n,), device=w.device, dtype=torch.float32)
+  check(lib.snb_prep_conv_weights_tc(_p(w), _p(out), kd, mode | bits, _stream(w)), "snb_prep_conv_weights_tc")
+  _count(2 if bits else 1)
   return out
 
 
-def conv_weights_tc_floats(kd):
-  return _cabi.lib().snb_conv_weights_tc_floats(kd)
+def conv_weights_tc_floats(kd, fmt="ws"):
+  lib = _cabi.lib()
+  return lib.snb_conv_weights_ws_floats(kd) if fmt == "ws" else lib.snb_conv_weights_tc_floats(kd)
 
 
 def prep_conv_weights_tc_batch(table, n):
@@ -142,22 +158,27 @@ def prep_conv_weights_tc_batch(table, n):
   _count(2)
 
 
-def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, passes=3,
-                flat=False, out=None, legacy3d=False, f16=True, walk96=False):
-  """Tensor-core (tcgen05) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; same returns as conv_c32.  f16 (default):
-  error-compensated fp16 operand split (kind::f16), else TF32 (passes = 3: 3xTF32, 1: plain); `wimg` must be in the same format.
-  2-D inputs: f16 -> snb_conv2d_c32_ws (the product kernel; walk96=True selects the older N = 96 walk kernel in the fp16 format),
-  TF32 -> snb_conv2d_c32_tc, flat=True -> the flat-tiled loader-warp kernel; 3-D inputs the TMA kernel."""
+def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lrelu=False, want_stats=False, fmt="ws",
+                flat=False, out=None, legacy3d=False):
+  """Tensor-core (tcgen05) 32->32 'same' 3x3 / 3x3x3 convolution + fused epilogue; returns (y, stats) with stats = [ntiles,2,32]
+  partial sums or None.  `fmt` (see _fmt_of) selects the kernel and must match the format `wimg` was prepared in:
+  "ws" -> snb_conv_c32_ws (product path, 2-D and 3-D); "h" / 3 / 1 -> the round-1 kernels (2-D: snb_conv2d_c32_tc walk kernel,
+  flat=True: the flat-tiled loader-warp kernel; 3-D: the TMA kernel, legacy3d: the loader-warp one) kept as cross-checks."""
   three_d = x.dim() == 5
   _req(x, "x"); _req(wimg, "wimg")
   lib = _cabi.lib()
-  use2d = (not three_d) and (not flat)
-  use_ws = use2d and f16 and not walk96               # 2-D product kernel: shifted operand copies, N = 32 (conv2d_c32_ws.cu)
+  bits, passes = _fmt_of(fmt)
+  use_ws = bits == CONV_WS
+  if use_ws and (flat or legacy3d):
+    raise RuntimeError("stereonet_b200: flat / legacy3d select round-1 kernels; use fmt 'h', 3 or 1 with them")
+  if fmt == "h" and ((flat and not three_d) or legacy3d):
+    raise RuntimeError("stereonet_b200: the fp16 operand split runs on the TMA / walk kernels only")
   if use_ws and want_stats and (scale is not None or lrelu or residual is not None):
-    raise RuntimeError("stereonet_b200: snb_conv2d_c32_ws takes BN statistics of the plain conv + bias output only")
+    raise RuntimeError("stereonet_b200: snb_conv_c32_ws takes BN statistics of the plain conv + bias output only")
+  use2d = (not three_d) and (not flat)
   fn, fn_tiles = (lib.snb_conv2d_c32_tc, lib.snb_conv2d_c32_tc_num_tiles) if use2d else (lib.snb_conv_c32_tc, lib.snb_conv_c32_tc_num_tiles)
   if use_ws:
-    fn_tiles = lib.snb_conv2d_c32_ws_num_tiles
+    fn_tiles = lib.snb_conv_c32_ws_num_tiles
   y = out if out is not None else torch.empty(out_shape(g, three_d), device=x.device, dtype=torch.float32)
   if out is not None:
     _req(out, "out")
@@ -172,14 +193,10 @@ def conv_c32_tc(x, wimg, g, bias=None, scale=None, shift=None, residual=None, lr
     if residual.shape != y.shape:
       raise RuntimeError("stereonet_b200: residual shape mismatch")
   e = ConvEpilogue(_p(bias), _p(scale), _p(shift), _p(residual), _p(stats), 1 if lrelu else 0)
-  if f16:
-    if passes != 3 or (flat and not three_d) or legacy3d:
-      raise RuntimeError("stereonet_b200: the fp16 operand split has 3 passes and runs on the product kernels only")
-    passes |= CONV_F16
   if three_d and legacy3d:
     passes |= 0x400                      # diagnostics: 3-D flat-tiled kernel with loader warps instead of the TMA kernel
   if use_ws:
-    check(lib.snb_conv2d_c32_ws(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), _stream(x)), "snb_conv2d_c32_ws")
+    check(lib.snb_conv_c32_ws(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), _stream(x)), "snb_conv_c32_ws")
   else:
     check(fn(_p(x), _p(wimg), _p(y), C.byref(g), C.byref(e), passes, _stream(x)), "snb_conv2d_c32_tc" if use2d else "snb_conv_c32_tc")
   _count()

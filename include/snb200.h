@@ -35,6 +35,9 @@ extern "C" {
  * operands (tcgen05.mma.kind::f16, K = 16, power-of-two weight scaling) instead of 3xTF32 — same three products, same
  * fp32-grade result, half the MMA count.  The weight image must have been prepared in the matching format. */
 #define SNB_CONV_F16 0x10
+/* OR-ed into `mode` of snb_prep_conv_weights_tc[_batch]: the weight image layout of snb_conv_c32_ws (fp16 split; one image per
+ * (window, kw) with the three taps of the walk axis stacked along N; snb_conv_weights_ws_floats(kd) floats). */
+#define SNB_CONV_WS 0x20
 
 /* Geometry of one convolution over channels-last tensors. 2-D convs use D = OD = KD = 1, pd = 0. */
 typedef struct {
@@ -106,18 +109,20 @@ SNB_API int snb_conv2d_c32_tc_num_tiles(const snb_conv_geom* g);
  * legacy path that feeds the A operand from shared memory instead of TMEM (for A/B measurements). */
 SNB_API int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
                               const snb_conv_epilogue* e, int passes, long long* counters, void* stream);
-/* Round-2 product kernel for the 2-D layers (fp16-split weight image, mode | SNB_CONV_F16, only): the kw shift is applied on the
- * way INTO the tensor core (converter warps write three shifted copies of every raw input row into TMEM, MMAs are M128 N32 K16),
- * so the accumulator is the convolution output itself and the epilogue is one 16 KB transpose instead of a 48 KB shift-add; a
- * residual that is the layer's own input (BasicBlock, stereo_net.py:50) comes from the rows already on chip.  Same contract as
- * snb_conv2d_c32_tc except: `stats` (train-mode BN partials; snb_conv2d_c32_ws_num_tiles() rows) may only be combined with
- * `bias` — which is how the adaptation step uses it. */
-SNB_API int snb_conv2d_c32_ws(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
-                      void* stream);
-SNB_API int snb_conv2d_c32_ws_num_tiles(const snb_conv_geom* g);
+/* Round-2 product kernel for the 2-D (dilated) and 3-D layers (csrc/conv_c32_ws.cu; weight image from
+ * snb_prep_conv_weights_tc with mode | SNB_CONV_WS): walk along the slowest kernel axis, the kw shift applied on the way INTO the
+ * tensor core (converter warps write three shifted fp16-split copies of every raw input row into TMEM), the three taps of the walk
+ * axis folded into N = 96 over a ring of accumulators, all weight images resident in shared memory, one TMA tile store per output
+ * tile; a residual that is the layer's own input (BasicBlock, stereo_net.py:50) comes from the rows already on chip.  Same contract
+ * as snb_conv_c32_tc except: `stats` (train-mode BN partials; snb_conv_c32_ws_num_tiles() rows) may only be combined with `bias` —
+ * which is how the adaptation step uses it. */
+SNB_API int snb_conv_c32_ws(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
+                    void* stream);
+SNB_API int snb_conv_c32_ws_num_tiles(const snb_conv_geom* g);
+SNB_API int snb_conv_weights_ws_floats(int kd);
 /* Diagnostics: same launch plus per-CTA cycle counters [grid][16]. */
-SNB_API int snb_conv2d_c32_ws_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
-                              const snb_conv_epilogue* e, long long* counters, void* stream);
+SNB_API int snb_conv_c32_ws_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
+                            const snb_conv_epilogue* e, long long* counters, void* stream);
 /* Repack [32][32][kd*3*3] weights into the tensor-core B-operand smem image (hi/lo TF32 split, SWIZZLE_128B K-major,
  * one 24 KB block per (kd,kh) window).  kd = 1 (2-D) or 3 (3-D).  mode 0: forward, 1: data gradient. */
 SNB_API int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int mode, void* stream);

@@ -24,16 +24,14 @@ x2 = torch.randn(1, 376, 1248, 32, device=dev); w2 = torch.randn(32, 32, 3, 3, d
 b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
 for dil in (1, 4):
   g = ops.geom(tuple(x2.shape), 3, dil=dil)
-  for fmt in ("h", 3):
-    wimg = ops.prep_conv_weights_tc(w2, f16=fmt == "h")
-    check(f"conv2d dil{dil} fmt {fmt}", lambda: (ops.conv_c32_tc(x2, wimg, g, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True, f16=fmt == "h")[0],))
-    if fmt == "h":
-      check(f"conv2d dil{dil} fmt h96", lambda: (ops.conv_c32_tc(x2, wimg, g, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True, f16=True, walk96=True)[0],))
+  for fmt in ("ws", "h", 3):
+    wimg = ops.prep_conv_weights_tc(w2, fmt=fmt)
+    check(f"conv2d dil{dil} fmt {fmt}", lambda: (ops.conv_c32_tc(x2, wimg, g, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True, fmt=fmt)[0],))
 x3 = torch.randn(1, 24, 47, 156, 32, device=dev); w3 = torch.randn(32, 32, 3, 3, 3, device=dev) * 0.05
 g3 = ops.geom(tuple(x3.shape), 3)
-for fmt in ("h", 3):
-  wimg3 = ops.prep_conv_weights_tc(w3, f16=fmt == "h")
-  check(f"conv3d fmt {fmt}", lambda: (ops.conv_c32_tc(x3, wimg3, g3, bias=b, scale=sc, shift=sh, lrelu=True, f16=fmt == "h")[0],))
+for fmt in ("ws", "h", 3):
+  wimg3 = ops.prep_conv_weights_tc(w3, fmt=fmt)
+  check(f"conv3d fmt {fmt}", lambda: (ops.conv_c32_tc(x3, wimg3, g3, bias=b, scale=sc, shift=sh, lrelu=True, fmt=fmt)[0],))
 w1 = torch.randn(1, 32, 3, 3, 3, device=dev) * 0.5; b1 = torch.randn(1, device=dev)
 check("head fused", lambda: tuple(t for t in ops.conv3d_out_softargmin(x3, w1, b1, True, True)))
 fl = torch.randn(1, 47, 156, 32, device=dev); fr = torch.randn(1, 47, 156, 32, device=dev)

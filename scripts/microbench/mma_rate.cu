@@ -14,7 +14,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int N, bool TA, int NACC, int BG>
+template <int N, bool TA, int NACC, int BG, int H16 = 0>
 __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters, int rnd, const float* gsrc) {
   __shared__ volatile int stop_flag;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters,
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC = H16 ? ((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24))
+                                 : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24));
   long long t0 = 0, t1 = 0;
   if (threadIdx.x < 32) {
     const uint32_t sa = base, sb = base + 16384;
@@ -65,7 +66,9 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters,
           for (int a = 0; a < NACC; ++a) {
             const uint32_t td = tmem + a * (N <= 96 ? 96 : (N <= 128 ? 128 : 256)) % 448;
             const uint64_t bd = make_desc(sb + ks * 32 + (BG == 4 ? ((it * 4 + ks) % 2) * 12288 : 0));
-            if (TA) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+            if (H16) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                                 :: "r"(td), "r"(ta + ks * 8), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
+            else if (TA) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
                                  :: "r"(td), "r"(ta + ks * 8), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
             else    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                                  :: "r"(td), "l"(make_desc(sa + ks * 32)), "l"(bd), "r"(IDESC), "r"(1u) : "memory");
@@ -129,23 +132,30 @@ __global__ void __launch_bounds__(288, 1) rate_kernel(long long* out, int iters,
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
 }
 
-template <int N, bool TA, int NACC, int BG>
+template <int N, bool TA, int NACC, int BG, int H16 = 0>
 void run(const char* tag, int rnd = 0, int iters = 200) {
   long long* d; cudaMalloc(&d, 148 * sizeof(long long));
   static float* gsrc = nullptr;
   if (!gsrc) { cudaMalloc(&gsrc, 1024 * 16384); cudaMemset(gsrc, 0, 1024 * 16384); }
   const int smem = 16384 + 32768 + 65536 + 2048;
-  cudaFuncSetAttribute(rate_kernel<N, TA, NACC, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC, BG><<<148, 288, smem>>>(d, iters, rnd, gsrc);
+  cudaFuncSetAttribute(rate_kernel<N, TA, NACC, BG, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) rate_kernel<N, TA, NACC, BG, H16><<<148, 288, smem>>>(d, iters, rnd, gsrc);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   double s = 0; for (int i = 0; i < 148; ++i) s += h[i];
   const double cyc = s / 148 / (iters * 4 * NACC);
-  printf("%-28s N=%3d acc=%d: %7.1f cycles/MMA  %7.1f MAC/clk/SM  (%s)\n", tag, N, NACC, cyc, 128.0 * N * 8 / cyc, cudaGetErrorString(e));
+  printf("%-28s N=%3d acc=%d: %7.1f cycles/MMA  %7.1f MAC/clk/SM  (%s)\n", tag, N, NACC, cyc, 128.0 * N * (H16 ? 16 : 8) / cyc, cudaGetErrorString(e));
   cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {      // round 2: kind::f16 (K = 16), A operand in TMEM
+    run<32, true, 1, 0, 1>("f16 K16, A tmem"); run<64, true, 1, 0, 1>("f16 K16, A tmem"); run<96, true, 1, 0, 1>("f16 K16, A tmem");
+    run<128, true, 1, 0, 1>("f16 K16, A tmem"); run<256, true, 1, 0, 1>("f16 K16, A tmem");
+    run<32, true, 3, 0, 1>("f16 K16, A tmem, 3 acc"); run<96, true, 3, 0, 1>("f16 K16, A tmem, 3 acc"); run<96, true, 3, 1, 1>("f16 K16, A tmem + LDS/STS");
+    run<32, true, 1, 0, 0>("tf32 K8, A tmem"); run<64, true, 1, 0, 0>("tf32 K8, A tmem");
+    return 0;
+  }
   run<32, false, 1, 0>("A smem"); run<64, false, 1, 0>("A smem"); run<96, false, 1, 0>("A smem"); run<128, false, 1, 0>("A smem"); run<192, false, 1, 0>("A smem"); run<256, false, 1, 0>("A smem");
   run<96, true, 1, 0>("A tmem"); run<128, true, 1, 0>("A tmem"); run<192, true, 1, 0>("A tmem"); run<256, true, 1, 0>("A tmem");
   run<96, false, 3, 0>("A smem, 3 accumulators"); run<96, true, 3, 0>("A tmem, 3 accumulators");

@@ -1,0 +1,29 @@
+"""The round-2 product kernels at KITTI size, three launches each (target of `ncu --set full -k regex:...`)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "adaptive-stereo-icra-2021_b200")); sys.path.insert(0, ROOT)
+import torch
+from stereonet_b200 import ops
+dev = "cuda:0"
+torch.manual_seed(0)
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+x2 = torch.randn(1, 376, 1248, 32, device=dev); w2 = torch.randn(32, 32, 3, 3, device=dev) * 0.1
+b = torch.randn(32, device=dev); sc = torch.rand(32, device=dev) + 0.5; sh = torch.randn(32, device=dev)
+x3 = torch.randn(1, 24, 47, 156, 32, device=dev); w3 = torch.randn(32, 32, 3, 3, 3, device=dev) * 0.05
+w1 = torch.randn(1, 32, 3, 3, 3, device=dev) * 0.5; b1 = torch.randn(1, device=dev)
+fl = torch.randn(1, 47, 156, 32, device=dev); fr = torch.randn(1, 47, 156, 32, device=dev)
+wi2 = ops.prep_conv_weights_tc(w2, fmt="ws"); wi3h = ops.prep_conv_weights_tc(w3, fmt="h"); wi3 = ops.prep_conv_weights_tc(w3, fmt="ws")
+g2 = ops.geom(tuple(x2.shape), 3, dil=1); g3 = ops.geom(tuple(x3.shape), 3)
+for _ in range(3):
+  flush.zero_()
+  ops.conv_c32_tc(x2, wi2, g2, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True, fmt="ws")
+  flush.zero_()
+  ops.conv_c32_tc(x3, wi3h, g3, bias=b, scale=sc, shift=sh, lrelu=True, fmt="h")
+  flush.zero_()
+  ops.conv_c32_tc(x3, wi3, g3, bias=b, scale=sc, shift=sh, lrelu=True, fmt="ws")
+  flush.zero_()
+  ops.conv3d_out_softargmin(x3, w1, b1, True, True)
+  flush.zero_()
+  ops.cost_volume(fl, fr, 24)
+torch.cuda.synchronize()
+print("ok")

@@ -35,9 +35,9 @@ for shape, dil in [((1, 376, 1248, 32), 1), ((1, 376, 1248, 32), 4), ((1, 376, 1
   g = ops.geom(shape, 3, dil=dil)
   ref, _ = ops.conv_c32(x, ops.prep_conv_weights(w), g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True)
   flops = 2 * 9 * 32 * 32 * x.numel() / 32
-  for fmt in ("h", "h96", 3, 1):
-    kw = dict(f16=True, passes=3, walk96=fmt == "h96") if fmt in ("h", "h96") else dict(f16=False, passes=fmt)
-    wimg = ops.prep_conv_weights_tc(w, f16=fmt in ("h", "h96"))
+  for fmt in ("ws", "h", 3, 1):
+    kw = dict(fmt=fmt)
+    wimg = ops.prep_conv_weights_tc(w, fmt=fmt)
     fn = lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, residual=x, lrelu=True, **kw)
     y, _ = fn()
     err = (y - ref).abs().max().item() / ref.abs().max().item()
@@ -53,9 +53,9 @@ for shape in [(1, 24, 47, 156, 32), (4, 24, 47, 156, 32)]:
   g = ops.geom(shape, 3)
   ref, _ = ops.conv_c32(x, ops.prep_conv_weights(w), g, bias=b, scale=sc, shift=sh, lrelu=True)
   flops = 2 * 27 * 32 * 32 * x.numel() / 32
-  for fmt in ("h", 3, 1):
-    kw = dict(f16=True, passes=3) if fmt == "h" else dict(f16=False, passes=fmt)
-    wimg = ops.prep_conv_weights_tc(w, f16=fmt == "h")
+  for fmt in ("ws", "h", 3, 1):
+    kw = dict(fmt=fmt)
+    wimg = ops.prep_conv_weights_tc(w, fmt=fmt)
     fn = lambda: ops.conv_c32_tc(x, wimg, g, bias=b, scale=sc, shift=sh, lrelu=True, **kw)
     y, _ = fn()
     err = (y - ref).abs().max().item() / ref.abs().max().item()

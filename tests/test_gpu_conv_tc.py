@@ -1,6 +1,6 @@
-"""GPU parity of the tcgen05 (tensor-core) 32->32 convolution against plain fp32 torch on the CPU.  Operand formats:
-"h" = error-compensated fp16 split (kind::f16, the product path) and 3 = 3xTF32 must be fp32-grade: 1e-5 of the output
-magnitude; 1 = plain single-pass TF32: 3e-3."""
+"""GPU parity of the tcgen05 (tensor-core) 32->32 convolutions against plain fp32 torch on the CPU.  Kernels / operand formats:
+"ws" = snb_conv_c32_ws (the product kernel, error-compensated fp16 split), "h" = the same split on the round-1 kernels and
+3 = 3xTF32 must be fp32-grade: 1e-5 of the output magnitude; 1 = plain single-pass TF32: 3e-3."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -9,22 +9,18 @@ from stereonet_b200 import ops
 from test_gpu_kernels import cl, uncl, rnd, close, DEV
 
 pytestmark = pytest.mark.gpu
-TOL = {"h": 1e-5, "h96": 1e-5, 3: 1e-5, 1: 3e-3}
+TOL = {"ws": 1e-5, "h": 1e-5, 3: 1e-5, 1: 3e-3}
 
 
 def kw(fmt):
-  """"h": the product kernels (2-D: shifted-operand N = 32 kernel, 3-D: TMA kernel) in the fp16 format; "h96": the 2-D N = 96
-  walk kernel in the fp16 format; 3 / 1: TF32 with that many passes."""
-  if fmt in ("h", "h96"):
-    return dict(f16=True, passes=3, walk96=fmt == "h96")
-  return dict(f16=False, passes=fmt)
+  return dict(fmt=fmt)
 
 
 def wimg(w, fmt, mode=0):
-  return ops.prep_conv_weights_tc(w.to(DEV), mode=mode, f16=fmt in ("h", "h96"))
+  return ops.prep_conv_weights_tc(w.to(DEV), mode=mode, fmt=fmt)
 
 
-@pytest.mark.parametrize("fmt", ["h", "h96", 3, 1])
+@pytest.mark.parametrize("fmt", ["ws", "h", 3, 1])
 @pytest.mark.parametrize("B,H,W,dil", [(1, 19, 45, 1), (2, 23, 37, 2), (1, 40, 50, 4), (1, 33, 41, 8), (1, 8, 128, 1),
                                        (1, 47, 156, 1), (1, 130, 260, 2), (2, 5, 300, 8), (1, 1, 7, 1), (1, 9, 129, 1),
                                        (1, 70, 256, 16), (3, 3, 128, 2)])
@@ -45,11 +41,16 @@ def test_conv_tc_f16_split_dynamic_range(wscale, xscale):
   x[0, :, 3, 5] = 0.0                                           # exact zeros and a few large outliers
   x[0, 7, 10, 20] = 6.0e4 if xscale >= 1.0 else x[0, 7, 10, 20]
   ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).float()
-  y, _ = ops.conv_c32_tc(cl(x), wimg(w, "h"), ops.geom((1, 21, 150, 32), 3), bias=b.to(DEV))
-  close(uncl(y), ref, 1e-5, f"f16 split wscale={wscale} xscale={xscale}")
+  for fmt in ("ws", "h"):
+    y, _ = ops.conv_c32_tc(cl(x), wimg(w, fmt), ops.geom((1, 21, 150, 32), 3), bias=b.to(DEV), fmt=fmt)
+    close(uncl(y), ref, 1e-5, f"f16 split [{fmt}] wscale={wscale} xscale={xscale}")
+  x3, w3 = rnd(1, 32, 5, 9, 40, seed=4) * xscale, rnd(32, 32, 3, 3, 3, seed=5, scale=wscale)
+  ref3 = F.conv3d(x3.double(), w3.double(), None, padding=1).float()
+  y3, _ = ops.conv_c32_tc(cl(x3), wimg(w3, "ws"), ops.geom((1, 5, 9, 40, 32), 3))
+  close(uncl(y3), ref3, 1e-5, f"f16 split [ws 3-D] wscale={wscale} xscale={xscale}")
 
 
-@pytest.mark.parametrize("fmt", ["h", "h96", 3])
+@pytest.mark.parametrize("fmt", ["ws", "h", 3])
 @pytest.mark.parametrize("B,H,W,dil", [(2, 23, 37, 2), (1, 47, 156, 1), (1, 64, 300, 4)])
 def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil, fmt):
   x, w, b = rnd(B, 32, H, W, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
@@ -57,7 +58,7 @@ def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil, fmt):
   z = F.conv2d(x, w, b, padding=dil, dilation=dil)
   ref = F.leaky_relu(z * scale.view(1, 32, 1, 1) + shift.view(1, 32, 1, 1), 0.2) + x
   xc = cl(x)
-  if fmt == "h":      # snb_conv2d_c32_ws: statistics of conv + bias only (the train-mode call), the full epilogue separately
+  if fmt == "ws":     # snb_conv_c32_ws: statistics of conv + bias only (the train-mode call), the full epilogue separately
     g = ops.geom((B, H, W, 32), 3, dil=dil)
     zc, stats = ops.conv_c32_tc(xc, wimg(w, fmt), g, bias=b.to(DEV), want_stats=True)
     close(uncl(zc), z, 1e-5, "conv2d ws z")
@@ -78,6 +79,28 @@ def test_conv2d_tc_full_epilogue_and_stats(B, H, W, dil, fmt):
   s = stats.double().sum(0).cpu()
   close(s[0], z.double().sum((0, 2, 3)), 1e-4, "sum z")
   close(s[1], (z.double() ** 2).sum((0, 2, 3)), 1e-4, "sum z^2")
+
+
+@pytest.mark.parametrize("B,D,H,W", [(1, 24, 9, 20), (2, 6, 7, 33), (1, 12, 17, 16), (1, 24, 47, 156), (1, 1, 3, 5), (2, 3, 16, 16),
+                                     (1, 24, 40, 120), (1, 12, 20, 60)])
+def test_conv_ws_3d(B, D, H, W):
+  """snb_conv_c32_ws, 3-D: walk along the disparity axis, two accumulator rings; statistics of conv + bias, then the full
+  epilogue (incl. a residual from global memory) in separate launches."""
+  x, w, b = rnd(B, 32, D, H, W, seed=1), rnd(32, 32, 3, 3, 3, seed=2, scale=0.05), rnd(32, seed=3)
+  scale, shift = rnd(32, seed=4).abs() + 0.5, rnd(32, seed=5)
+  z = F.conv3d(x, w, b, padding=1)
+  ref = F.leaky_relu(z * scale.view(1, 32, 1, 1, 1) + shift.view(1, 32, 1, 1, 1), 0.2)
+  g = ops.geom((B, D, H, W, 32), 3)
+  xc = cl(x)
+  zc, stats = ops.conv_c32_tc(xc, wimg(w, "ws"), g, bias=b.to(DEV), want_stats=True)
+  close(uncl(zc), z, 1e-5, "ws conv3d z")
+  s = stats.double().sum(0).cpu()
+  close(s[0], z.double().sum((0, 2, 3, 4)), 1e-4, "sum z")
+  close(s[1], (z.double() ** 2).sum((0, 2, 3, 4)), 1e-4, "sum z^2")
+  y, _ = ops.conv_c32_tc(xc, wimg(w, "ws"), g, bias=b.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV), lrelu=True)
+  close(uncl(y), ref, 1e-5, "ws conv3d epilogue")
+  y2, _ = ops.conv_c32_tc(xc, wimg(w, "ws"), g, bias=b.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV), lrelu=True, residual=xc)
+  close(uncl(y2), ref + x, 1e-5, "ws conv3d epilogue + residual")
 
 
 @pytest.mark.parametrize("passes", ["h", 3, 1])
@@ -101,11 +124,11 @@ def test_conv_tc_kitti_refinement_size():
   x, w, b = rnd(1, 32, 376, 1248, seed=1), rnd(32, 32, 3, 3, seed=2, scale=0.1), rnd(32, seed=3)
   for dil in (1, 8):
     ref = F.conv2d(x, w, b, padding=dil, dilation=dil)
-    y, _ = ops.conv_c32_tc(cl(x), wimg(w, "h"), ops.geom((1, 376, 1248, 32), 3, dil=dil), bias=b.to(DEV))
+    y, _ = ops.conv_c32_tc(cl(x), wimg(w, "ws"), ops.geom((1, 376, 1248, 32), 3, dil=dil), bias=b.to(DEV))
     close(uncl(y), ref, 1e-5, f"tc conv2d 376x1248 dil={dil}")
 
 
-@pytest.mark.parametrize("fmt", ["h", 3])
+@pytest.mark.parametrize("fmt", ["ws", "h", 3])
 def test_conv_tc_dgrad_weights(fmt):
   x = rnd(1, 32, 14, 27, seed=1).requires_grad_()
   w = rnd(32, 32, 3, 3, seed=2, scale=0.1)

@@ -1,7 +1,7 @@
 """The A/B switches of the library select between kernels of this library (never a fallback).  Each variant must give the
 same results as the default path: the CUDA-core cross-check kernels (SNB200_SMALL_CONV=ffma), launches without programmatic
 dependent launch (SNB200_PDL=0) and — selected by the test itself through fused.set_conv_backend, not the environment — the
-3xTF32 operand split and the fp32 FFMA kernel instead of the fp16 split of the 32->32 convolutions.  The switches are read once
+round-1 kernels with the fp16 split, the 3xTF32 operand split and the fp32 FFMA kernel instead of snb_conv_c32_ws.  The switches are read once
 per process, so every variant runs in its own interpreter."""
 import os
 import subprocess
@@ -33,7 +33,7 @@ from stereonet_b200 import ops
 from stereonet_b200.autograd import fused
 if os.environ.get("SNB_TEST_BACKEND"):
   fused.set_conv_backend(os.environ["SNB_TEST_BACKEND"])
-h16 = fused.CONV_BACKEND == "h3"
+fmt = fused._FMT.get(fused.CONV_BACKEND, "ws")
 dev = "cuda:0"
 k = 3
 f = S.FeatureExtractorNetwork(k).to(dev).eval(); s = S.StereoNet(k, 1, 0).to(dev).eval()
@@ -44,7 +44,7 @@ with torch.no_grad():
   out = s(l, f(l), f(r), "l", output_cost_volume=True)
   x3 = torch.randn(1, 6, 9, 150, 32, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
   w3 = torch.randn(32, 32, 3, 3, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) * 0.05
-  y3, st3 = ops.conv_c32_tc(x3, ops.prep_conv_weights_tc(w3, f16=h16), ops.geom(tuple(x3.shape), 3), lrelu=True, want_stats=True, f16=h16)
+  y3, st3 = ops.conv_c32_tc(x3, ops.prep_conv_weights_tc(w3, fmt=fmt), ops.geom(tuple(x3.shape), 3), want_stats=True, fmt=fmt)
 torch.cuda.synchronize()
 np.savez(sys.argv[2], disp=out["pred_disp_l/0"].cpu().numpy(), coarse=out["pred_disp_l/3"].cpu().numpy(),
          cost=out["cost_volume_l/3"].cpu().numpy(), y3=y3.cpu().numpy(), st3=st3.double().sum(0).cpu().numpy())
@@ -64,7 +64,7 @@ def default_run():
   return _run({})
 
 
-@pytest.mark.parametrize("env", [{"SNB200_SMALL_CONV": "ffma"}, {"SNB200_PDL": "0"}, {"SNB_TEST_BACKEND": "tc3"},
+@pytest.mark.parametrize("env", [{"SNB200_SMALL_CONV": "ffma"}, {"SNB200_PDL": "0"}, {"SNB_TEST_BACKEND": "h3"}, {"SNB_TEST_BACKEND": "tc3"},
                                  {"SNB_TEST_BACKEND": "ffma", "SNB200_SMALL_CONV": "ffma", "SNB200_PDL": "0"}])
 def test_variant_matches_default(default_run, env):
   got = _run(env)
@@ -93,7 +93,8 @@ def test_weight_prep_batch_matches_per_layer_prep():
     if key[0] == "wtc":
       ref = ops.prep_conv_weights_tc(conv.weight, mode)
       assert torch.equal(views[0], ref), (key, tuple(conv.weight.shape))
-      assert float(views[0][ops.conv_weights_tc_floats(1) // 6 + 16]) in [2.0 ** -e for e in range(-20, 41)]    # the 2^-s slot
+      slot = 9 * 3072 if conv.weight.dim() == 5 else 3072 + 16
+      assert float(views[0][slot]) in [2.0 ** -e for e in range(-20, 41)]    # the 2^-s slot
       n3x3 += 1
     else:
       w = conv.weight.detach()
