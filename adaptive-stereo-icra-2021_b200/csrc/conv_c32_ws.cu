@@ -175,6 +175,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   float* sRed = sPar + 96;                                  // [2 groups][4 warps][64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_entry = p.dbg ? clock64() : 0;
   const int RW = 128 + 2 * p.dil;                           // rows of a raw window
   const int HW = p.H * p.W;
 
@@ -240,7 +241,9 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // =============================================================== MMA issuer (converged warp, elected lane), window-major
-    tc::mbar_wait_spin(wbar, 0);                   // resident weight images (requested before griddepcontrol.wait)
+    const long long t_w0 = p.dbg ? clock64() : 0;
+    tc::mbar_wait_spin(wbar, 0);                   // resident weight images
+    if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[8] = t_w0 - t_entry; dd[9] = clock64() - t_w0; }
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NR * C::RAW_BYTES + 2 * C::NSTG * STG_BYTES;
     long long tile_base = 0;
@@ -525,7 +528,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     }
     if (tma_out && et == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");    // all stores complete before the CTA exits
-    if (p.dbg && et == 0 && egrp == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = clock64() - t_ebegin; d[7] = t_bar; d[9] = t_px; d[10] = t_out; d[8] = t_ld; d[15] = t_bar2; }
+    if (p.dbg && et == 0 && egrp == 0) { long long* d = p.dbg + blockIdx.x * 16; d[5] = t_tfull; d[6] = clock64() - t_ebegin; d[7] = t_bar; d[10] = t_out; d[15] = clock64() - t_entry; }
   }
 
   tc_fence_before();

@@ -55,6 +55,15 @@ import os
 # "tc3" = 3xTF32 split, "tc1" = single-pass TF32 (~1e-3 relative), "ffma" = fp32 CUDA-core kernel.
 CONV_BACKEND = "ws"
 _FMT = {"ws": "ws", "h3": "h", "tc3": 3, "tc1": 1}
+# 3-D layers under the "ws" back end: snb_conv_c32_ws has a 3-D variant (all 27 tap images resident, 3.4x less L2 traffic), but at
+# batch 1 its walk along the 24 disparity slices fills only 116 of 148 SMs and it measures 55-60 us per KITTI filter layer against
+# 52-56 us for the TMA kernel of conv3d_c32_tma.cu in the same fp16 operand format — so that one stays the product kernel for 3-D.
+WS_3D_FMT = "h"
+
+
+def _fmt(three_d):
+  f = _FMT[CONV_BACKEND]
+  return WS_3D_FMT if (f == "ws" and three_d) else f
 
 
 def set_conv_backend(name):
@@ -65,12 +74,12 @@ def set_conv_backend(name):
   bump_epoch()                 # cached weight images are in the previous backend's format
 
 
-def _tc_kw():
-  return dict(fmt=_FMT[CONV_BACKEND])
+def _tc_kw(three_d=False):
+  return dict(fmt=_fmt(three_d))
 
 
 def wprep_tc(conv, mode=0):
-  fmt = _FMT[CONV_BACKEND]
+  fmt = _fmt(conv.weight.dim() == 5)
   return _cached(conv, ("wtc", mode, fmt), [conv.weight], lambda: ops.prep_conv_weights_tc(conv.weight, mode, fmt=fmt))
 
 
@@ -78,7 +87,7 @@ def conv3x3_c32(x, conv, g, **kw):
   """Backend dispatch for the 'same' 3x3(x3) convolution + fused epilogue."""
   if CONV_BACKEND == "ffma":
     return ops.conv_c32(x, wprep(conv), g, **kw)
-  return ops.conv_c32_tc(x, wprep_tc(conv), g, **_tc_kw(), **kw)
+  return ops.conv_c32_tc(x, wprep_tc(conv), g, **_tc_kw(x.dim() == 5), **kw)
 
 
 def wprep(conv, mode=0):
@@ -106,7 +115,7 @@ def conv3x3_c32_dgrad(dy, conv, g, residual=None):
   """Data gradient of a stride-1 'same' 3x3(x3) conv: the same convolution kernels with flipped/transposed weights."""
   if CONV_BACKEND == "ffma":
     return ops.conv_c32(dy, wprep(conv, 1), g, residual=residual)
-  return ops.conv_c32_tc(dy, wprep_tc(conv, 1), g, residual=residual, **_tc_kw())
+  return ops.conv_c32_tc(dy, wprep_tc(conv, 1), g, residual=residual, **_tc_kw(dy.dim() == 5))
 
 
 def conv3x3_c32_wgrad(x, dz, g, wshape):
@@ -144,7 +153,7 @@ def conv5x5s2_first(img, conv):
 
 def wprep_tc_phases(conv, mode):
   """Tensor-core weight images of the four polyphase 3x3 sub-kernels of a 5x5 stride-2 conv (csrc/phase.cu)."""
-  fmt = _FMT[CONV_BACKEND]
+  fmt = _fmt(False)
 
   def make():
     w = conv.weight.detach()
@@ -166,9 +175,7 @@ class WeightPrepBatch:
 
   def __init__(self, nets, modes=(0, 1)):
     self.items = []                      # (conv, cache key, views, source pointer)
-    self.backend = CONV_BACKEND
-    fmt = _FMT[CONV_BACKEND]
-    fbit = ops._fmt_of(fmt)[0]
+    self.backend = (CONV_BACKEND, WS_3D_FMT)
     rows = []
     plan = []
     for net in nets:
@@ -178,6 +185,8 @@ class WeightPrepBatch:
         w = m.weight
         if tuple(w.shape[:2]) != (32, 32):
           continue
+        fmt = _fmt(w.dim() == 5)
+        fbit = ops._fmt_of(fmt)[0]
         if tuple(w.shape[2:]) in ((3, 3), (3, 3, 3)) and m.stride[0] == 1:
           kd = 3 if w.dim() == 5 else 1
           for mode in modes:
@@ -185,16 +194,16 @@ class WeightPrepBatch:
         elif tuple(w.shape[2:]) == (5, 5) and m.stride[0] == 2:
           for mode in modes:
             plan.append((m, ("wtc_phase", mode, fmt), [(3, mode | fbit, 1, a, b) for a in (0, 1) for b in (0, 1)]))
-    size = lambda nwin: ops.conv_weights_tc_floats(nwin // 3, fmt)
-    total = sum(size(cfg[0]) for _, _, cfgs in plan for cfg in cfgs)
+    size = lambda nwin, key: ops.conv_weights_tc_floats(nwin // 3, key[2])
+    total = sum(size(cfg[0], key) for _, key, cfgs in plan for cfg in cfgs)
     dev = plan[0][0].weight.device
     self.buf = torch.empty((total,), device=dev, dtype=torch.float32)
     off = 0
     for m, key, cfgs in plan:
       views = []
       for nwin, mode, kind, a, b in cfgs:
-        v = self.buf[off:off + size(nwin)]
-        off += size(nwin)
+        v = self.buf[off:off + size(nwin, key)]
+        off += size(nwin, key)
         views.append(v)
         rows.append([m.weight.data_ptr(), v.data_ptr(), nwin | (mode << 8) | (kind << 16) | (a << 24) | (b << 28), 0])
       self.items.append((m, key, views, m.weight.data_ptr()))
@@ -202,7 +211,7 @@ class WeightPrepBatch:
     self.n = len(rows)
 
   def valid(self):
-    return self.backend == CONV_BACKEND and all(m.weight.data_ptr() == ptr and m.weight.is_contiguous() for m, _, _, ptr in self.items)
+    return self.backend == (CONV_BACKEND, WS_3D_FMT) and all(m.weight.data_ptr() == ptr and m.weight.is_contiguous() for m, _, _, ptr in self.items)
 
   def refresh(self):
     ops.prep_conv_weights_tc_batch(self.table, self.n)

@@ -91,9 +91,9 @@ def test_weight_prep_batch_matches_per_layer_prep():
   for conv, key, views, _ in batch.items:
     mode = key[1]
     if key[0] == "wtc":
-      ref = ops.prep_conv_weights_tc(conv.weight, mode)
+      ref = ops.prep_conv_weights_tc(conv.weight, mode, fmt=key[2])
       assert torch.equal(views[0], ref), (key, tuple(conv.weight.shape))
-      slot = 9 * 3072 if conv.weight.dim() == 5 else 3072 + 16
+      slot = 3072 + 16
       assert float(views[0][slot]) in [2.0 ** -e for e in range(-20, 41)]    # the 2^-s slot
       n3x3 += 1
     else:
@@ -107,8 +107,8 @@ def test_weight_prep_batch_matches_per_layer_prep():
           # power-of-two scalings, so the images may differ but the convolutions they drive must not
           xs = torch.randn(1, 9, 40, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(a * 2 + b))
           g3 = ops.geom(tuple(xs.shape), 3)
-          y_b, _ = ops.conv_c32_tc(xs, views[i], g3)
-          y_l, _ = ops.conv_c32_tc(xs, ops.prep_conv_weights_tc(sub, mode), g3)
+          y_b, _ = ops.conv_c32_tc(xs, views[i], g3, fmt=key[2])
+          y_l, _ = ops.conv_c32_tc(xs, ops.prep_conv_weights_tc(sub, mode, fmt=key[2]), g3, fmt=key[2])
           assert float((y_b - y_l).abs().max()) <= 2e-6 * max(1.0, float(y_l.abs().max())), (key, a, b)
           i += 1
       n5x5 += 1
