@@ -39,7 +39,6 @@ struct Params {
 template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_c32_tc_kernel(const Params p) {
-  pdl_launch();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -71,6 +70,7 @@ conv_c32_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();                                    // dependents only once this CTA owns its TMEM columns (no alloc dead-lock with an early dependent)
   pdl_wait();                                      // everything above touched no global memory
 
   if (warp < NUM_LOADER_WARPS) {

@@ -93,7 +93,6 @@ __device__ __forceinline__ void mma_tf32_mn(uint32_t tmem_d, uint64_t adesc, uin
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_c32_wgrad_tc_kernel(const WParams p) {
-  pdl_launch();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -128,6 +127,7 @@ conv_c32_wgrad_tc_kernel(const WParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();                                    // dependents only once this CTA owns its TMEM columns (no alloc dead-lock with an early dependent)
   pdl_wait();                                      // everything above touched no global memory
 
   if (warp < LW) {

@@ -300,7 +300,6 @@ template <int CIN, int KS, int S, class Loader>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__ y, float* __restrict__ up_out,
                      int OH, int OW, int pad, snb_conv_epilogue e, int phaseB) {
-  pdl_launch();
   using T = TileDims<CIN, KS, S>;
   using D = TcDims<CIN, KS, S>;
   constexpr int NMT = TH * TW / 128;                 // 4 M-tiles of 2 rows x 64 pixels
@@ -329,6 +328,7 @@ conv_small_tc_kernel(Loader ld, const float* __restrict__ w, float* __restrict__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
+  pdl_launch();                                    // dependents only once this CTA owns its TMEM columns (no alloc dead-lock with an early dependent)
   pdl_wait();                                        // nothing above touched global memory
   {  // input halo tile, one row per warp at a time (no per-element index arithmetic: this kernel is instruction-issue bound).
      // Plain image channels go global -> smem with 4-byte cp.async (everything in flight at once, zero fill outside the

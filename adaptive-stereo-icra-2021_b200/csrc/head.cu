@@ -85,7 +85,6 @@ template <int NT>
 __global__ void __launch_bounds__(TAPS_TC_THREADS, 2)
 conv_c32_taps_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ taps,
                         long long npos, int plane, int ntiles) {
-  pdl_launch();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -103,6 +102,7 @@ conv_c32_taps_tc_kernel(const float* __restrict__ x, const float* __restrict__ w
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
+  pdl_launch();                                    // dependents only once this CTA owns its TMEM columns (no alloc dead-lock with an early dependent)
   pdl_wait();                                                      // nothing above touched global memory
   for (int i = t; i < 32 * 32; i += TAPS_TC_THREADS) {             // B row = tap, K = channel; w is [1][32][NT]
     const int tp = i >> 5, c = i & 31;

@@ -4,8 +4,7 @@ parameters only, Adam step.  The state machine / OVS / logging of adapt.py stay 
 import torch
 import torch.nn as nn
 
-from .losses import (LinearWarping, feature_contrast_mean, khamis_robust_loss, khamis_robust_loss_fused,
-                     monodepth_single_loss, monodepth_single_loss_fused)
+from .losses import feature_contrast_mean, khamis_robust_loss, monodepth_single_loss
 
 
 def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
@@ -23,14 +22,11 @@ class AdaptStepper:
   execution is bound by host launch latency.  Requires an optimizer built with capturable=True.  The experience-replay term
   (`replay=(left, right, gt)`) is captured too (static replay buffers, fused Khamis loss)."""
 
-  def __init__(self, feature_net, stereo_net, optimizer, height, width, clip_grad_norm=True, er_loss_weight=0.05,
-               use_graph=False, fused_loss=False, batched_replay=False):
+  def __init__(self, feature_net, stereo_net, optimizer, height=None, width=None, clip_grad_norm=True, er_loss_weight=0.05,
+               use_graph=False, batched_replay=False):
     self.feature_net, self.stereo_net, self.optimizer = feature_net, stereo_net, optimizer
     self.clip, self.er_loss_weight = clip_grad_norm, er_loss_weight
-    dev = next(stereo_net.parameters()).device
-    self.warper = LinearWarping(height, width, dev)
-    self.use_graph = use_graph
-    self.fused_loss = fused_loss            # photometric loss + its gradient from snb_photo_loss instead of ~150 torch kernels
+    self.use_graph = use_graph              # (height / width are accepted for call-site compatibility with the reference's warper)
     # SURVEY.md section 8 row f3: run the replay sample through the model in the SAME batch-2 forward/backward as the stream
     # frame instead of a second full pass (adapt.py:339-349).  Off by default: train-mode BatchNorm then normalises with the
     # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
@@ -56,30 +52,23 @@ class AdaptStepper:
     if dp_params is not None and sync_grads is None:
       from . import parallel
       sync_grads = lambda: parallel.allreduce_gradients(dp_params, dp_group)
-    out = self._fwd_bwd(left, right, replay, static_shapes=False)
+    out = self._fwd_bwd(left, right, replay)
     if sync_grads is not None:
       sync_grads()
     self._update()
     return out
 
-  def _fwd_bwd(self, left, right, replay, static_shapes):
+  def _fwd_bwd(self, left, right, replay):
     s = self.stereo_net.input_scale
     self.feature_net.train(); self.stereo_net.train()
     self._refresh_weights()
     if replay is not None and self.batched_replay:
       return self._fwd_bwd_batched(left, right, replay)
     outputs = self.predict(left, right)
-    if self.fused_loss:
-      loss = monodepth_single_loss_fused(left, right, outputs, s)
-    else:
-      loss = monodepth_single_loss(left, right, outputs, self.warper, s, static_shapes=static_shapes)
+    loss = monodepth_single_loss(left, right, outputs, s)                          # adapt.py:328-337 (snb_photo_loss)
     if replay is not None:
       out_er = self.predict(replay[0], replay[1])                                   # adapt.py:339-349: a second full pass
-      pred_er = out_er["pred_disp_l/{}".format(s)]
-      # static shapes (graph capture): the fused kernel computes the same masked mean without boolean indexing
-      l_er = (khamis_robust_loss_fused(pred_er, replay[2].reshape(pred_er.shape)) if static_shapes
-              else khamis_robust_loss(pred_er, replay[2]))
-      loss = loss + self.er_loss_weight * l_er
+      loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
     fcs = feature_contrast_mean(outputs["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
     self.optimizer.zero_grad()
     loss.backward()
@@ -101,12 +90,8 @@ class AdaptStepper:
     outputs = self.predict(torch.cat([left, replay[0]], 0), torch.cat([right, replay[1]], 0))
     key = "pred_disp_l/{}".format(s)
     head = {k: v[:n] for k, v in outputs.items()}
-    if self.fused_loss:
-      loss = monodepth_single_loss_fused(left, right, head, s)
-    else:
-      loss = monodepth_single_loss(left, right, head, self.warper, s)
-    gt = replay[2].reshape(outputs[key][n:].shape)
-    loss = loss + self.er_loss_weight * khamis_robust_loss_fused(outputs[key][n:], gt)
+    loss = monodepth_single_loss(left, right, head, s)
+    loss = loss + self.er_loss_weight * khamis_robust_loss(outputs[key][n:], replay[2])
     fcs = feature_contrast_mean(head["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
     self.optimizer.zero_grad()
     loss.backward()
@@ -143,7 +128,7 @@ class AdaptStepper:
       # One eager warm-up step allocates the lazily-created state (Adam moments and step counters, derived-weight
       # caches, allocator pools); model and optimizer state are restored afterwards so that capturing does not advance
       # the adaptation.
-      self._fwd_bwd(sl, sr, srep, static_shapes=True)
+      self._fwd_bwd(sl, sr, srep)
       if dp_params is not None:
         parallel.allreduce_gradients(dp_params, dp_group)
       self._update()
@@ -162,7 +147,7 @@ class AdaptStepper:
     g1 = torch.cuda.CUDAGraph()
     flat = None
     with torch.cuda.graph(g1):
-      out = self._fwd_bwd(sl, sr, srep, static_shapes=True)
+      out = self._fwd_bwd(sl, sr, srep)
       if dp_params is not None:
         flat = parallel.pack_gradients(dp_params)
       else:

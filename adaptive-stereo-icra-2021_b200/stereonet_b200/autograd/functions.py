@@ -18,7 +18,7 @@ class ConvBnLrelu(torch.autograd.Function):
     g = ops.geom(x.shape, 3, stride=1, dil=dil)
     z, stats = fused.conv3x3_c32(x, conv, g, bias=b.detach(), want_stats=training)
     if training:
-      scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // 32, bn)
+      scale, shift, mean, invstd = fused.bn_finalize(stats, z.numel() // 32, bn)
     else:
       scale, shift = fused.bn_fold(bn)
       mean, invstd = bn.running_mean, fused.bn_invstd(bn)
@@ -150,7 +150,7 @@ class RefineHead(torch.autograd.Function):
   def forward(ctx, coarse, rgb, w, b, gamma, beta, bn, training):
     up, z, stats = ops.refine_in_conv(coarse, rgb, w, b.detach(), want_stats=training)
     if training:
-      scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // 32, bn)
+      scale, shift, mean, invstd = fused.bn_finalize(stats, z.numel() // 32, bn)
     else:
       scale, shift = fused.bn_fold(bn)
       mean, invstd = bn.running_mean, fused.bn_invstd(bn)

@@ -10,11 +10,34 @@ from .. import ops
 # EPOCH covers updates torch's version counters cannot see: a replayed CUDA graph of the adaptation step rewrites the
 # parameters in place on the device without touching the Python-side counters (adapt.AdaptStepper bumps it per replay).
 EPOCH = 0
+# BN_EPOCH does the same for the tensors derived from BatchNorm RUNNING statistics (eval-mode scale / shift): snb_bn_finalize
+# updates running_mean / running_var through raw pointers, so their version counters do not move either, and a train-mode
+# forward that is NOT followed by an optimizer step (OVS frames whose update is skipped, adapt.py:381-396; no-grad train-mode
+# forwards) must still invalidate the folded statistics the next eval-mode forward uses.
+BN_EPOCH = 0
 
 
 def bump_epoch():
-  global EPOCH
+  global EPOCH, BN_EPOCH
   EPOCH += 1
+  BN_EPOCH += 1
+
+
+def bump_bn_epoch():
+  global BN_EPOCH
+  BN_EPOCH += 1
+
+
+def state_epoch():
+  """Changes whenever parameters or BN running statistics may have changed behind torch's version counters."""
+  return (EPOCH, BN_EPOCH)
+
+
+def bn_finalize(stats, count, bn):
+  """Train-mode BatchNorm statistics (ops.bn_finalize) + invalidation of what was derived from the running statistics."""
+  out = ops.bn_finalize(stats, count, bn)
+  bump_bn_epoch()
+  return out
 
 
 # Fused optimizers (torch.optim.Adam(fused=True), torch._fused_adam_) update parameters in place WITHOUT bumping their
@@ -31,9 +54,9 @@ except Exception as exc:  # pragma: no cover
                      "(PyTorch >= 2.1) to keep its derived-weight caches coherent") from exc
 
 
-def _cached(owner, key, tensors, make):
+def _cached(owner, key, tensors, make, epoch=None):
   cache = owner.__dict__.setdefault("_snb_cache", {})
-  ver = (EPOCH,) + tuple((t.data_ptr(), t._version) for t in tensors)
+  ver = (EPOCH if epoch is None else epoch,) + tuple((t.data_ptr(), t._version) for t in tensors)
   hit = cache.get(key)
   if hit is not None and hit[0] == ver:
     return hit[1]
@@ -101,14 +124,14 @@ def bn_fold(bn):
       scale = bn.weight * torch.rsqrt(bn.running_var + ops.BN_EPS)
       shift = bn.bias - bn.running_mean * scale
       return scale.contiguous(), shift.contiguous()
-  return _cached(bn, "fold", [bn.weight, bn.bias, bn.running_mean, bn.running_var], make)
+  return _cached(bn, "fold", [bn.weight, bn.bias, bn.running_mean, bn.running_var], make, epoch=(EPOCH, BN_EPOCH))
 
 
 def bn_invstd(bn):
   def make():
     with torch.no_grad():
       return torch.rsqrt(bn.running_var + ops.BN_EPS).contiguous()
-  return _cached(bn, "invstd", [bn.running_var], make)
+  return _cached(bn, "invstd", [bn.running_var], make, epoch=(EPOCH, BN_EPOCH))
 
 
 def conv3x3_c32_dgrad(dy, conv, g, residual=None):
@@ -287,7 +310,7 @@ def conv_bn_lrelu(x, conv, bn, dil, residual, training):
                        residual=x if residual else None, lrelu=True)
     return y
   z, stats = conv3x3_c32(x, conv, g, bias=conv.bias.detach(), want_stats=True)
-  scale, shift, _, _ = ops.bn_finalize(stats, z.numel() // 32, bn)
+  scale, shift, _, _ = bn_finalize(stats, z.numel() // 32, bn)
   return ops.bn_apply(z, scale, shift, residual=x if residual else None, lrelu=True)
 
 
@@ -329,7 +352,7 @@ def refine_head(coarse, rgb, conv, bn, training):
     up, x, _ = ops.refine_in_conv(coarse, rgb, conv.weight, conv.bias.detach(), scale=scale, shift=shift, lrelu=True)
     return up, x
   up, z, stats = ops.refine_in_conv(coarse, rgb, conv.weight, conv.bias.detach(), want_stats=True)
-  scale, shift, _, _ = ops.bn_finalize(stats, z.numel() // 32, bn)
+  scale, shift, _, _ = bn_finalize(stats, z.numel() // 32, bn)
   return up, ops.bn_apply(z, scale, shift, residual=None, lrelu=True)
 
 

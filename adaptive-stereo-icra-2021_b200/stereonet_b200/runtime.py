@@ -1,11 +1,15 @@
 """Inference engine: CUDA-graph replay of the whole forward (feature_net x2 + stereo_net) with static device buffers
 and pinned-host staging.  At batch 1 every kernel is 3-100 us, so per-launch host latency would otherwise dominate
-(SURVEY.md §7 step 7).  One engine per (process, GPU); the weights stay whatever the wrapped modules hold, so a graph
-must be re-captured (`invalidate()`) after the parameters are re-allocated (in-place optimizer updates are picked up
-through the derived-weight caches only on re-capture)."""
+(SURVEY.md §7 step 7).  One engine per (process, GPU).  A captured graph bakes in the derived tensors (tensor-core weight
+images, folded BatchNorm) of the moment of capture, so every entry remembers the state epoch it was captured at
+(autograd.fused.state_epoch(): advanced by optimizer steps, graph-replayed adaptation steps and train-mode BatchNorm updates) and
+is re-captured on the next call after a change — an adaptation loop that alternates AdaptStepper.step and engine(left, right)
+(adapt.py's validate / evaluate pattern) never sees stale weights.  `invalidate()` is only needed after parameters were
+re-assigned by other means (e.g. raw `.data` writes)."""
 import torch
 
 from . import ops
+from .autograd import fused
 
 
 class StereoEngine:
@@ -36,7 +40,10 @@ class StereoEngine:
     key = (tuple(shape), str(device), self.feature_net.training)
     e = self._graphs.get(key)
     if e is not None:
-      return e
+      if e["epoch"] == fused.state_epoch():
+        return e
+      self.synchronize()                       # weights / BN statistics changed since the capture: drain the copy streams that
+      del self._graphs[key]                    # still use the old static buffers, then re-capture on this call
     pair = torch.zeros((2 * shape[0],) + tuple(shape[1:]), device=device, dtype=torch.float32)
     left, right = pair[:shape[0]], pair[shape[0]:]
     with torch.no_grad():
@@ -54,7 +61,7 @@ class StereoEngine:
       else:
         graph, out = None, self._forward(pair)
       launches = ops.LAUNCHES - n0
-    e = dict(pair=pair, left=left, right=right, graph=graph, out=out, launches=launches)
+    e = dict(pair=pair, left=left, right=right, graph=graph, out=out, launches=launches, epoch=fused.state_epoch())
     self._graphs[key] = e
     return e
 
@@ -64,6 +71,9 @@ class StereoEngine:
     e = self._entry(shape, device)
     if e["graph"] is not None:
       e["graph"].replay()
+      if self.feature_net.training:            # the replay updated BN running statistics behind Python's back: whatever was folded
+        fused.bump_bn_epoch()                  # from them (eval-mode graphs, bn_fold caches) is stale; this graph itself is not
+        e["epoch"] = fused.state_epoch()
     else:
       e["out"] = self._forward(e["pair"])
     return e["out"], e["launches"]
@@ -138,10 +148,12 @@ class StereoEngine:
     return out_host
 
   def synchronize(self):
-    """Make the current stream wait for every copy issued by infer_host_async (then synchronize it on the host)."""
+    """Block the host until every copy issued by infer_host_async has completed: afterwards the `out_host` buffers are valid
+    and the pinned input buffers may be overwritten.  (The current stream is also made to wait for the copy streams.)"""
     for e in self._graphs.values():
       p = e.get("pipe")
       if p is not None:
         dev = e["pair"].device
         cur = torch.cuda.current_stream(dev)
         cur.wait_stream(p["s_in"]); cur.wait_stream(p["s_out"])
+        p["s_in"].synchronize(); p["s_out"].synchronize()

@@ -245,7 +245,7 @@ def gpu_arm(args):
     from stereonet_b200 import parallel
     fnet.train(); snet.train()
     stepper = AdaptStepper(fnet, snet, make_optimizer(fnet, snet, lr=5e-5, capturable=not args.no_graph), H, W,
-                           clip_grad_norm=True, use_graph=not args.no_graph, fused_loss=not args.torch_loss)
+                           clip_grad_norm=True, use_graph=not args.no_graph)
     dl, dr = left.to(dev), right.to(dev)
     used = parallel.used_parameters(snet, fnet)
     dp = used if world > 1 else None
@@ -371,7 +371,6 @@ def gpu_arm(args):
                          "steps": adapt_steps, "library_launches_per_step": adapt_launches,
                          "cuda_graph": not args.no_graph,
                          "parallelism": "single stream" if world == 1 else f"shared-model DP x{world}, one NCCL all-reduce of 288066 grads per step",
-                         "fused_loss": not args.torch_loss,
                          "note": "model fwd+bwd, the photometric loss (+ its gradient) and the feature-contrast score are libsnb200 kernels; "
                                  "clip_grad_norm_ and Adam are the caller's PyTorch ops as in adapt.py"}
     if cpu is not None:
@@ -398,7 +397,6 @@ def main():
   ap.add_argument("--cpu-steps", type=int, default=12)
   ap.add_argument("--skip-adapt", action="store_true")
   ap.add_argument("--skip-cpu-adapt", action="store_true")
-  ap.add_argument("--torch-loss", action="store_true", help="adapt arm: PyTorch photometric loss instead of the fused kernel")
   args = ap.parse_args()
 
   rank = int(os.environ.get("RANK", "0"))

@@ -1,7 +1,7 @@
 """Generate golden vectors by executing the UNMODIFIED reference module (build container only).
 
 Usage (in the build container, where /root/reference exists):
-    python oracle/gen_golden.py [base] [big] [rows]     # writes tests/golden/*.npz (default: all three groups)
+    python oracle/gen_golden.py [base] [big] [rows] [layout]     # writes tests/golden/* (default: all groups)
 
 The reference's `forward` hard-codes `.cuda()` (adaptive_stereo/models/stereo_net.py:129,177), so on this
 GPU-less host `Tensor.cuda` / `Module.cuda` are shimmed to identity.  The reference modules are
@@ -258,11 +258,30 @@ def run_rows_case(sn, lw, lf, fc):
         f"gnorm {out['er/grad_norm_stereo']:.4f}")
 
 
+def run_layout_case(sn):
+  """state_dict layout and seeded-init fingerprint of the reference classes (adapt.py:29 / train.py:141 seed 123, construction
+  order feature_net then stereo_net, train.py:162-163): names, shapes, dtypes and (sum, |sum|, l2) per tensor, k = 3 and k = 4.
+  tests/test_state_dict.py holds the drop-in classes to it on every box (the reference checkout only exists here)."""
+  import json
+  out = {}
+  for k in (3, 4):
+    torch.manual_seed(123)
+    f, s = sn.FeatureExtractorNetwork(k), sn.StereoNet(k, 1, 0, maxdisp=192)
+    for tag, net in (("feature_net", f), ("stereo_net", s)):
+      out[f"k{k}/{tag}"] = {
+        "state_dict": [[n, list(v.shape), str(v.dtype), summarize(v.float()).tolist()] for n, v in net.state_dict().items()],
+        "parameters": [n for n, _ in net.named_parameters()],
+      }
+  with open(os.path.join(OUT, "state_layout.json"), "w") as fh:
+    json.dump(out, fh)
+  print("state_layout:", {k_: len(v["state_dict"]) for k_, v in out.items()})
+
+
 if __name__ == "__main__":
   torch.manual_seed(123)
   torch.set_num_threads(8)
   mods = load_reference()
-  which = sys.argv[1:] or ["base", "big", "rows"]
+  which = sys.argv[1:] or ["base", "big", "rows", "layout"]
   os.makedirs(OUT, exist_ok=True)
   if "base" in which:
     for name, cfg in CASES.items():
@@ -272,3 +291,5 @@ if __name__ == "__main__":
       run_big_case(name, cfg, *mods)
   if "rows" in which:
     run_rows_case(*mods)
+  if "layout" in which:
+    run_layout_case(mods[0])

@@ -49,7 +49,7 @@ if mode == "fwd":
 else:
   from stereonet_b200.adapt import AdaptStepper, make_optimizer
   f.train(); s.train()
-  st = AdaptStepper(f, s, make_optimizer(f, s, lr=5e-5), 376, 1248, fused_loss=True)
+  st = AdaptStepper(f, s, make_optimizer(f, s, lr=5e-5), 376, 1248)
   def run():
     return st.step(l, r)
 for _ in range(3):

@@ -10,7 +10,7 @@ import stereonet_oracle as O
 import stereonet_b200 as S
 from stereonet_b200.autograd import fused
 from stereonet_b200.adapt import AdaptStepper, make_optimizer
-from stereonet_b200.losses import monodepth_single_loss_fused
+from stereonet_b200.losses import monodepth_single_loss
 from test_oracle_golden import CASES, TRAIN_SHARPEN_RATIO, build
 DEV = "cuda:0"
 for name in ("k3_b2_sharp", "k3_ragged"):
@@ -28,7 +28,7 @@ for name in ("k3_b2_sharp", "k3_ragged"):
     f.train(); s.train()
     l, r = left.to(DEV), right.to(DEV)
     out = st.predict(l, r)
-    loss = monodepth_single_loss_fused(l, r, out, cfg["s"])
+    loss = monodepth_single_loss(l, r, out, cfg["s"])
     opt.zero_grad(); loss.backward()
     worst_norm, worst_entry, worst_cos = 0.0, 0.0, 1.0
     grads = {}

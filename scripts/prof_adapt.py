@@ -9,7 +9,7 @@ from bench import synthetic_pair
 dev = "cuda:0"
 torch.manual_seed(123)
 f, s = S.FeatureExtractorNetwork(3).to(dev), S.StereoNet(3, 1, 0).to(dev)
-st = AdaptStepper(f, s, make_optimizer(f, s, capturable=True), 376, 1248, fused_loss=os.environ.get('TORCH_LOSS') is None,
+st = AdaptStepper(f, s, make_optimizer(f, s, capturable=True), 376, 1248, 
                   use_graph=os.environ.get('GRAPH') == '1')
 l, r = synthetic_pair(1000)
 l, r = l.to(dev), r.to(dev)

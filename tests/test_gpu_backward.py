@@ -164,9 +164,9 @@ def test_refinement_backward(training):
     close(prm.grad.cpu(), sd[p + n].grad, 2e-2 if training else 5e-3, n)
 
 
-@pytest.mark.parametrize("fused_loss", [False, True])
+@pytest.mark.parametrize("loss_impl", ["oracle", "fused"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["train"]])
-def test_adapt_step_vs_reference_golden(name, fused_loss):
+def test_adapt_step_vs_reference_golden(name, loss_impl):
   """One full adaptation step (adapt.py:313-337,381-394) on the GPU vs the reference's own step (golden vectors).
 
   Tolerances: the reference gradient itself is ill-conditioned at this size — perturbing the input images by 1e-7
@@ -175,7 +175,7 @@ def test_adapt_step_vs_reference_golden(name, fused_loss):
   BN; measured with the oracle on the CPU).  The bounds below sit just outside that band; the
   layer-level tests in this file, which use exactly representable data, pin every backward kernel to 2e-5."""
   from stereonet_b200.adapt import AdaptStepper, make_optimizer
-  from stereonet_b200.losses import monodepth_single_loss, monodepth_single_loss_fused
+  from stereonet_b200.losses import monodepth_single_loss
   cfg = CASES[name]
   g = np.load(os.path.join(GOLD, name + ".npz"))
   fsd, _, left, right, _ = build(cfg)
@@ -187,10 +187,10 @@ def test_adapt_step_vs_reference_golden(name, fused_loss):
   f.train(); s.train()
   l, r = left.to(DEV), right.to(DEV)
   outputs = stepper.predict(l, r)
-  if fused_loss:     # snb_photo_loss (row f1) against the reference's own loss value and gradients
-    loss = monodepth_single_loss_fused(l, r, outputs, cfg["s"])
-  else:
-    loss = monodepth_single_loss(l, r, outputs, stepper.warper, cfg["s"])
+  if loss_impl == "fused":     # snb_photo_loss (row f1, the product path) against the reference's own loss value and gradients
+    loss = monodepth_single_loss(l, r, outputs, cfg["s"])
+  else:                        # the oracle's torch restatement of adapt.py:78-86 seeds the CUDA backward instead (isolates the model)
+    loss = O.monodepth_single_loss(l, r, outputs["pred_disp_l/{}".format(cfg["s"])])
   opt.zero_grad()
   loss.backward()
   print(f"[parity] {name} loss {loss.item():.7f} vs reference {float(g['train/loss']):.7f}")
@@ -327,20 +327,19 @@ def test_adapt_step_cuda_graph_matches_eager():
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 37, 90), (2, 64, 130), (1, 376, 1248)])
-def test_fused_photo_loss_matches_torch(B, H, W):
+def test_fused_photo_loss_matches_oracle(B, H, W):
   """snb_photo_loss (warp + SSIM + L1 + edge-aware smoothness + masked mean, value and d/d disp fused)
-  against the plain-PyTorch mirror of the reference loss (losses.monodepth_single_loss, autograd) on the same GPU."""
-  from stereonet_b200.losses import LinearWarping, monodepth_single_loss, monodepth_single_loss_fused
+  against the oracle's plain-PyTorch restatement of the reference loss (O.monodepth_single_loss, autograd)."""
+  from stereonet_b200.losses import monodepth_single_loss
   left, right, gt = O.make_stereo_pair(B, H, W, seed=1000, max_disp_px=min(60.0, W / 4))
   g = torch.Generator().manual_seed(5)
   disp = (gt.clamp(min=0) + 3.0 * torch.rand(B, 1, H, W, generator=g) + 1.0).to(DEV)       # positive, textured, some pixels invalid
   l, r = left.to(DEV), right.to(DEV)
-  warper = LinearWarping(H, W, torch.device(DEV))
   d_ref = disp.clone().requires_grad_()
-  loss_ref = monodepth_single_loss(l, r, {"pred_disp_l/0": d_ref}, warper, 0)
+  loss_ref = O.monodepth_single_loss(l, r, d_ref)
   loss_ref.backward()
   d_fused = disp.clone().requires_grad_()
-  loss_fused = monodepth_single_loss_fused(l, r, {"pred_disp_l/0": d_fused}, 0)
+  loss_fused = monodepth_single_loss(l, r, {"pred_disp_l/0": d_fused}, 0)
   (2.0 * loss_fused).backward()                                       # exercises the grad_output scaling
   assert abs(loss_fused.item() - loss_ref.item()) <= 2e-6 * max(1.0, abs(loss_ref.item())), (loss_fused.item(), loss_ref.item())
   gr, gf = d_ref.grad, d_fused.grad / 2.0
@@ -353,8 +352,9 @@ def test_fused_photo_loss_matches_torch(B, H, W):
   assert cos > 0.99999, cos
 
 
-def test_adapt_step_fused_loss_matches_torch_loss():
-  """Three adaptation steps with fused_loss=True leave the same weights as with the PyTorch loss."""
+def test_adapt_step_fused_loss_matches_oracle_loss():
+  """Three graph-replayed adaptation steps (snb_photo_loss inside) leave the same weights as three eager steps whose loss is
+  the oracle's plain-PyTorch restatement of adapt.py:78-86 (autograd seeds the same CUDA backward)."""
   from stereonet_b200.adapt import AdaptStepper, make_optimizer
   k, Hh, Ww = 3, 96, 256
   fsd, ssd = O.make_feature_state(k, 11), O.make_stereo_state(22, sharpen=10.0)
@@ -363,12 +363,23 @@ def test_adapt_step_fused_loss_matches_torch_loss():
   for fused_loss in (False, True):
     f = S.FeatureExtractorNetwork(k).to(DEV); s = S.StereoNet(k, 1, 0).to(DEV)
     f.load_state_dict(fsd); s.load_state_dict(ssd)
-    st = AdaptStepper(f, s, make_optimizer(f, s, lr=5e-5, capturable=True), Hh, Ww, use_graph=fused_loss, fused_loss=fused_loss)
-    losses = [st.step(l.to(DEV), r.to(DEV))[0].item() for l, r in frames]
+    opt = make_optimizer(f, s, lr=5e-5, capturable=True)
+    st = AdaptStepper(f, s, opt, Hh, Ww, use_graph=fused_loss)
+    if fused_loss:
+      losses = [st.step(l.to(DEV), r.to(DEV))[0].item() for l, r in frames]
+    else:
+      losses = []
+      f.train(); s.train()
+      for l, r in frames:
+        l, r = l.to(DEV), r.to(DEV)
+        loss = O.monodepth_single_loss(l, r, st.predict(l, r)["pred_disp_l/0"])
+        opt.zero_grad(); loss.backward(); st._update()
+        losses.append(loss.item())
     torch.cuda.synchronize()
     res.append((losses, {n: v.detach().cpu().clone() for n, v in s.state_dict().items()}))
   (la, wa), (lb, wb) = res
-  assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-5, (la, lb)
+  # step 1 runs on identical weights; later steps on weights that may have drifted by up to 2*lr per entry (below)
+  assert abs(la[0] - lb[0]) < 2e-5 and max(abs(a - b) for a, b in zip(la, lb)) < 3e-4, (la, lb)
   # Adam's first steps move every weight by ~lr * sign(gradient): entries whose tiny gradient differs in rounding (the
   # backward pass is ill-conditioned through the LeakyReLU / batch-stat BN kinks) land up to 2*lr apart,
   # so compare the accumulated UPDATE as a direction and bound single entries by the step budget (3 steps x 2 x lr).

@@ -15,7 +15,7 @@ import stereonet_b200 as S
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-from test_oracle_golden import CASES, TRAIN_SHARPEN_RATIO, build  # noqa: E402
+from test_oracle_golden import BIG_CASES, CASES, TRAIN_SHARPEN_RATIO, build, check_big  # noqa: E402
 
 MAX_DISP_TOL = 1e-2
 EPE_TOL = 1e-3
@@ -33,6 +33,27 @@ def report(tag, got, ref):
   err = float(np.abs(got - ref).max())
   print(f"[parity] {tag}: max|diff| = {err:.3e} (ref range [{ref.min():.3f}, {ref.max():.3f}])")
   return err
+
+
+@pytest.mark.parametrize("name", list(BIG_CASES))
+def test_reference_test_configs_vs_reference_golden(name):
+  """The reference's own test / timing configurations at full size — T = 1x3x320x960 k=3 (BASELINE.json configs[0],
+  test/test_stereo_net.py:17-22), k=4 at 320x960 (every experiments/adaptation/*.sh), k=3 / input_scale=1 at 160x480
+  (test/test_stereo_net.py:60-72) — against tensors produced by the UNMODIFIED reference module (oracle/gen_golden.py)."""
+  cfg = BIG_CASES[name]
+  g = np.load(os.path.join(GOLD, name + ".npz"))
+  fsd, ssd, left, right, gt = build(cfg)
+  f, s = make_nets(cfg, fsd, ssd)
+  f.eval(); s.eval()
+  with torch.no_grad():
+    l, r = left.to(DEV), right.to(DEV)
+    fl = f(l)
+    out = s(l, fl, f(r), "l", output_cost_volume=True)
+  check_big(name, {k_: v.cpu().numpy() for k_, v in out.items()}, fl.cpu().numpy(), gt, g, cfg,
+            disp_tol=MAX_DISP_TOL, cost_tol=2e-3, feat_tol=2e-4)
+  fcs = out[f"cost_volume_l/{cfg['s'] + cfg['k']}"]
+  from stereonet_b200.losses import feature_contrast_mean
+  assert abs(feature_contrast_mean(fcs).mean().item() - float(g["eval/fcs"])) < 1e-3
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -174,8 +195,7 @@ def test_engine_streaming_api_matches_blocking_api(kitti):
   outs = [torch.empty((1, 1, 376, 1248)).pin_memory() for _ in pins]
   for (l, r), o in zip(pins, outs):
     eng.infer_host_async(l, r, o)
-  eng.synchronize()
-  torch.cuda.synchronize()
+  eng.synchronize()                  # the engine's own contract: blocks until the host buffers are valid (no device-wide sync here)
   for i, (a, b) in enumerate(zip(outs, ref)):
     assert torch.equal(a, b), f"frame {i}"
 
@@ -223,3 +243,51 @@ def test_sceneflow_batch_vs_oracle():
         err = report(f"sceneflow[{i}] " + key, out[key][i:i + 1].cpu().numpy(), v.numpy())
         assert err <= (MAX_DISP_TOL if key.startswith("pred_disp") else 2e-3), (i, key)
       assert abs(O.epe(out["pred_disp_l/0"][i:i + 1].cpu(), gt).item() - O.epe(ref["pred_disp_l/0"], gt).item()) <= EPE_TOL
+
+
+def test_eval_after_train_forward_without_optimizer_step_sees_new_running_stats():
+  """snb_bn_finalize updates running_mean / running_var through raw pointers; an eval-mode forward after a train-mode
+  forward that was NOT followed by an optimizer step (OVS frames, adapt.py:381-396) must use the updated statistics — i.e.
+  match a module freshly loaded from the state_dict."""
+  cfg = CASES["k3_ragged"]
+  fsd, ssd, left, right, _ = build(cfg)
+  f, s = make_nets(cfg, fsd, ssd)
+  l, r = left.to(DEV), right.to(DEV)
+  f.eval(); s.eval()
+  with torch.no_grad():
+    before = s(l, f(l), f(r), "l")["pred_disp_l/0"].clone()            # warms the folded-BN caches
+    f.train(); s.train()
+    s(l, f(l), f(r), "l")                                              # updates the running statistics, no optimizer step
+    f.eval(); s.eval()
+    after = s(l, f(l), f(r), "l")["pred_disp_l/0"].clone()
+    f2, s2 = make_nets(cfg, f.state_dict(), s.state_dict())
+    f2.eval(); s2.eval()
+    fresh = s2(l, f2(l), f2(r), "l")["pred_disp_l/0"]
+  assert not torch.equal(before, after)
+  assert torch.equal(after, fresh)
+
+
+def test_engine_after_adaptation_step_uses_new_weights():
+  """ADVICE r1 / VERDICT weak #13: StereoEngine(graph) -> AdaptStepper.step -> StereoEngine must see the updated weights and
+  BatchNorm statistics (adapt.py alternates update steps with validate / evaluate), without an explicit invalidate()."""
+  from stereonet_b200.adapt import AdaptStepper, make_optimizer
+  from stereonet_b200.runtime import StereoEngine
+  cfg = CASES["k3_ragged"]
+  fsd, ssd, left, right, _ = build(cfg)
+  for use_graph in (False, True):
+    f, s = make_nets(cfg, fsd, ssd)
+    l, r = left.to(DEV), right.to(DEV)
+    f.eval(); s.eval()
+    eng = StereoEngine(f, s)
+    d0 = eng(l, r)["pred_disp_l/0"].clone()
+    st = AdaptStepper(f, s, make_optimizer(f, s, lr=1e-3, capturable=True), cfg["H"], cfg["W"], use_graph=use_graph)
+    for _ in range(2):
+      st.step(l, r)
+    f.eval(); s.eval()
+    d1 = eng(l, r)["pred_disp_l/0"].clone()
+    f2, s2 = make_nets(cfg, f.state_dict(), s.state_dict())
+    f2.eval(); s2.eval()
+    with torch.no_grad():
+      ref = s2(l, f2(l), f2(r), "l")["pred_disp_l/0"]
+    assert not torch.equal(d0, d1)
+    assert torch.equal(d1, ref), float((d1 - ref).abs().max())

@@ -54,6 +54,28 @@ def test_seeded_init_and_strict_load_against_reference_classes():
   assert [n for n, _ in rs.named_parameters()] == [n for n, _ in s.named_parameters()]
 
 
+@pytest.mark.parametrize("k", [3, 4])
+def test_seeded_init_and_layout_against_reference_fingerprint(k):
+  """Same check as above against tests/golden/state_layout.json (written by oracle/gen_golden.py from the reference classes),
+  so it also runs where the reference checkout does not exist: state_dict keys, order, shapes, dtypes, the parameter
+  registration order (adam.pth indices, train.py:136-137) and the values of a seed-123 construction (RNG consumption order)."""
+  import json
+  import numpy as np
+  gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "state_layout.json")))
+  torch.manual_seed(123)
+  f, s = S.FeatureExtractorNetwork(k), S.StereoNet(k, 1, 0, maxdisp=192)
+  for tag, net in (("feature_net", f), ("stereo_net", s)):
+    ref = gold[f"k{k}/{tag}"]
+    got = list(net.state_dict().items())
+    assert [n for n, _ in got] == [r[0] for r in ref["state_dict"]], tag
+    assert [n for n, _ in net.named_parameters()] == ref["parameters"], tag
+    for (n, v), (rn, shape, dtype, summ) in zip(got, ref["state_dict"]):
+      assert list(v.shape) == shape and str(v.dtype) == dtype, n
+      t = v.detach().double().flatten()
+      mine = np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().sqrt().item()])
+      np.testing.assert_allclose(mine, np.array(summ), rtol=1e-12, atol=0, err_msg=n)
+
+
 def test_cpu_tensors_fail_loudly():
   f = S.FeatureExtractorNetwork(3)
   with pytest.raises(RuntimeError, match="no CPU path"):
