@@ -8,4 +8,40 @@ from .models.stereo_net import (FeatureExtractorNetwork, StereoNet, EdgeAwareRef
                                 BasicBlock, convbn, convbn_3d)
 
 __all__ = ["FeatureExtractorNetwork", "StereoNet", "EdgeAwareRefinement", "DisparityRegression", "BasicBlock",
-           "convbn", "convbn_3d"]
+           "convbn", "convbn_3d", "install"]
+
+
+def install(short_names=True):
+  """Make `adaptive_stereo.models.stereo_net` (and, with short_names, `models.stereo_net` as test/test_stereo_net.py:10 imports it)
+  resolve to this drop-in in the running interpreter, leaving every other reference module (adaptive_stereo.utils.*, .datasets.*,
+  models.linear_warping, ...) where it is.  Call it before the reference's entry points import the model; idempotent.  The static
+  alternative is the namespace-package shim directory `adaptive-stereo-icra-2021_b200/shim`."""
+  import importlib
+  import sys
+  import types
+  from .models import stereo_net as impl
+
+  def ensure_pkg(name):
+    try:
+      return importlib.import_module(name)
+    except ImportError:
+      pkg = types.ModuleType(name)
+      pkg.__path__ = []                      # a package without files of its own
+      sys.modules[name] = pkg
+      parent, _, leaf = name.rpartition(".")
+      if parent:
+        setattr(ensure_pkg(parent), leaf, pkg)
+      return pkg
+
+  installed = []
+  for full in (["adaptive_stereo.models.stereo_net"] + (["models.stereo_net"] if short_names else [])):
+    parent, _, leaf = full.rpartition(".")
+    mod = types.ModuleType(full)
+    mod.__doc__ = "stereonet_b200 drop-in for " + full
+    for n in ("FeatureExtractorNetwork", "StereoNet", "DisparityRegression", "EdgeAwareRefinement", "BasicBlock", "convbn", "convbn_3d"):
+      setattr(mod, n, getattr(impl, n))
+    mod.__all__ = [n for n in dir(mod) if not n.startswith("_")]
+    sys.modules[full] = mod
+    setattr(ensure_pkg(parent), leaf, mod)
+    installed.append(full)
+  return installed

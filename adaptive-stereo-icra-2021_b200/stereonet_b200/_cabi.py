@@ -78,6 +78,9 @@ SIGNATURES = {
   "snb_khamis_loss": (_I, [_P, _P, _P, _P, _P, _LL, _P]),
   "snb_khamis_loss_workspace_floats": (_I, [_LL]),
   "snb_eval_metrics": (_I, [_P, _P, _P, _I, _LL, _P]),
+  "snb_multi_gather": (_I, [_P, _P, _P, _I, _P, _P]),
+  "snb_adam_clip_step": (_I, [_P, _I, _P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _P, _P]),
+  "snb_adam_clip_workspace_bytes": (_I, []),
 }
 
 _lib = None

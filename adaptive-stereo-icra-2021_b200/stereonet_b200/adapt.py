@@ -7,9 +7,14 @@ import torch.nn as nn
 from .losses import feature_contrast_mean, khamis_robust_loss, monodepth_single_loss
 
 
-def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False):
-  """adapt.py:208-210: two parameter groups, stereo_net first.  capturable=True keeps Adam's step counters on the device
+def make_optimizer(feature_net, stereo_net, lr=5e-5, capturable=False, fused=False):
+  """adapt.py:208-210: two parameter groups, stereo_net first.  fused=True: optim.FusedAdamClip — clip_grad_norm_ on the stereo_net
+  group + Adam as three launches of this library over one flat gradient bucket (always capturable; checkpoint-compatible with
+  torch.optim.Adam).  Otherwise torch.optim.Adam as in the reference; capturable=True keeps its step counters on the device
   (needed by AdaptStepper(use_graph=True))."""
+  if fused:
+    from .optim import FusedAdamClip
+    return FusedAdamClip(stereo_net, feature_net, lr=lr)
   # capturable: step counters live on the device; fused: one multi-tensor kernel per group instead of ~220 tiny
   # per-parameter bias-correction kernels (same update rule, torch.optim.Adam defaults)
   return torch.optim.Adam([{"params": stereo_net.parameters()}, {"params": feature_net.parameters()}], lr=lr,
@@ -34,25 +39,36 @@ class AdaptStepper:
     self._graphs = {}
     self._wprep = None                      # fused.WeightPrepBatch: all derived weight images in one launch per step
     self.launches_per_step = None
-    if use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
-      raise RuntimeError("AdaptStepper(use_graph=True) needs make_optimizer(..., capturable=True)")
+    from .optim import FusedAdamClip
+    self.fused_opt = isinstance(optimizer, FusedAdamClip)
+    if self.fused_opt:
+      optimizer.clip_norm = 1.0 if clip_grad_norm else None
+    elif use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
+      raise RuntimeError("AdaptStepper(use_graph=True) needs make_optimizer(..., capturable=True) or fused=True")
 
   def predict(self, left, right):
     fl, fr = self.feature_net(left), self.feature_net(right)                       # adapt.py:72
     return self.stereo_net(left, fl, fr, "l", output_cost_volume=True)             # adapt.py:73
 
-  def step(self, left, right, replay=None, sync_grads=None, dp_params=None, dp_group=None):
+  def step(self, left, right, replay=None, sync_grads=None, dp_params=None, dp_group=None, dp_bucket=None):
     """One gradient update (adapt.py:313-314,328-337,381-394).  `replay` = (left, right, gt_disp) adds the
-    experience-replay term (adapt.py:339-349).  Shared-model data parallelism: either `sync_grads` (a callable run
-    between backward and clip, eager path only) or `dp_params` (+ `dp_group`): the gradients of those parameters are
-    packed into one flat bucket, SUM-all-reduced over NCCL and averaged.  With use_graph=True the step then becomes
-    graph(fwd + loss + bwd + pack) -> eager all-reduce -> graph(unpack + clip + Adam): the collective is not captured."""
+    experience-replay term (adapt.py:339-349).  Shared-model data parallelism:
+      * `dp_bucket` (parallel.DPBucket, with an optim.FusedAdamClip optimizer): gradients are gathered into the flat bucket by one
+        kernel, the bucket (gradients + BatchNorm running statistics) is SUM-all-reduced by ONE NCCL call, the statistics are
+        averaged in place and the fused clip + Adam kernel applies 1 / world — no per-parameter pack / unpack;
+      * `dp_params` (+ `dp_group`) with a torch optimizer: pack -> all-reduce -> unpack (round-1 path);
+      * `sync_grads`: a callable run between backward and the update (eager path only).
+    With use_graph=True the step is graph(fwd + loss + bwd + gather) -> eager all-reduce -> graph(clip + Adam)."""
     if self.use_graph and sync_grads is None:
-      return self._step_graph(left, right, dp_params, dp_group, replay)
-    if dp_params is not None and sync_grads is None:
+      return self._step_graph(left, right, dp_params, dp_group, replay, dp_bucket)
+    if dp_params is not None and sync_grads is None and dp_bucket is None:
       from . import parallel
       sync_grads = lambda: parallel.allreduce_gradients(dp_params, dp_group)
     out = self._fwd_bwd(left, right, replay)
+    if dp_bucket is not None:
+      self.optimizer.pack()
+      self._update(grad_scale=dp_bucket.allreduce(dp_group), packed=True)
+      return out
     if sync_grads is not None:
       sync_grads()
     self._update()
@@ -97,7 +113,10 @@ class AdaptStepper:
     loss.backward()
     return loss.detach(), fcs, head
 
-  def _update(self):
+  def _update(self, grad_scale=1.0, packed=False):
+    if self.fused_opt:
+      self.optimizer.step(grad_scale=grad_scale, packed=packed)                   # clip (adapt.py:391-392) + Adam (:393), 3 launches
+      return
     if self.clip:
       nn.utils.clip_grad_norm_(self.stereo_net.parameters(), 1.0)                 # adapt.py:391-392
     self.optimizer.step()
@@ -106,11 +125,14 @@ class AdaptStepper:
   def _state_tensors(self):
     ts = [p for net in (self.stereo_net, self.feature_net) for p in net.parameters()]
     ts += [b for net in (self.stereo_net, self.feature_net) for b in net.buffers()]
-    for st in self.optimizer.state.values():
-      ts += [v for v in st.values() if isinstance(v, torch.Tensor)]
+    if self.fused_opt:
+      ts += [self.optimizer.exp_avg, self.optimizer.exp_avg_sq, self.optimizer.step_t]
+    else:
+      for st in self.optimizer.state.values():
+        ts += [v for v in st.values() if isinstance(v, torch.Tensor)]
     return ts
 
-  def _capture(self, left, right, dp_params, dp_group, replay=None):
+  def _capture(self, left, right, dp_params, dp_group, replay=None, dp_bucket=None):
     import torch.distributed as dist
     from . import ops, parallel
     from .autograd import fused
@@ -118,8 +140,8 @@ class AdaptStepper:
     dev = left.device
     sl, sr = left.clone(), right.clone()
     srep = None if replay is None else tuple(t.clone() for t in replay)        # static replay buffers (left, right, gt)
-    world = dist.get_world_size(dp_group) if dp_params is not None else 1
-    fresh = len(self.optimizer.state) == 0
+    world = dist.get_world_size(dp_group) if (dp_params is not None or dp_bucket is not None) else 1
+    fresh = (not self.fused_opt) and len(self.optimizer.state) == 0
     snap = [(t, t.detach().clone()) for t in self._state_tensors()]
     cur = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(device=dev)
@@ -129,9 +151,13 @@ class AdaptStepper:
       # caches, allocator pools); model and optimizer state are restored afterwards so that capturing does not advance
       # the adaptation.
       self._fwd_bwd(sl, sr, srep)
-      if dp_params is not None:
-        parallel.allreduce_gradients(dp_params, dp_group)
-      self._update()
+      if dp_bucket is not None:
+        self.optimizer.pack()
+        self._update(grad_scale=dp_bucket.allreduce(dp_group), packed=True)
+      else:
+        if dp_params is not None:
+          parallel.allreduce_gradients(dp_params, dp_group)
+        self._update()
       self.optimizer.zero_grad(set_to_none=True)
       with torch.no_grad():
         for t, saved in snap:                 # in place: the graphs will hold these addresses
@@ -148,12 +174,21 @@ class AdaptStepper:
     flat = None
     with torch.cuda.graph(g1):
       out = self._fwd_bwd(sl, sr, srep)
-      if dp_params is not None:
+      if dp_bucket is not None:
+        self.optimizer.pack()
+      elif dp_params is not None:
         flat = parallel.pack_gradients(dp_params)
       else:
         self._update()
     g2 = None
-    if dp_params is not None:
+    if dp_bucket is not None:
+      g2 = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g2, pool=g1.pool()):
+        with torch.no_grad():
+          dp_bucket.stats.mul_(1.0 / world)
+        self._update(grad_scale=1.0 / world, packed=True)
+      flat = dp_bucket.flat
+    elif dp_params is not None:
       g2 = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g2, pool=g1.pool()):
         with torch.no_grad():
@@ -162,14 +197,14 @@ class AdaptStepper:
     self.launches_per_step = ops.LAUNCHES - n0          # library kernels inside one replay
     return dict(g1=g1, g2=g2, flat=flat, left=sl, right=sr, replay=srep, out=out)
 
-  def _step_graph(self, left, right, dp_params, dp_group, replay=None):
+  def _step_graph(self, left, right, dp_params, dp_group, replay=None, dp_bucket=None):
     import torch.distributed as dist
     from .autograd import fused
-    key = (tuple(left.shape), str(left.device), None if dp_params is None else len(dp_params),
+    key = (tuple(left.shape), str(left.device), None if dp_params is None else len(dp_params), dp_bucket is not None,
            None if replay is None else tuple(tuple(t.shape) for t in replay), self.batched_replay)
     e = self._graphs.get(key)
     if e is None:
-      e = self._graphs[key] = self._capture(left, right, dp_params, dp_group, replay)
+      e = self._graphs[key] = self._capture(left, right, dp_params, dp_group, replay, dp_bucket)
     e["left"].copy_(left, non_blocking=True)
     e["right"].copy_(right, non_blocking=True)
     if replay is not None:

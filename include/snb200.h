@@ -276,6 +276,23 @@ SNB_API int snb_khamis_loss_workspace_floats(long long n);
  * D1-all_t = out[2 + t] / out[1].  One CTA per sample, deterministic. */
 SNB_API int snb_eval_metrics(const float* pred, const float* gt, float* out, int B, long long hw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer side of the adaptation step (adapt.py:391-393) and the flat gradient bucket of shared-model data parallelism
+ * (SURVEY.md section 8e).
+ * snb_multi_gather: n device tensors (src[i], count[i] floats; src[i] == NULL writes zeros) -> dst + dst_off[i].  src / dst_off /
+ * count are HOST arrays (they travel as kernel parameters: CUDA-graph capturable, no table upload). */
+SNB_API int snb_multi_gather(const float* const* src, const long long* dst_off, const long long* count, int n, float* dst, void* stream);
+/* clip_grad_norm_(first n_clip elements of the bucket, max_norm; max_norm <= 0: no clipping) + Adam (no weight decay, no amsgrad)
+ * over the flat bucket: g = flat_grad * grad_scale (* clip coefficient inside the clipped group); exp_avg / exp_avg_sq are flat
+ * buffers laid out like the bucket; `step` is a device float incremented by the call (bias corrections are computed on the
+ * device: capturable).  chunk_table: device [nchunks][3] int64 = {parameter address of the chunk, flat offset, count <= 1024}.
+ * workspace: snb_adam_clip_workspace_bytes() bytes, 8-byte aligned; after the call its last four floats hold {clip coefficient,
+ * lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t), total norm of the clipped group}.  Three launches. */
+SNB_API int snb_adam_clip_step(const long long* chunk_table, int nchunks, const float* flat_grad, float* exp_avg, float* exp_avg_sq,
+                       float* step, long long n_total, long long n_clip, float max_norm, float grad_scale, float lr,
+                       float beta1, float beta2, float eps, void* workspace, void* stream);
+SNB_API int snb_adam_clip_workspace_bytes(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,3 +64,51 @@ def test_allreduce_gradients_matches_single_process_mean():
     for a, b in zip(got[:5], exp[:5]):
       assert torch.allclose(a, b, atol=1e-7)
     assert torch.allclose(got[5], exp[7], atol=1e-7)
+
+
+def test_used_bn_buffers_excludes_dead_conv2():
+  f, s = S.FeatureExtractorNetwork(3), S.StereoNet(3, 1, 0)
+  bufs = parallel.used_bn_buffers(s, f)
+  # stereo_net: 4 filter BNs + conv2d_feature + 6 blocks = 11; feature_net: 6 blocks; two buffers each
+  assert len(bufs) == 2 * (11 + 6) and all(b.numel() == 32 for b in bufs)
+  assert bufs[0] is s.filter[0][0][1].running_mean and bufs[1] is s.filter[0][0][1].running_var
+
+
+def _bcast_worker(rank, world, port, out):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  torch.manual_seed(10 + rank)                                  # different initial weights per rank
+  f, s = S.FeatureExtractorNetwork(3), S.StereoNet(3, 1, 0)
+  with torch.no_grad():
+    s.filter[1][0][1].running_mean.fill_(float(rank) + 0.5)
+  parallel.broadcast_state(s, f, src=0)
+  out[rank] = (s.conv3d_alone.weight.detach().clone(), f.conv_alone.bias.detach().clone(), s.filter[1][0][1].running_mean.clone(),
+               int(s.filter[1][0][1].num_batches_tracked))
+  dist.destroy_process_group()
+
+
+def test_broadcast_state_makes_replicas_identical():
+  world, port = 2, 29518
+  mgr = mp.Manager()
+  out = mgr.dict()
+  mp.spawn(_bcast_worker, args=(world, port, out), nprocs=world, join=True)
+  for a, b in zip(out[0][:3], out[1][:3]):
+    assert torch.equal(a, b)
+  assert float(out[1][2][0]) == 0.5
+
+
+def test_replay_reservoir_follows_algorithm_r():
+  """reservoir.ReplayReservoir mirrors utils/stereo_reservoir.py:5-64: fills up, rejects duplicate indices, then replaces with
+  probability max_size / i; seeded draws are reproducible."""
+  from stereonet_b200.reservoir import ReplayReservoir
+  t = torch.zeros(1)
+  r = ReplayReservoir(4, seed=3)
+  assert all(r.add(t + i, t, t, i) for i in range(4)) and r.size() == 4
+  assert r.add(t, t, t, 2) is False and r.i == 5                 # duplicate index: counted as streamed, not stored
+  added = sum(bool(r.add(t + i, t, t, i)) for i in range(10, 410))
+  assert r.size() == 4 and 5 <= added <= 60                      # expectation ~ 4 * ln(405 / 5) = 17.6
+  assert len({it[0] for it in r.buf}) == 4 and r.indices == {it[0] for it in r.buf}
+  a = ReplayReservoir(4, seed=7); b = ReplayReservoir(4, seed=7)
+  for i in range(50):
+    a.add(t + i, t, t, i); b.add(t + i, t, t, i)
+  assert [float(a.sample()[0]) for _ in range(8)] == [float(b.sample()[0]) for _ in range(8)]
