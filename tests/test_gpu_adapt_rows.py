@@ -151,7 +151,8 @@ def test_replay_step_vs_reference_golden():
       _, _, tag, n = key.split("/", 3)
       v = (s if tag == "s" else f).state_dict()[n].cpu().numpy()
       if "num_batches" in key:
-        assert int(v) == int(GOLD[key]) == (0 if ".conv2." in n else 2), key        # two train-mode passes per step (conv2: never run)
+        # two train-mode passes per step; feature_net runs on the left and the right image of each; conv2 never runs
+        assert int(v) == int(GOLD[key]) == (0 if ".conv2." in n else (2 if tag == "s" else 4)), key
       else:
         assert np.abs(v - GOLD[key]).max() <= 1e-4 * max(1.0, np.abs(GOLD[key]).max()), key
   d = np.abs(s.conv3d_alone.weight.detach().cpu().numpy() - GOLD["er/post/s/conv3d_alone.weight"])

@@ -42,8 +42,8 @@ def test_fused_adam_clip_matches_torch(gscale):
     if gscale > 1:
       assert norm_ref.item() > 1.0
   for (n, pa), (_, pb) in zip(list(sa.named_parameters()) + list(fa.named_parameters()), list(sb.named_parameters()) + list(fb.named_parameters())):
-    # 4 steps of at most lr each; the two implementations differ by rounding in m / (sqrt(v) + eps)
-    assert (pa - pb).abs().max().item() <= 2e-9 + 2e-6 * 4 * 5e-5 / 5e-5 * 5e-5, n
+    # the two implementations differ by rounding in m / (sqrt(v) + eps): a couple of ulps of the weight (measured: 1 ulp)
+    assert (pa - pb).abs().max().item() <= 3e-7 * pa.abs().max().item() + 1e-9, n
   # checkpoint format: torch.optim.Adam can load ours and vice versa (adam.pth, train.py:136-137)
   sd = opt.state_dict()
   ref2 = torch.optim.Adam([{"params": sb.parameters()}, {"params": fb.parameters()}], lr=1e-3)
