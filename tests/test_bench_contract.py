@@ -1,5 +1,5 @@
-"""CPU-only: the committed bench line (profiles/r1_bench_n1_final.json, written by `python bench.py` on a B200) carries every
-key of the bench contract, and the derived quantities are consistent with each other."""
+"""CPU-only: the committed bench lines (profiles/r2_bench_n1.json when present, else round 1's; written by `python bench.py` on a
+B200) carry every key of the bench contract, and the derived quantities are consistent with each other."""
 import json
 import os
 
@@ -7,7 +7,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _line(name):
+  r2 = {"r1_bench_n1_final.json": "r2_bench_n1.json", "r1_bench_reference_arm.json": "r2_bench_reference_arm.json"}.get(name)
+  if r2 and os.path.exists(os.path.join(ROOT, "profiles", r2)):
+    name = r2
   return json.load(open(os.path.join(ROOT, "profiles", name)))
+
+
+def test_round2_line_entries():
+  """Round-2 additions: every timed region >= 2 s, >= 50 adaptation steps, the other BASELINE.json configurations as keyed entries,
+  the CPU baseline measured on the reference's own modules."""
+  import pytest
+  if not os.path.exists(os.path.join(ROOT, "profiles", "r2_bench_n1.json")):
+    pytest.skip("no round-2 bench line committed yet")
+  d = _line("r1_bench_n1_final.json")
+  assert d["steps"] * d["ms_per_step"] >= 1990.0
+  assert d["e2e"]["steps"] * d["e2e"]["ms_per_step"] >= 1990.0
+  a = d["adapt"]
+  assert a["steps"] >= 50 and a["steps"] * a["ms_per_step"] >= 1990.0
+  assert abs(a["value"] - 1e3 / a["ms_per_step"]) <= 1e-6 * a["value"]
+  sf = d["sceneflow_b32"]
+  assert sf["scaling"] == "strong" and abs(sf["value"] - 32e3 / sf["ms_per_batch"]) <= 1e-6 * sf["value"]
+  assert len(d["timing_configs"]) >= 5
+  assert d["cpu_baseline"]["kind"] == "reference"
+  assert "traffic_source" in d["roofline"]
 
 
 def test_n1_line_has_the_contract_keys():
