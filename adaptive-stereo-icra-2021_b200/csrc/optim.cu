@@ -43,8 +43,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 
 // ws layout (floats): [0] clip coefficient, [1] lr / (1 - beta1^t), [2] 1 / sqrt(1 - beta2^t), [3] total norm of the clipped group
-__global__ void adam_finalize_kernel(const double* __restrict__ part, float* __restrict__ step, float max_norm, float lr,
-                                     float beta1, float beta2, float* __restrict__ ws) {
+__global__ void adam_finalize_kernel(const double* __restrict__ part, float* __restrict__ step, float max_norm, double lr,
+                                     double beta1, double beta2, float* __restrict__ ws) {
   pdl_launch(); pdl_wait();
   if (threadIdx.x != 0) return;
   double s = 0.0;
@@ -55,8 +55,8 @@ __global__ void adam_finalize_kernel(const double* __restrict__ part, float* __r
   const float t = step[0] + 1.f;
   step[0] = t;
   ws[0] = coef;
-  ws[1] = (float)((double)lr / (1.0 - pow((double)beta1, (double)t)));
-  ws[2] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+  ws[1] = (float)(lr / (1.0 - pow(beta1, (double)t)));
+  ws[2] = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)t)));
   ws[3] = norm;
 }
 
@@ -64,7 +64,7 @@ __global__ void adam_finalize_kernel(const double* __restrict__ part, float* __r
 __global__ void __launch_bounds__(256) adam_update_kernel(const long long* __restrict__ table, const float* __restrict__ grad,
                                                           float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                           const float* __restrict__ ws, long long n_clip, float grad_scale,
-                                                          float beta1, float beta2, float eps) {
+                                                          float beta1, float beta2, float omb1, float omb2, float eps) {
   pdl_launch(); pdl_wait();
   const long long* e = table + 3 * (long long)blockIdx.x;
   float* __restrict__ p = reinterpret_cast<float*>(e[0]);
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) adam_update_kernel(const long long* __res
   for (int i = threadIdx.x; i < cnt; i += 256) {
     const long long j = off + i;
     const float g = grad[j] * grad_scale * (j < n_clip ? coef : 1.f);
-    const float m = beta1 * exp_avg[j] + (1.f - beta1) * g;
-    const float v = beta2 * exp_avg_sq[j] + (1.f - beta2) * g * g;
+    const float m = beta1 * exp_avg[j] + omb1 * g;
+    const float v = beta2 * exp_avg_sq[j] + omb2 * g * g;
     exp_avg[j] = m; exp_avg_sq[j] = v;
     const float denom = sqrtf(v) * inv_bc2 + eps;
     p[i] -= step_size * (m / denom);
@@ -105,8 +105,8 @@ extern "C" int snb_multi_gather(const float* const* src, const long long* dst_of
 extern "C" int snb_adam_clip_workspace_bytes(void) { return NORM_BLOCKS * (int)sizeof(double) + 4 * (int)sizeof(float); }
 
 extern "C" int snb_adam_clip_step(const long long* chunk_table, int nchunks, const float* flat_grad, float* exp_avg, float* exp_avg_sq,
-                                  float* step, long long n_total, long long n_clip, float max_norm, float grad_scale, float lr,
-                                  float beta1, float beta2, float eps, void* workspace, void* stream) {
+                                  float* step, long long n_total, long long n_clip, float max_norm, float grad_scale, double lr,
+                                  double beta1, double beta2, double eps, void* workspace, void* stream) {
   SNB_REQUIRE(chunk_table && nchunks > 0 && flat_grad && exp_avg && exp_avg_sq && step && workspace, "snb_adam_clip_step: bad args");
   SNB_REQUIRE(n_clip >= 0 && n_clip <= n_total, "snb_adam_clip_step: clipped group exceeds the bucket");
   SNB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "snb_adam_clip_step: workspace must be 8-byte aligned");
@@ -117,7 +117,7 @@ extern "C" int snb_adam_clip_step(const long long* chunk_table, int nchunks, con
   snb_launch(adam_finalize_kernel, 1, 32, 0, stream, (const double*)part, step, max_norm, lr, beta1, beta2, ws);
   SNB_LAUNCH_CHECK("adam_finalize_kernel");
   snb_launch(adam_update_kernel, nchunks, 256, 0, stream, chunk_table, flat_grad, exp_avg, exp_avg_sq, (const float*)ws, n_clip, grad_scale,
-             beta1, beta2, eps);
+             (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps);   // 1 - beta in double, as torch.optim.Adam forms it
   SNB_LAUNCH_CHECK("adam_update_kernel");
   return 0;
 }

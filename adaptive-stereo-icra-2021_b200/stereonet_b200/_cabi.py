@@ -15,7 +15,7 @@ class ConvEpilogue(C.Structure):
               ("stats", C.c_void_p), ("lrelu", C.c_int)]
 
 
-_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 _GP, _EP = C.POINTER(ConvGeom), C.POINTER(ConvEpilogue)
 
 # name -> (restype, argtypes); every symbol include/snb200.h declares
@@ -79,7 +79,7 @@ SIGNATURES = {
   "snb_khamis_loss_workspace_floats": (_I, [_LL]),
   "snb_eval_metrics": (_I, [_P, _P, _P, _I, _LL, _P]),
   "snb_multi_gather": (_I, [_P, _P, _P, _I, _P, _P]),
-  "snb_adam_clip_step": (_I, [_P, _I, _P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _P, _P]),
+  "snb_adam_clip_step": (_I, [_P, _I, _P, _P, _P, _P, _LL, _LL, _F, _F, _D, _D, _D, _D, _P, _P]),
   "snb_adam_clip_workspace_bytes": (_I, []),
 }
 

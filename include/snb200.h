@@ -289,8 +289,8 @@ SNB_API int snb_multi_gather(const float* const* src, const long long* dst_off, 
  * workspace: snb_adam_clip_workspace_bytes() bytes, 8-byte aligned; after the call its last four floats hold {clip coefficient,
  * lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t), total norm of the clipped group}.  Three launches. */
 SNB_API int snb_adam_clip_step(const long long* chunk_table, int nchunks, const float* flat_grad, float* exp_avg, float* exp_avg_sq,
-                       float* step, long long n_total, long long n_clip, float max_norm, float grad_scale, float lr,
-                       float beta1, float beta2, float eps, void* workspace, void* stream);
+                       float* step, long long n_total, long long n_clip, float max_norm, float grad_scale, double lr,
+                       double beta1, double beta2, double eps, void* workspace, void* stream);
 SNB_API int snb_adam_clip_workspace_bytes(void);
 
 #ifdef __cplusplus
