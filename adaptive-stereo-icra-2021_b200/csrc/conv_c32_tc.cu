@@ -368,9 +368,37 @@ __device__ __forceinline__ void store_ws_split(float* __restrict__ out, bool d3,
   }
 }
 __device__ __forceinline__ int scale_slot_of(int mode_bits, int nwin) {
-  return ((mode_bits & SNB_CONV_WS) && nwin == 9) ? 9 * (B_BYTES / 4) : WIMG_SCALE_SLOT;
+  return ((mode_bits & SNB_CONV_WS) && nwin >= 9) ? nwin * (B_BYTES / 4) : WIMG_SCALE_SLOT;      // nwin 9: 3-D set, 10: the P4 set below
 }
 
+// ---- the ten-image set of a 5x5 stride-2 layer for conv_c32_ws.cu MODE_P4 (forward only): phase (a,b) = window a*2+b contributes
+// the images kw' = 0..(b ? 1 : 2) (first image 0 / 3 / 5 / 8), each 12 KB [wh | wl''] with rows [kz' = 2 | 1 | 0] x 32 cout holding
+// w[cout][cin][2 kz' + a][2 kw' + b] (zero past the 5x5 support); ONE scale 2^-s for the whole layer after the ten images.
+__device__ __forceinline__ void store_p4_images(const float* __restrict__ w, float* __restrict__ out, float scale, int first, int step) {
+  for (int i = first; i < 10 * 96 * 32; i += step) {
+    const int k = i & 31, row = (i >> 5) % 96, img = i / (96 * 32);
+    const int win = img < 3 ? 0 : (img < 5 ? 1 : (img < 8 ? 2 : 3));
+    const int kwp = img - (win == 0 ? 0 : win == 1 ? 3 : win == 2 ? 5 : 8);
+    const int kz = 2 - (row >> 5), co = row & 31;
+    const int y5 = 2 * kz + (win >> 1), x5 = 2 * kwp + (win & 1);
+    const float v = (y5 < 5 && x5 < 5) ? w[((size_t)co * 32 + k) * 25 + y5 * 5 + x5] : 0.f;
+    const float vs = v * scale;
+    const __half wh = __float2half_rn(vs);
+    const float whf = __half2float(wh);
+    __half* im = reinterpret_cast<__half*>(out) + (size_t)img * (B_BYTES / 2);
+    const int sw = co & 7;
+    im[row * 64 + ((((k >> 3)) ^ sw) << 3) + (k & 7)] = wh;
+    im[row * 64 + ((((k >> 3) + 4) ^ sw) << 3) + (k & 7)] = __float2half_rn((vs - whf) * 2048.f);
+  }
+}
+__global__ void prep_weights_p4_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  pdl_wait();            // no early trigger: see WEIGHT-IMAGE WRITERS below
+  store_p4_images(w, out, 1.f / out[10 * (B_BYTES / 4)], blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// WEIGHT-IMAGE WRITERS never call griddepcontrol.launch_dependents: the launch after one of these kernels therefore starts only
+// when it has completed, and — launches forming a chain — so does every later one.  That is what lets conv_c32_ws.cu fetch its
+// resident weight images BEFORE its own griddepcontrol.wait, under the tail of whatever kernel precedes it.
 // 2^-s for one weight tensor of `numel` floats: s = 13 - floor(log2 max|w|), i.e. max|w * 2^s| in [2^13, 2^14) — far from the
 // fp16 overflow (65504) and with the low parts wl ~ 2^-11 w' of everything above 2^-16 max|w| still normal fp16 numbers.
 __device__ __forceinline__ void weight_scale_block(const float* __restrict__ w, int numel, float* __restrict__ slot) {
@@ -390,11 +418,11 @@ __device__ __forceinline__ void weight_scale_block(const float* __restrict__ w, 
   }
 }
 __global__ void weight_scale_kernel(const float* __restrict__ w, int numel, float* __restrict__ slot) {
-  pdl_launch(); pdl_wait();
+  pdl_wait();            // no early trigger: see WEIGHT-IMAGE WRITERS below
   weight_scale_block(w, numel, slot);
 }
 __global__ void weight_scale_batch_kernel(const long long* __restrict__ table) {
-  pdl_launch(); pdl_wait();
+  pdl_wait();            // no early trigger: see WEIGHT-IMAGE WRITERS below
   const long long* e = table + 4 * blockIdx.x;
   const int cfg = (int)e[2];
   if (((cfg >> 8) & (SNB_CONV_F16 | SNB_CONV_WS)) == 0) return;
@@ -407,7 +435,7 @@ __global__ void weight_scale_batch_kernel(const long long* __restrict__ table) {
 // SWIZZLE_128B K-major smem image (row n = 128 B, 16-B chunk c stored at c ^ (n & 7)).  mode 1: data-gradient weights.
 // mode | SNB_CONV_F16: the fp16-split format above.
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int nwin, int mode) {
-  pdl_launch(); pdl_wait();
+  pdl_wait();            // no early trigger: see WEIGHT-IMAGE WRITERS below
   const bool f16 = (mode & SNB_CONV_F16) != 0, ws = (mode & SNB_CONV_WS) != 0;
   const float scale = (f16 || ws) ? 1.f / out[scale_slot_of(mode, nwin)] : 1.f;
   mode &= 0xf;
@@ -433,7 +461,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
 
 // Batched variant: blockIdx.y picks a table entry {w, out, config, 0} (see snb_prep_conv_weights_tc_batch in snb200.h).
 __global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table) {
-  pdl_launch(); pdl_wait();
+  pdl_wait();            // no early trigger: see WEIGHT-IMAGE WRITERS below
   const long long* e = table + 4 * blockIdx.y;
   const float* __restrict__ w = reinterpret_cast<const float*>(e[0]);
   float* __restrict__ out = reinterpret_cast<float*>(e[1]);
@@ -441,6 +469,7 @@ __global__ void prep_weights_tc_batch_kernel(const long long* __restrict__ table
   const int nwin = cfg & 0xff, mode = (cfg >> 8) & 0xf, kind = (cfg >> 16) & 0xff, pa = (cfg >> 24) & 0xf, pb = (cfg >> 28) & 0xf;
   const bool f16 = ((cfg >> 8) & SNB_CONV_F16) != 0, ws = ((cfg >> 8) & SNB_CONV_WS) != 0;
   const float scale = (f16 || ws) ? 1.f / out[scale_slot_of(cfg >> 8, nwin)] : 1.f;
+  if (kind == 2) { store_p4_images(w, out, scale, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); return; }
   const int taps = nwin * 3;
   const int total = nwin * 96 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -511,6 +540,15 @@ extern "C" int snb_prep_conv_weights_tc(const float* w, float* out, int kd, int 
   }
   snb_launch(tc::prep_weights_tc_kernel, snb_ceil_div(nwin * 96 * 32, 256), 256, 0, stream, w, out, nwin, mode);
   SNB_LAUNCH_CHECK("prep_weights_tc_kernel");
+  return 0;
+}
+
+extern "C" int snb_prep_conv5x5s2_weights_ws(const float* w, float* out, void* stream) {
+  SNB_REQUIRE(w && out, "snb_prep_conv5x5s2_weights_ws: null pointer");
+  snb_launch(tc::weight_scale_kernel, 1, 256, 0, stream, w, 1024 * 25, out + 10 * (tc::B_BYTES / 4));
+  SNB_LAUNCH_CHECK("weight_scale_kernel");
+  snb_launch(tc::prep_weights_p4_kernel, 36, 256, 0, stream, w, out);
+  SNB_LAUNCH_CHECK("prep_weights_p4_kernel");
   return 0;
 }
 

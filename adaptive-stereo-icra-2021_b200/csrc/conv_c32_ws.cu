@@ -48,16 +48,26 @@ constexpr int RING = 4;                                  // accumulator ring: 32
 constexpr int NR = 4;                                    // raw window ring depth
 constexpr int STG_BYTES = 128 * 128;                     // one output tile, fp32
 
-template <bool D3> struct Cfg {
-  static constexpr int NWIN = D3 ? 3 : 1;                // raw windows per walk step (3-D: kh = 0, 1, 2)
-  static constexpr int NIMG = D3 ? 9 : 3;                // resident weight images, index = win * 3 + kw
-  static constexpr int IMG_BYTES = D3 ? B_BYTES : 2 * B_BYTES;      // 3-D: [wh | wl''] 12 KB; 2-D: P [wh | wl] + Q [2^-11 wh | -] 24 KB
-  static constexpr int RAW_BYTES = D3 ? 17 * 1024 : 20 * 1024;      // 130 / up to 160 position rows of 128 B
-  static constexpr int NSTG = D3 ? 1 : 2;                // staging tiles per epilogue group
-  static constexpr int NA = D3 ? 2 : 3;                  // A slots of 96 columns = 3 kw x (xh 16 | xl' 16)
+// MODE 0: 2-D 3x3 (dilated).  MODE 1: 3-D 3x3x3.  MODE 2: 5x5 stride-2 pad-2 conv written over the four polyphase images of its
+// input (x[2i+a][2j+b] -> phase a*2+b, output-sized): out = sum over phases of a 3x3 'same' conv with the sub-kernel
+// w[2kz+a][2kw+b] — the four phase rows of one walk step are four raw windows feeding ONE accumulator ring, so the whole layer is
+// one launch instead of four chained ones that re-read and re-write the output (round 2, first half: 80 us per KITTI layer).
+constexpr int MODE_2D = 0, MODE_3D = 1, MODE_P4 = 2;
+template <int MODE> struct Cfg {
+  static constexpr bool TWO = MODE != MODE_2D;           // two accumulator rings D1 / D2 and [wh | wl''] images
+  static constexpr bool FLAT = MODE == MODE_3D;          // positions = un-padded flat index of a (b,d) slice, walk along d
+  static constexpr int NWIN = MODE == MODE_3D ? 3 : (MODE == MODE_P4 ? 4 : 1);     // raw windows per walk step (3-D: kh; P4: phase)
+  static constexpr int NIMG = MODE == MODE_3D ? 9 : (MODE == MODE_P4 ? 10 : 3);    // resident weight images
+  static constexpr int IMG_BYTES = TWO ? B_BYTES : 2 * B_BYTES;     // TWO: [wh | wl''] 12 KB; 2-D: P [wh | wl] + Q [2^-11 wh | -] 24 KB
+  static constexpr int RAW_BYTES = TWO ? 17 * 1024 : 20 * 1024;     // 130 / up to 160 position rows of 128 B
+  static constexpr int NSTG = TWO ? 1 : 2;               // staging tiles per epilogue group
+  static constexpr int NA = TWO ? 2 : 3;                 // A slots of 96 columns = 3 kw x (xh 16 | xl' 16)
   static constexpr int NRES = 3;                         // 2-D: residual slots of 32 columns
-  static constexpr int D1_BASE = 0, D2_BASE = RING * 32, RES_BASE = RING * 32, A_BASE = D3 ? 2 * RING * 32 : RING * 32 + NRES * 32;
+  static constexpr int D1_BASE = 0, D2_BASE = RING * 32, RES_BASE = RING * 32, A_BASE = TWO ? 2 * RING * 32 : RING * 32 + NRES * 32;
   static constexpr int SMEM_BYTES = NR * RAW_BYTES + 2 * NSTG * STG_BYTES + NIMG * IMG_BYTES + 4096 + 1024;
+  // first weight image of a window and its number of kw taps (P4: odd-column phases have taps kw' = 0, 1 only: x5 = 2 kw' + 1 < 5)
+  __host__ __device__ static constexpr int img_base(int win) { return MODE == MODE_P4 ? (win == 0 ? 0 : win == 1 ? 3 : win == 2 ? 5 : 8) : win * 3; }
+  __host__ __device__ static constexpr int nkw(int win) { return (MODE == MODE_P4 && (win & 1)) ? 2 : 3; }
   static_assert(A_BASE + NA * 96 <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
@@ -79,7 +89,7 @@ struct Params {
 // 3-D: slices z0, z0 + 1, ... of position tile `cb`, volume b.
 struct Strip { int b, cb, z0, ntiles; };
 
-template <bool D3>
+template <bool D3>      // D3 = flat 3-D geometry
 __device__ __forceinline__ Strip decode_strip(const Params& p, int sid) {
   Strip s;
   const int seg = sid % p.nseg; sid /= p.nseg;
@@ -122,15 +132,16 @@ __device__ __forceinline__ void mma_f16_i(uint32_t tmem_d, uint32_t tmem_a, uint
 // descriptor is (per-group base) + (compile-time offset), so an MMA costs its UTCHMMA plus a couple of uniform adds — the single
 // issuing thread is slow (a version with per-MMA loops / predicates over runtime group tables ran 2x slower end to end).
 // SKIP_FIRST: the first product(s) of (kw = 0, ks = 0) were issued by the caller (new tile, accumulate = 0).
-template <bool D3, int NG, bool SKIP_FIRST>
+template <int MODE, int NG, bool SKIP_FIRST, int NKW>
 __device__ __forceinline__ void issue_window(uint32_t d1, uint32_t d2, const uint32_t (&g_d)[3], uint32_t ta, uint32_t img0,
                                              const uint32_t (&g_b)[3], const uint32_t (&g_i)[3]) {
-  using C = Cfg<D3>;
+  using C = Cfg<MODE>;
+  constexpr bool D3 = C::TWO;
   uint64_t bd[NG]; uint32_t dd1[NG], dd2[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) { bd[g] = make_desc(img0 + g_b[g]); dd1[g] = d1 + g_d[g]; dd2[g] = d2 + g_d[g]; }
 #pragma unroll
-  for (int kw = 0; kw < 3; ++kw) {
+  for (int kw = 0; kw < NKW; ++kw) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const uint32_t a = ta + kw * 32 + ks * 8;
@@ -151,11 +162,12 @@ __device__ __forceinline__ void issue_window(uint32_t d1, uint32_t d2, const uin
 
 // FOLD (the product setting): one N = 96 MMA over the three ring blocks per product (see above) instead of three N = 32 MMAs:
 // 37 / 40 / 44 us against 41 / 44 / 48 us per KITTI refinement block (dilation 1 / 4 / 8), 55 against 61 us per 3-D filter layer.
-template <bool D3, bool FOLD>
+template <int MODE, bool FOLD>
 __global__ void __launch_bounds__(NTHREADS_WS, 1)
 conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const Params p) {
-  using C = Cfg<D3>;
+  using C = Cfg<MODE>;
   constexpr int NA = C::NA, NRES = C::NRES, NWIN = C::NWIN;
+  constexpr bool D3 = C::FLAT, TWO = C::TWO;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -196,16 +208,19 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_launch();                                    // only after this CTA owns its TMEM columns
-  pdl_wait();                                      // everything above touched no global memory
-  // (Fetching the resident weight images before this wait, under the previous kernel's tail, was tried: it races with the weight
-  // preparation kernel whenever that is the immediately preceding launch — first forward after an optimizer step / load.)
+  // The resident weight images are fetched BEFORE the grid-dependency wait, under the tail of the previous kernel: their only
+  // writers (the weight preparation kernels, conv_c32_tc.cu "WEIGHT-IMAGE WRITERS") never trigger their dependents early, so
+  // every launch that follows one of them starts after it has completed.  Everything else this kernel reads comes after the wait.
   if (warp == 1 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" :: "l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" :: "l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
     mbar_expect_tx(wbar, C::NIMG * C::IMG_BYTES);
     for (int w = 0; w < C::NIMG; ++w)
       bulk_g2s(sB + w * C::IMG_BYTES, p.wimg + (size_t)w * (C::IMG_BYTES / 4), C::IMG_BYTES, wbar);
   }
-  const int scale_slot = D3 ? 9 * (B_BYTES / 4) : WIMG_SCALE_SLOT;
+  pdl_launch();                                    // only after this CTA owns its TMEM columns
+  pdl_wait();
+  const int scale_slot = TWO ? C::NIMG * (B_BYTES / 4) : WIMG_SCALE_SLOT;
   if (tid >= EPI_WARP0 * 32 && tid < EPI_WARP0 * 32 + 32) {
     // y = lrelu(scale * (acc * 2^-s + bias) + shift) = lrelu(acc * alpha + beta)
     const int c = tid - EPI_WARP0 * 32;
@@ -231,6 +246,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             WSWAIT(w_r, tc::mbar_wait(&rempty[sa], ((ac / NR) & 1) ^ 1));
             mbar_expect_tx(&rfull[sa], bytes);
             if (D3) tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - 1 + (win - 1) * p.W, s.z0 + u - 1, s.b);
+            else if (MODE == MODE_P4) tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - 1, s.z0 + u - 1, win * p.B + s.b);
             else    tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - p.dil, s.z0 + (u - 1) * p.dil, s.b);
             ++ac;
           }
@@ -286,7 +302,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           WSWAIT(t_tempty, mbar_wait_warp(&tempty[tc_new % RING], (uint32_t)(((tc_new / RING) & 1) ^ 1)));
           tc_fence_after();
         }
-        const uint32_t d1 = tmem_u + C::D1_BASE, d2 = tmem_u + (D3 ? C::D2_BASE : C::D1_BASE);
+        const uint32_t d1 = tmem_u + C::D1_BASE, d2 = tmem_u + (TWO ? C::D2_BASE : C::D1_BASE);
 #pragma unroll
         for (int win = 0; win < NWIN; ++win, ++win_count) {
           const uint32_t aslot = win_count % NA;
@@ -294,25 +310,30 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           tc_fence_after();
           const uint32_t ta = tmem_u + C::A_BASE + aslot * 96;
           const bool fresh_step = has_new && win == 0;          // the new tile's accumulators have not been written yet
-          const uint32_t img0 = sb_u32 + win * 3 * C::IMG_BYTES;  // image (win, kw = 0)
+          const uint32_t img0 = sb_u32 + C::img_base(win) * C::IMG_BYTES;  // image (win, kw = 0)
+          const int nkw = C::nkw(win);                          // a constant per unrolled window
           if (elect_one()) {
             if (fresh_step) {
               // first product(s) of a new tile: the old tiles accumulate, the new one starts with accumulate = 0
               if (go_i[0]) mma_f16_i(d1 + go_d[0], ta, make_desc(img0 + go_b[0]), go_i[0], 1);
               if (go_i[1]) mma_f16_i(d1 + go_d[1], ta, make_desc(img0 + go_b[1]), go_i[1], 1);
               mma_f16_i(d1 + new_d, ta, make_desc(img0 + 2 * 4096), idesc_n(1), 0);             // D1 = xh . wh
-              if (D3) {
+              if (TWO) {
                 if (go_i[0]) mma_f16_i(d2 + go_d[0], ta + 16, make_desc(img0 + go_b[0]), go_i[0], 1);
                 if (go_i[1]) mma_f16_i(d2 + go_d[1], ta + 16, make_desc(img0 + go_b[1]), go_i[1], 1);
                 mma_f16_i(d2 + new_d, ta + 16, make_desc(img0 + 2 * 4096), idesc_n(1), 0);      // D2 = xl' . wh
               }
-              if (ng == 1) issue_window<D3, 1, true>(d1, d2, g_d, ta, img0, g_b, g_i);
-              else if (ng == 2) issue_window<D3, 2, true>(d1, d2, g_d, ta, img0, g_b, g_i);
-              else issue_window<D3, 3, true>(d1, d2, g_d, ta, img0, g_b, g_i);
-            } else {
-              if (ng == 1) issue_window<D3, 1, false>(d1, d2, g_d, ta, img0, g_b, g_i);
-              else if (ng == 2) issue_window<D3, 2, false>(d1, d2, g_d, ta, img0, g_b, g_i);
-              else issue_window<D3, 3, false>(d1, d2, g_d, ta, img0, g_b, g_i);
+              if (ng == 1) issue_window<MODE, 1, true, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else if (ng == 2) issue_window<MODE, 2, true, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else issue_window<MODE, 3, true, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+            } else if (nkw == 3) {
+              if (ng == 1) issue_window<MODE, 1, false, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else if (ng == 2) issue_window<MODE, 2, false, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else issue_window<MODE, 3, false, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+            } else {                                            // P4, odd-column phase (never the first window of a step)
+              if (ng == 1) issue_window<MODE, 1, false, 2>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else if (ng == 2) issue_window<MODE, 2, false, 2>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else issue_window<MODE, 3, false, 2>(d1, d2, g_d, ta, img0, g_b, g_i);
             }
             if (win == NWIN - 1 && u >= 2) mma_commit_raw(&tfull[(tile_base + u - 2) % RING]);   // tile u-2 has all its kz taps
             mma_commit_raw(&aempty[aslot]);
@@ -349,11 +370,13 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           const unsigned char* rawp = base + sr * C::RAW_BYTES;
           const uint32_t ta = tlane + C::A_BASE + aslot * 96;
           // 2-D: this window is the centre row (kz = 1) of tile j = u - 1: its un-shifted pixels are that tile's residual
-          const bool centre = !D3 && p.res_mode == 1 && u >= 1 && u <= s.ntiles;
+          const bool centre = MODE == MODE_2D && p.res_mode == 1 && u >= 1 && u <= s.ntiles;
+          const int nkw = C::nkw(win);
           const long long tcount = tile_base + (u - 1);
           bool a_free = false;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
+            if (kw >= nkw) break;
             const int row = m + kw * p.dil;
             const unsigned char* rp = rawp + row * 128;
             float4 v[8];
@@ -361,7 +384,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
             uint32_t hl[32];
             split_f16(v, hl);
-            if (kw == 2) {                                   // last read of the raw window: release it once the loads have returned
+            if (kw == nkw - 1) {                             // last read of the raw window: release it once the loads have returned
               const uint32_t dep = hl[0] ^ hl[5] ^ hl[10] ^ hl[15] ^ hl[3] ^ hl[6] ^ hl[9] ^ hl[12];     // one word of each of the 8 loads
               __syncwarp();
               if (lane == 0) mbar_arrive_after(&rempty[sr], dep);
@@ -377,7 +400,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               a_free = true;
             }
             tmem_st32(ta + kw * 32, hl);
-            if (!D3 && kw == 1 && centre) {
+            if (MODE == MODE_2D && kw == 1 && centre) {
               const int rslot = (int)(tcount % NRES);
               WSWAIT(w_rs, tc::mbar_wait(&rsempty[rslot], (uint32_t)(((tcount / NRES) & 1) ^ 1)));
               tc_fence_after();
@@ -448,7 +471,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const long long tB = p.dbg ? clock64() : 0;
         {
           float acc[32], res[32];
-          if (D3) {
+          if (TWO) {
             tmem_ld32x2(tlane + C::D1_BASE + slot * 32, tlane + C::D2_BASE + slot * 32, acc, res);
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = fmaf(res[i], 1.f / 2048.f, acc[i]);             // D1 + 2^-11 D2
@@ -460,7 +483,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           if (p.dbg) t_ld += clock64() - tB;
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { mbar_arrive(&tempty[slot]); if (!D3 && p.res_mode == 1) mbar_arrive(&rsempty[rslot]); }
+          if (lane == 0) { mbar_arrive(&tempty[slot]); if (!TWO && p.res_mode == 1) mbar_arrive(&rsempty[rslot]); }
           float* row = stg + m * 32;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -471,7 +494,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             o.z = fmaf(acc[4 * c + 2], a4.z, b4.z); o.w = fmaf(acc[4 * c + 3], a4.w, b4.w);
             o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
             o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
-            if (!D3 && p.res_mode == 1) { o.x += res[4 * c]; o.y += res[4 * c + 1]; o.z += res[4 * c + 2]; o.w += res[4 * c + 3]; }
+            if (!TWO && p.res_mode == 1) { o.x += res[4 * c]; o.y += res[4 * c + 1]; o.z += res[4 * c + 2]; o.w += res[4 * c + 3]; }
             *reinterpret_cast<float4*>(row + ((c ^ (m & 7)) << 2)) = o;
           }
         }
@@ -582,12 +605,12 @@ extern "C" int snb_conv_c32_ws_num_tiles(const snb_conv_geom* g) {
   return g->KD == 3 ? p.B * p.D * p.ncb : p.B * p.H * p.ncb;          // one stats row per output tile
 }
 
-extern "C" int snb_conv_weights_ws_floats(int kd) {
-  return kd == 3 ? 9 * (tc::B_BYTES / 4) + 4 : 3 * tc::WIMG_FLOATS_PER_WINDOW;
+extern "C" int snb_conv_weights_ws_floats(int kd) {      // kd = 5: the ten-image set of the 5x5 stride-2 layer (MODE_P4)
+  return kd == 5 ? 10 * (tc::B_BYTES / 4) + 4 : (kd == 3 ? 9 * (tc::B_BYTES / 4) + 4 : 3 * tc::WIMG_FLOATS_PER_WINDOW);
 }
 
 static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
-                     long long* dbg, void* stream) {
+                     long long* dbg, void* stream, bool p4 = false) {
   wsk::Params p;
   if (int rc = ws_setup(g, p, "snb_conv_c32_ws")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv_c32_ws: null pointer");
@@ -595,8 +618,9 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
   SNB_REQUIRE(!e->scale || e->shift, "snb_conv_c32_ws: scale without shift");
   SNB_REQUIRE(!e->stats || (!e->scale && !e->lrelu && !e->residual), "snb_conv_c32_ws: statistics are taken of the plain conv + bias output");
   const bool d3 = g->KD == 3;
+  SNB_REQUIRE(!p4 || (!d3 && g->dil == 1), "snb_conv5x5s2_c32_ws: bad geometry");
   p.wimg = wimg; p.y = y; p.e = *e; p.dbg = dbg;
-  p.res_mode = e->residual == nullptr ? 0 : ((e->residual == x && !d3) ? 1 : 2);
+  p.res_mode = e->residual == nullptr ? 0 : ((e->residual == x && !d3 && !p4) ? 1 : 2);
   snb_encode_tiled_fn enc = snb_get_encode_tiled();
   SNB_REQUIRE(enc != nullptr, "snb_conv_c32_ws: cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap tmap, tmap_out;
@@ -609,10 +633,11 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
     dims[0] = 32; dims[1] = (cuuint64_t)g->W; dims[2] = (cuuint64_t)g->H; dims[3] = (cuuint64_t)g->B;
     strides[0] = 128; strides[1] = (cuuint64_t)g->W * 128; strides[2] = (cuuint64_t)g->W * g->H * 128;
   }
+  cuuint64_t dims_in[4] = {dims[0], dims[1], dims[2], p4 ? 4 * dims[3] : dims[3]};      // P4: [phase][image] along the outer axis
   const cuuint32_t box[4] = {32, (cuuint32_t)(128 + 2 * g->dil), 1, 1};
   const cuuint32_t box_out[4] = {32, 128, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims_in, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv_c32_ws: cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -625,11 +650,12 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nstrips < sms ? p.nstrips : sms;
   static const bool fold = []() { const char* s = getenv("SNB200_WS_FOLD"); return !(s != nullptr && s[0] == '0'); }();   // SNB200_WS_FOLD=0: N = 32 MMAs (measurements)
-#define WS_GO(D3V, FOLDV) do { \
-    SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<D3V, FOLDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<D3V>::SMEM_BYTES)); \
-    snb_launch(wsk::conv_c32_ws_kernel<D3V, FOLDV>, grid, wsk::NTHREADS_WS, wsk::Cfg<D3V>::SMEM_BYTES, stream, tmap, tmap_out, p); } while (0)
-  if (d3) { if (fold) WS_GO(true, true); else WS_GO(true, false); }
-  else    { if (fold) WS_GO(false, true); else WS_GO(false, false); }
+#define WS_GO(MODEV, FOLDV) do { \
+    SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<MODEV, FOLDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<MODEV>::SMEM_BYTES)); \
+    snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, p); } while (0)
+  if (p4) WS_GO(wsk::MODE_P4, true);
+  else if (d3) { if (fold) WS_GO(wsk::MODE_3D, true); else WS_GO(wsk::MODE_3D, false); }
+  else    { if (fold) WS_GO(wsk::MODE_2D, true); else WS_GO(wsk::MODE_2D, false); }
 #undef WS_GO
   SNB_LAUNCH_CHECK("conv_c32_ws_kernel");
   return 0;
@@ -644,4 +670,15 @@ extern "C" int snb_conv_c32_ws_profile(const float* x, const float* wimg, float*
                                        const snb_conv_epilogue* e, long long* counters, void* stream) {
   SNB_REQUIRE(counters != nullptr, "snb_conv_c32_ws_profile: null counters");
   return ws_launch(x, wimg, y, g, e, counters, stream);
+}
+
+// 5x5 stride-2 pad-2 32->32 convolution (downsample[1:], stereo_net.py:64-70) over the polyphase images of its input:
+// phases [4][B][OH][OW][32] (phase a*2+b holds x[2i+a][2j+b], zero where that is outside x), y [B][OH][OW][32].
+extern "C" int snb_conv5x5s2_c32_ws(const float* phases, const float* wimg, float* y, int B, int OH, int OW,
+                                    const snb_conv_epilogue* e, void* stream) {
+  snb_conv_geom g;
+  g.B = B; g.D = 1; g.H = OH; g.W = OW; g.OD = 1; g.OH = OH; g.OW = OW; g.KD = 1; g.KH = 3; g.KW = 3;
+  g.stride = 1; g.dil = 1; g.pd = 0; g.ph = 1; g.pw = 1; g.transposed = 0;
+  SNB_REQUIRE(e && !e->residual, "snb_conv5x5s2_c32_ws: no residual input");
+  return ws_launch(phases, wimg, y, &g, e, nullptr, stream, true);
 }

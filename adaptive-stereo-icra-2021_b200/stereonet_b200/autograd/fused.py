@@ -190,6 +190,11 @@ def wprep_tc_phases(conv, mode):
   return _cached(conv, ("wtc_phase", mode, fmt), [conv.weight], make)
 
 
+def wprep_p4(conv):
+  """The ten-image set of a 5x5 stride-2 layer for the one-launch kernel (ops.conv5x5s2_c32_ws)."""
+  return _cached(conv, ("wtc_p4", 0, "ws"), [conv.weight], lambda: ops.prep_conv5x5s2_weights_ws(conv.weight.detach().contiguous()))
+
+
 class WeightPrepBatch:
   """Every tensor-core weight image the adaptation step needs (forward and data-gradient images of all used 3x3 / 3x3x3
   32->32 convolutions, the polyphase images of the 5x5 stride-2 ones) refreshed by ONE launch after an optimizer update,
@@ -216,8 +221,11 @@ class WeightPrepBatch:
             plan.append((m, ("wtc", mode, fmt), [(kd * 3, mode | fbit, 0, 0, 0)]))
         elif tuple(w.shape[2:]) == (5, 5) and m.stride[0] == 2:
           for mode in modes:
-            plan.append((m, ("wtc_phase", mode, fmt), [(3, mode | fbit, 1, a, b) for a in (0, 1) for b in (0, 1)]))
-    size = lambda nwin, key: ops.conv_weights_tc_floats(nwin // 3, key[2])
+            if mode == 0 and fmt == "ws":          # forward: the one-launch kernel's image set
+              plan.append((m, ("wtc_p4", 0, "ws"), [(10, fbit, 2, 0, 0)]))
+            else:
+              plan.append((m, ("wtc_phase", mode, fmt), [(3, mode | fbit, 1, a, b) for a in (0, 1) for b in (0, 1)]))
+    size = lambda nwin, key: ops.conv_weights_tc_floats(5 if nwin == 10 else nwin // 3, key[2])
     total = sum(size(cfg[0], key) for _, key, cfgs in plan for cfg in cfgs)
     dev = plan[0][0].weight.device
     self.buf = torch.empty((total,), device=dev, dtype=torch.float32)
@@ -240,7 +248,7 @@ class WeightPrepBatch:
     ops.prep_conv_weights_tc_batch(self.table, self.n)
     for m, key, views, _ in self.items:
       ver = (EPOCH, (m.weight.data_ptr(), m.weight._version))
-      m.__dict__.setdefault("_snb_cache", {})[key] = (ver, views[0] if key[0] == "wtc" else views)
+      m.__dict__.setdefault("_snb_cache", {})[key] = (ver, views if key[0] == "wtc_phase" else views[0])
 
 
 def conv5x5s2_c32(x, conv, bias, phases=None):
@@ -251,6 +259,8 @@ def conv5x5s2_c32(x, conv, bias, phases=None):
     y, _ = ops.conv_c32(x, wprep(conv), g, bias=bias)
     return y
   ph = phases if phases is not None else ops.phase_split(x)
+  if CONV_BACKEND == "ws":
+    return ops.conv5x5s2_c32_ws(ph, wprep_p4(conv), bias=bias)
   g3 = ops.geom(ph[0].shape, 3, stride=1, dil=1)
   y = None
   for i, wimg in enumerate(wprep_tc_phases(conv, 0)):

@@ -152,6 +152,30 @@ def conv_weights_tc_floats(kd, fmt="ws"):
   return lib.snb_conv_weights_ws_floats(kd) if fmt == "ws" else lib.snb_conv_weights_tc_floats(kd)
 
 
+def prep_conv5x5s2_weights_ws(w):
+  """[32,32,5,5] weight -> the ten-image set of conv5x5s2_c32_ws (snb_prep_conv5x5s2_weights_ws)."""
+  _req(w, "weight", 4)
+  if tuple(w.shape) != (32, 32, 5, 5):
+    raise RuntimeError(f"stereonet_b200: expected a [32,32,5,5] weight, got {tuple(w.shape)}")
+  out = torch.empty((_cabi.lib().snb_conv_weights_ws_floats(5),), device=w.device, dtype=torch.float32)
+  check(_cabi.lib().snb_prep_conv5x5s2_weights_ws(_p(w), _p(out), _stream(w)), "snb_prep_conv5x5s2_weights_ws")
+  _count(2)
+  return out
+
+
+def conv5x5s2_c32_ws(phases, wimg, bias=None, lrelu=False):
+  """5x5 stride-2 pad-2 32->32 conv over the polyphase images [4,B,OH,OW,32] of its input, ONE tensor-core launch."""
+  _req(phases, "phases", 5); _req(wimg, "wimg")
+  if phases.shape[0] != 4 or phases.shape[-1] != 32:
+    raise RuntimeError(f"stereonet_b200: phases must be [4,B,OH,OW,32], got {tuple(phases.shape)}")
+  _, B, OH, OW, _ = phases.shape
+  y = torch.empty((B, OH, OW, 32), device=phases.device, dtype=torch.float32)
+  e = ConvEpilogue(_p(bias), None, None, None, None, 1 if lrelu else 0)
+  check(_cabi.lib().snb_conv5x5s2_c32_ws(_p(phases), _p(wimg), _p(y), B, OH, OW, C.byref(e), _stream(phases)), "snb_conv5x5s2_c32_ws")
+  _count()
+  return y
+
+
 def prep_conv_weights_tc_batch(table, n):
   """One launch for n weight images; `table` is an int64 device tensor [n,4] (see snb_prep_conv_weights_tc_batch)."""
   check(_cabi.lib().snb_prep_conv_weights_tc_batch(_p(table), n, _stream(table)), "snb_prep_conv_weights_tc_batch")

@@ -119,7 +119,13 @@ SNB_API int snb_conv2d_c32_tc_profile(const float* x, const float* wimg, float* 
 SNB_API int snb_conv_c32_ws(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
                     void* stream);
 SNB_API int snb_conv_c32_ws_num_tiles(const snb_conv_geom* g);
-SNB_API int snb_conv_weights_ws_floats(int kd);
+SNB_API int snb_conv_weights_ws_floats(int kd);      /* kd = 1, 3; 5: the image set of snb_conv5x5s2_c32_ws */
+/* downsample[1:] (nn.Conv2d(32, 32, 5, stride 2, padding 2), stereo_net.py:64-70) in ONE launch of the same kernel: the four
+ * polyphase images of the input (snb_phase_split / snb_conv5x5s2_c3 with phases = 1; [4][B][OH][OW][32]) are four raw windows per
+ * walk step feeding one accumulator ring.  wimg from snb_prep_conv5x5s2_weights_ws (or batch kind 2).  No residual input. */
+SNB_API int snb_conv5x5s2_c32_ws(const float* phases, const float* wimg, float* y, int B, int OH, int OW,
+                         const snb_conv_epilogue* e, void* stream);
+SNB_API int snb_prep_conv5x5s2_weights_ws(const float* w, float* out, void* stream);
 /* Diagnostics: same launch plus per-CTA cycle counters [grid][16]. */
 SNB_API int snb_conv_c32_ws_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
                             const snb_conv_epilogue* e, long long* counters, void* stream);
@@ -131,7 +137,8 @@ SNB_API int snb_conv_weights_tc_floats(int kd);
  * table: n device-resident entries of 4 int64 = {source weight pointer, output image pointer, config, 0};
  * config = nwin | mode << 8 | kind << 16 | a << 24 | b << 28.  kind 0: a [32][32][nwin*3] weight as in
  * snb_prep_conv_weights_tc (nwin = 3 kd).  kind 1: the polyphase 3x3 sub-kernel (a, b) of a [32][32][5][5] stride-2 weight,
- * sub[i][j] = w[2i + a][2j + b] (zero outside the 5x5 support), nwin = 3 (csrc/phase.cu). */
+ * sub[i][j] = w[2i + a][2j + b] (zero outside the 5x5 support), nwin = 3 (csrc/phase.cu).  kind 2: the image set of
+ * snb_conv5x5s2_c32_ws from a [32][32][5][5] weight (nwin = 10, mode = SNB_CONV_WS). */
 SNB_API int snb_prep_conv_weights_tc_batch(const long long* table, int n, void* stream);
 
 /* Polyphase helpers for the stride-2 5x5 32->32 layers (stereo_net.py:64-70): the convolution is the sum of four stride-1

@@ -96,6 +96,13 @@ def test_weight_prep_batch_matches_per_layer_prep():
       slot = 3072 + 16
       assert float(views[0][slot]) in [2.0 ** -e for e in range(-20, 41)]    # the 2^-s slot
       n3x3 += 1
+    elif key[0] == "wtc_p4":
+      ref = ops.prep_conv5x5s2_weights_ws(conv.weight.detach())
+      n = 10 * 3072 + 1                                   # ten 12 KB images + the 2^-s slot (the 3 floats after it are padding)
+      assert torch.equal(views[0][:n], ref[:n]), key
+      assert fused.wprep_p4(conv) is views[0]
+      n5x5 += 1
+      continue
     else:
       w = conv.weight.detach()
       i = 0
