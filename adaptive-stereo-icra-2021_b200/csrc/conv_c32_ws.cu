@@ -56,6 +56,7 @@ constexpr int MODE_2D = 0, MODE_3D = 1, MODE_P4 = 2;
 template <int MODE> struct Cfg {
   static constexpr bool TWO = MODE != MODE_2D;           // two accumulator rings D1 / D2 and [wh | wl''] images
   static constexpr bool FLAT = MODE == MODE_3D;          // positions = un-padded flat index of a (b,d) slice, walk along d
+  static constexpr bool ONCE = MODE == MODE_3D;          // converters: split every raw row ONCE, in place, then read it three times
   static constexpr int NWIN = MODE == MODE_3D ? 3 : (MODE == MODE_P4 ? 4 : 1);     // raw windows per walk step (3-D: kh; P4: phase)
   static constexpr int NIMG = MODE == MODE_3D ? 9 : (MODE == MODE_P4 ? 10 : 3);    // resident weight images
   static constexpr int IMG_BYTES = TWO ? B_BYTES : 2 * B_BYTES;     // TWO: [wh | wl''] 12 KB; 2-D: P [wh | wl] + Q [2^-11 wh | -] 24 KB
@@ -374,6 +375,63 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           const int nkw = C::nkw(win);
           const long long tcount = tile_base + (u - 1);
           bool a_free = false;
+          if (C::ONCE) {
+            // 3-D: nine (kh,kw) operand copies per walk step made the converters — not the tensor pipe — the bound of this kernel
+            // (all converters idled: 59 -> 35 us per KITTI layer; the MMA warp waited for operands a third of the time).  So every
+            // raw row is split once, IN PLACE (the 128-B fp32 row becomes the 128-B [xh | xl'] row, same swizzle), and the three
+            // kw-shifted copies are plain 128-B reads: a third of the conversion arithmetic for 256 more smem wavefronts per window.
+            unsigned char* rw = base + sr * C::RAW_BYTES;
+            {
+              unsigned char* rp = rw + m * 128;
+              float4 v[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (m & 7)) << 4));
+              uint32_t hl[32];
+              split_f16(v, hl);
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(rp + ((c ^ (m & 7)) << 4)) = make_uint4(hl[4 * c], hl[4 * c + 1], hl[4 * c + 2], hl[4 * c + 3]);
+            }
+            if (quad == 3 && lane < 16) {                     // the two halo rows 128, 129: one 16-B input chunk per lane
+              const int row = 128 + (lane >> 3), c = lane & 7;
+              unsigned char* rp = rw + row * 128;
+              const float4 x = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+              const uint32_t h0 = pack_f16x2(x.x, x.y), h1 = pack_f16x2(x.z, x.w);
+              const float2 f0 = unpack_f16x2(h0), f1 = unpack_f16x2(h1);
+              const uint32_t l0 = pack_f16x2((x.x - f0.x) * 2048.f, (x.y - f0.y) * 2048.f);
+              const uint32_t l1 = pack_f16x2((x.z - f1.x) * 2048.f, (x.w - f1.y) * 2048.f);
+              __syncwarp(0x0000ffffu);                        // in place: every lane has read its chunk before any lane writes
+              *reinterpret_cast<uint2*>(rp + (((c >> 1) ^ (row & 7)) << 4) + (c & 1) * 8) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(rp + (((4 + (c >> 1)) ^ (row & 7)) << 4) + (c & 1) * 8) = make_uint2(l0, l1);
+            }
+            fence_async_smem();                               // these generic-proxy writes precede the TMA's next write of the slot
+            group_bar(7 + (int)grp);                          // the split rows of all four warps are visible
+            WSWAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
+            tc_fence_after();
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int row = m + kw;
+              const unsigned char* rp = rw + row * 128;
+              uint32_t hl[32];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rp + ((c ^ (row & 7)) << 4));
+                hl[4 * c] = q.x; hl[4 * c + 1] = q.y; hl[4 * c + 2] = q.z; hl[4 * c + 3] = q.w;
+              }
+              if (kw == 2) {                                  // last read of the window: release it once the loads have returned
+                const uint32_t dep = hl[0] ^ hl[4] ^ hl[8] ^ hl[12] ^ hl[16] ^ hl[20] ^ hl[24] ^ hl[28];
+                __syncwarp();
+                if (lane == 0) mbar_arrive_after(&rempty[sr], dep);
+              }
+              if ((kw == 0 && wcol == 0) || (kw == 2 && wcol == p.W - 1)) {
+                // un-padded flat index: this tap wrapped into the neighbouring image row -> it is zero padding
+#pragma unroll
+                for (int i = 0; i < 32; ++i) hl[i] = 0u;
+              }
+              tmem_st32(ta + kw * 32, hl);
+            }
+            a_free = true;
+          } else
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             if (kw >= nkw) break;

@@ -78,10 +78,10 @@ import os
 # "tc3" = 3xTF32 split, "tc1" = single-pass TF32 (~1e-3 relative), "ffma" = fp32 CUDA-core kernel.
 CONV_BACKEND = "ws"
 _FMT = {"ws": "ws", "h3": "h", "tc3": 3, "tc1": 1}
-# 3-D layers under the "ws" back end: snb_conv_c32_ws has a 3-D variant (all 27 tap images resident, 3.4x less L2 traffic), but at
-# batch 1 its walk along the 24 disparity slices fills only 116 of 148 SMs and it measures 55-60 us per KITTI filter layer against
-# 52-56 us for the TMA kernel of conv3d_c32_tma.cu in the same fp16 operand format — so that one stays the product kernel for 3-D.
-WS_3D_FMT = "h"
+# 3-D layers under the "ws" back end: the 3-D variant of snb_conv_c32_ws (all 27 tap images resident, every raw row brought on
+# chip once per three disparity taps and split to fp16 ONCE, in place).  38 us per KITTI filter layer inside a graph against 50 us
+# for the TMA kernel of conv3d_c32_tma.cu ("h": the same operand format, weights streamed per window), which stays as the cross-check.
+WS_3D_FMT = "ws"
 
 
 def _fmt(three_d):
