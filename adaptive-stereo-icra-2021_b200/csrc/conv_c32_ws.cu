@@ -36,6 +36,8 @@
 // 10-17 epilogue (two groups, alternating tiles).
 #include <cuda.h>
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
 #include "tc_common.cuh"
 
 namespace wsk {
@@ -56,7 +58,7 @@ constexpr int MODE_2D = 0, MODE_3D = 1, MODE_P4 = 2;
 template <int MODE> struct Cfg {
   static constexpr bool TWO = MODE != MODE_2D;           // two accumulator rings D1 / D2 and [wh | wl''] images
   static constexpr bool FLAT = MODE == MODE_3D;          // positions = un-padded flat index of a (b,d) slice, walk along d
-  static constexpr bool ONCE = MODE == MODE_3D;          // converters: split every raw row ONCE, in place, then read it three times
+  static constexpr bool ONCE = MODE != MODE_2D;          // converters: split every raw row ONCE, in place, then read it three times
   static constexpr int NWIN = MODE == MODE_3D ? 3 : (MODE == MODE_P4 ? 4 : 1);     // raw windows per walk step (3-D: kh; P4: phase)
   static constexpr int NIMG = MODE == MODE_3D ? 9 : (MODE == MODE_P4 ? 10 : 3);    // resident weight images
   static constexpr int IMG_BYTES = TWO ? B_BYTES : 2 * B_BYTES;     // TWO: [wh | wl''] 12 KB; 2-D: P [wh | wl] + Q [2^-11 wh | -] 24 KB
@@ -77,7 +79,9 @@ struct Params {
   const float* wimg; float* y;
   int B, D, H, W, dil;
   int ncb;                  // 2-D: column blocks of 128 pixels per row.  3-D: 128-position tiles per (b,d) slice
-  int cmax, L, nseg;        // longest chain (2-D: ceil(H/dil) rows, 3-D: D slices), tiles per strip, segments per chain
+  int cmax;                 // longest chain (2-D: ceil(H/dil) rows, 3-D: D slices)
+  int La, nsa, Lb;          // every chain = nsa long strips of La tiles + one short strip of Lb tiles (Lb may be 0)
+  int nchains, nlong;       // nlong = nchains * nsa; strips [0, nlong) are the long ones, [nlong, nstrips) the short ones
   int nstrips;
   int res_mode;             // 0: none, 1: residual == input (on-chip, 2-D), 2: residual from global memory
   snb_conv_epilogue e;
@@ -93,22 +97,30 @@ struct Strip { int b, cb, z0, ntiles; };
 template <bool D3>      // D3 = flat 3-D geometry
 __device__ __forceinline__ Strip decode_strip(const Params& p, int sid) {
   Strip s;
-  const int seg = sid % p.nseg; sid /= p.nseg;
+  int j0, cap;
+  if (sid < p.nlong) { const int seg = sid / p.nchains; sid -= seg * p.nchains; j0 = seg * p.La; cap = p.La; }
+  else               { sid -= p.nlong; j0 = p.nsa * p.La; cap = p.Lb; }
   if (D3) {
     s.cb = sid % p.ncb; s.b = sid / p.ncb;
-    const int j0 = seg * p.L;
-    s.ntiles = p.D - j0; if (s.ntiles > p.L) s.ntiles = p.L; if (s.ntiles < 0) s.ntiles = 0;
+    s.ntiles = p.D - j0; if (s.ntiles > cap) s.ntiles = cap; if (s.ntiles < 0) s.ntiles = 0;
     s.z0 = j0;
   } else {
     const int rho = sid % p.dil; sid /= p.dil;
     s.cb = sid % p.ncb; s.b = sid / p.ncb;
     const int chain = (rho < p.H) ? (p.H - rho + p.dil - 1) / p.dil : 0;
-    const int j0 = seg * p.L;
-    s.ntiles = chain - j0; if (s.ntiles > p.L) s.ntiles = p.L; if (s.ntiles < 0) s.ntiles = 0;
+    s.ntiles = chain - j0; if (s.ntiles > cap) s.ntiles = cap; if (s.ntiles < 0) s.ntiles = 0;
     s.z0 = rho + j0 * p.dil;
   }
   return s;
 }
+// Strips are dealt to the CTAs in rounds of gridDim.x, every other round in reverse order ("snake"): the long strips come first,
+// so the CTAs that got the short ones at the end of a round are the first to get a second strip.  All four roles walk the same
+// sequence.  (sid_k >= k * gridDim.x, so the first invalid k ends the sequence.)
+__device__ __forceinline__ int strip_at(int k) {
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  return k * G + ((k & 1) ? G - 1 - b : b);
+}
+#define WS_FOR_STRIPS(sid) for (int _k = 0, sid = strip_at(0); sid < p.nstrips; sid = strip_at(++_k))
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -237,7 +249,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       uint32_t ac = 0;
       long long w_r = 0; const long long t0 = clock64();
       const uint32_t bytes = (uint32_t)RW * 128u;
-      for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+      WS_FOR_STRIPS(sid) {
         const Strip s = decode_strip<D3>(p, sid);
         if (s.ntiles == 0) continue;
         for (int u = 0; u < s.ntiles + 2; ++u) {
@@ -266,7 +278,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     long long tile_base = 0;
     uint32_t win_count = 0;
     long long t_full = 0, t_tempty = 0; const long long t_mbegin = clock64();
-    for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+    WS_FOR_STRIPS(sid) {
       const Strip s = decode_strip<D3>(p, sid);
       if (s.ntiles == 0) continue;
       for (int u = 0; u < s.ntiles + 2; ++u) {
@@ -357,7 +369,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     long long w_rf = 0, w_ae = 0, w_rs = 0; const long long t0 = clock64();
     uint32_t cnt = 0;                                              // windows so far (all strips)
     long long tile_base = 0;
-    for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+    WS_FOR_STRIPS(sid) {
       const Strip s = decode_strip<D3>(p, sid);
       if (s.ntiles == 0) continue;
       int wcol = 0;
@@ -410,6 +422,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             tc_fence_after();
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
+              if (kw >= nkw) break;
               const int row = m + kw;
               const unsigned char* rp = rw + row * 128;
               uint32_t hl[32];
@@ -418,12 +431,12 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 const uint4 q = *reinterpret_cast<const uint4*>(rp + ((c ^ (row & 7)) << 4));
                 hl[4 * c] = q.x; hl[4 * c + 1] = q.y; hl[4 * c + 2] = q.z; hl[4 * c + 3] = q.w;
               }
-              if (kw == 2) {                                  // last read of the window: release it once the loads have returned
+              if (kw == nkw - 1) {                            // last read of the window: release it once the loads have returned
                 const uint32_t dep = hl[0] ^ hl[4] ^ hl[8] ^ hl[12] ^ hl[16] ^ hl[20] ^ hl[24] ^ hl[28];
                 __syncwarp();
                 if (lane == 0) mbar_arrive_after(&rempty[sr], dep);
               }
-              if ((kw == 0 && wcol == 0) || (kw == 2 && wcol == p.W - 1)) {
+              if (D3 && ((kw == 0 && wcol == 0) || (kw == 2 && wcol == p.W - 1))) {
                 // un-padded flat index: this tap wrapped into the neighbouring image row -> it is zero padding
 #pragma unroll
                 for (int i = 0; i < 32; ++i) hl[i] = 0u;
@@ -504,7 +517,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     asm volatile("bar.sync 6, 256;\n" ::: "memory");          // sPar (written by the first epilogue warp) is visible
     long long tcount = 0;
     long long t_tfull = 0, t_px = 0, t_out = 0, t_bar = 0, t_ld = 0, t_bar2 = 0; const long long t_ebegin = clock64();
-    for (int sid = blockIdx.x; sid < p.nstrips; sid += gridDim.x) {
+    WS_FOR_STRIPS(sid) {
       const Strip s = decode_strip<D3>(p, sid);
       const int x0 = s.cb * 128;                               // first pixel (2-D) / flat position (3-D) of the tile
       for (int j = 0; j < s.ntiles; ++j, ++tcount) {
@@ -634,24 +647,53 @@ static int ws_setup(const snb_conv_geom* g, wsk::Params& p, const char* who) {
   p.B = g->B; p.D = g->D; p.H = g->H; p.W = g->W; p.dil = g->dil;
   p.ncb = d3 ? snb_ceil_div((long long)g->H * g->W, 128) : snb_ceil_div(g->W, 128);
   p.cmax = d3 ? g->D : snb_ceil_div(g->H, g->dil);
-  // Strips = chains of up to cmax tiles along the walk axis, cut into nseg segments of L tiles; a strip costs L + 2 walk steps.
-  // Pick nseg so that the busiest CTA (ceil(strips / SMs) strips) runs the fewest steps.
+  // Strips: every chain of cmax tiles along the walk axis is cut into nsa strips of La tiles plus one strip of the remaining Lb
+  // tiles; a strip of L tiles costs L + 2 walk steps.  (La, nsa) minimises the steps of the busiest CTA under the snake dealing of
+  // strip_at() — e.g. the KITTI cost volume (58 chains of 24 slices): 2 x 10 + 4 -> 12 steps on 148 CTAs, where equal halves
+  // (2 x 12) cost 14 steps on 116 CTAs.  The result is cached per (chains, cmax).
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long nchains = (long long)g->B * p.ncb * (d3 ? 1 : g->dil);
-  long long best = -1; int best_nseg = 1;
-  for (int nseg = 1; nseg <= p.cmax && nseg <= 256; ++nseg) {
-    const int L = snb_ceil_div(p.cmax, nseg);
-    if (L < 2 && nseg > 1) break;
-    const long long ns = nchains * nseg;
-    const long long cost = ((ns + sms - 1) / sms) * (L + 2);
-    if (best < 0 || cost < best) { best = cost; best_nseg = nseg; }
+  SNB_REQUIRE(nchains * p.cmax < (1ll << 30), "%s: too many strips", who);
+  struct Plan { long long nchains; int cmax, sms, La, nsa, Lb; };
+  static std::mutex mu;
+  static std::vector<Plan> cache;
+  Plan plan{nchains, p.cmax, sms, 0, 0, 0};
+  bool hit = false;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Plan& c : cache) if (c.nchains == nchains && c.cmax == p.cmax && c.sms == sms) { plan = c; hit = true; break; }
   }
-  p.nseg = best_nseg;
-  p.L = snb_ceil_div(p.cmax, p.nseg);
-  p.nseg = snb_ceil_div(p.cmax, p.L);                  // drop segments that would be empty for every chain
-  const long long ns = nchains * p.nseg;
+  if (!hit) {
+    long long best = -1;
+    std::vector<long long> load;
+    for (int La = 1; La <= p.cmax; ++La) {
+      const int nsa = p.cmax / La, Lb = p.cmax - nsa * La;
+      if ((La < 2 || (Lb > 0 && Lb < 2 && La > 2)) && p.cmax >= 4) continue;      // strips of one tile cost three steps: not worth looking at
+      const long long nlong = nchains * nsa, ns = nlong + (Lb > 0 ? nchains : 0);
+      long long cost;
+      if (ns > 16ll * sms) {
+        cost = ((nlong + sms - 1) / sms) * (La + 2) + (Lb > 0 ? ((nchains + sms - 1) / sms) * (Lb + 2) : 0);   // many strips: an upper bound will do
+      } else {
+        const int G = (int)(ns < sms ? ns : sms);
+        load.assign(G, 0);
+        for (long long sid = 0; sid < ns; ++sid) {
+          const long long k = sid / G; const int pos = (int)(sid % G);
+          load[(k & 1) ? G - 1 - pos : pos] += (sid < nlong ? La : Lb) + 2;
+        }
+        cost = 0;
+        for (long long v : load) cost = v > cost ? v : cost;
+      }
+      if (best < 0 || cost < best) { best = cost; plan.La = La; plan.nsa = nsa; plan.Lb = Lb; }
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 256) cache.clear();
+    cache.push_back(plan);
+  }
+  p.La = plan.La; p.nsa = plan.nsa; p.Lb = plan.Lb;
+  p.nchains = (int)nchains; p.nlong = (int)(nchains * p.nsa);
+  const long long ns = (long long)p.nlong + (p.Lb > 0 ? nchains : 0);
   SNB_REQUIRE(ns < (1ll << 30), "%s: too many strips", who);
   p.nstrips = (int)ns;
   return 0;
