@@ -59,6 +59,35 @@ cost_volume_fwd_kernel(const float4* __restrict__ left, const float4* __restrict
   }
 }
 
+// Small volumes (the batch-1 KITTI volume is 22.5 MB and stays in L2): a CTA per (row, disparity level) and no staging at all —
+// both operand rows are L1 / L2 hits, every float4 of output is two independent loads, a subtraction and a store, and all
+// B*H*D CTAs are resident at once, so nothing waits on a staging round trip.
+__global__ void __launch_bounds__(256)
+cost_volume_fwd_direct_kernel(const float4* __restrict__ left, const float4* __restrict__ right, float4* __restrict__ cost,
+                              int D, int H, int W) {
+  pdl_launch(); pdl_wait();
+  const int row = blockIdx.x, d = blockIdx.y;        // row = b*H + y
+  const int b = row / H, y = row - b * H;
+  const int row_f4 = W * 8, first = min(d, W) * 8;
+  const float4* lp = left + (size_t)row * row_f4;
+  const float4* rp = right + (size_t)row * row_f4 - d * 8;
+  float4* out = cost + (((size_t)b * D + d) * H + y) * (size_t)row_f4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < first; i += 256) out[i] = zero;
+  int i = first + threadIdx.x;
+  for (; i + 768 < row_f4; i += 1024) {               // four independent load pairs in flight per thread
+    float4 l[4], r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { l[k] = __ldg(lp + i + 256 * k); r[k] = __ldg(rp + i + 256 * k); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[i + 256 * k] = make_float4(l[k].x - r[k].x, l[k].y - r[k].y, l[k].z - r[k].z, l[k].w - r[k].w);
+  }
+  for (; i < row_f4; i += 256) {
+    const float4 l = __ldg(lp + i), r = __ldg(rp + i);
+    out[i] = make_float4(l.x - r.x, l.y - r.y, l.z - r.z, l.w - r.w);
+  }
+}
+
 // Adjoint: dL[x] = sum_{d<=x} g[d][x];  dR[x'] = -sum_{d : x'+d < W} g[d][x'+d]   
 __global__ void __launch_bounds__(256)
 cost_volume_bwd_kernel(const float4* __restrict__ g, float4* __restrict__ dleft, float4* __restrict__ dright,
@@ -86,6 +115,13 @@ extern "C" int snb_cost_volume_fwd(const float* left, const float* right, float*
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int rows = B * H;
+  // Volumes that stay in L2 (the batch-1 KITTI volume is 22.5 MB) take the un-staged kernel: 7.1 against 11.0 us back to back
+  // (3.4 TB/s); from batch 8 on (195 MB) both forms run at the same 4.8 TB/s and the staged one moves a tenth of the operand bytes.
+  if ((size_t)B * D * H * W * 128 <= (size_t)64 << 20 && D <= 65535) {
+    snb_launch(cost_volume_fwd_direct_kernel, dim3(rows, D), 256, 0, stream, (const float4*)left, (const float4*)right, (float4*)cost, D, H, W);
+    SNB_LAUNCH_CHECK("cost_volume_fwd_direct_kernel");
+    return 0;
+  }
   // >= 2 CTAs per SM so one CTA's bulk-copy latency hides behind the stores of another; segments of at least 8 columns
   int nseg = (2 * sms + rows - 1) / rows;
   if (nseg > (W + 7) / 8) nseg = (W + 7) / 8;

@@ -32,7 +32,8 @@ def close(got, ref, rtol, what=""):
   assert err <= rtol * mag, f"{what}: max err {err:.3e} vs magnitude {mag:.3e} (rtol {rtol})"
 
 
-@pytest.mark.parametrize("B,H,W,D", [(1, 5, 40, 24), (2, 7, 16, 24), (1, 47, 156, 24), (1, 3, 9, 12), (1, 4, 33, 6)])
+@pytest.mark.parametrize("B,H,W,D", [(1, 5, 40, 24), (2, 7, 16, 24), (1, 47, 156, 24), (1, 3, 9, 12), (1, 4, 33, 6),
+                                     (4, 47, 156, 24), (3, 40, 150, 40)])      # the last two (> 64 MB) take the TMA-staged kernel
 def test_cost_volume_bit_exact(B, H, W, D):
   L, R = rnd(B, 32, H, W, seed=1), rnd(B, 32, H, W, seed=2)
   ref = O.cost_volume_numpy(L.numpy(), R.numpy(), D)
