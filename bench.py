@@ -492,7 +492,7 @@ def gpu_arm(args):
       ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
     except Exception:
       pass
-    ncu_k = ncu.get("conv3d_tma_h" if dom_name == "filter_conv3d_32x32" else "conv2d_ws", {})
+    ncu_k = ncu.get("conv3d_ws" if dom_name == "filter_conv3d_32x32" else "conv2d_ws_dil4", {})
     roofline = {"kernel": dom_name, "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
                 "frac": dom["frac"], "traffic": ncu_k.get("dram_bytes"),
                 "traffic_source": "profiles/r2_ncu_summary.json (ncu --set full capture of this kernel; not re-measured in this run)",
