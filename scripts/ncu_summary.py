@@ -54,7 +54,9 @@ for key, sub, sel in NAMES:
       "dram_bytes": (scale_bytes(f(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum")) or 0) + (scale_bytes(f(r, "dram__bytes_write.sum"), unit("dram__bytes_write.sum")) or 0),
       "dram_read_bytes": scale_bytes(f(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum")),
       "dram_write_bytes": scale_bytes(f(r, "dram__bytes_write.sum"), unit("dram__bytes_write.sum")),
-      "tensor_pipe_active_pct": None if (hm is None or not cyc) else round(100.0 * hm / cyc, 1),
+      "tensor_pipe_active_pct": f(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+      "tensor_pipe_active_pct_of_active_cycles": f(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+      "tensor_pipe_in_flight_pct": None if (hm is None or not cyc) else round(50.0 * hm / cyc, 1),   # realtime counter is per TPC (2 SMs)
       "tensor_mem_active_pct": f(r, "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
       "l1tex_throughput_pct": f(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
       "lts_throughput_pct": f(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
@@ -69,4 +71,6 @@ for key, sub, sel in NAMES:
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 for k, e in out.items():
   if isinstance(e, dict):
-    print(f"{k:28s} {e['duration_us']:7.1f} us  dram {e['dram_bytes'] / 1e6:7.1f} MB  tensor {e['tensor_pipe_active_pct']}  l1tex {e['l1tex_throughput_pct']}")
+    print(f"{k:28s} {e['duration_us']:7.1f} us  dram {e['dram_bytes'] / 1e6:7.1f} MB (r {e['dram_read_bytes'] / 1e6:6.1f} w {e['dram_write_bytes'] / 1e6:6.1f})  "
+          f"tensor pipe active {e['tensor_pipe_active_pct']:5.1f} % (in flight {e['tensor_pipe_in_flight_pct']})  l1tex {e['l1tex_throughput_pct']:5.1f} %  "
+          f"lts {e['lts_throughput_pct']:5.1f} %  smem wavefronts {e['smem_lsu_wavefronts']:.3g}  warp instr {e['warp_instructions']:.3g}  regs {e['registers_per_thread']:.0f}")

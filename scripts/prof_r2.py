@@ -21,7 +21,7 @@ xs = torch.randn(2, 47, 156, 32, device=dev); gs = ops.geom(tuple(xs.shape), 3)
 cz = torch.rand(1, 47, 156, device=dev) * 20; wr = torch.randn(32, 4, 3, 3, device=dev) * 0.1
 wt = torch.randn(1, 32, 3, 3, device=dev) * 0.1; bt = torch.randn(1, device=dev)
 if os.environ.get("PROF_SET", "all") in ("b", "all"):  # the rest of the forward: first conv, P4, small layers, refinement in / out
-  for _ in range(3):
+  for _ in range(int(os.environ.get("PROF_REPS", "3"))):
     flush.zero_()
     ph = ops.conv5x5s2_c3_phases(img2, w0, b)
     flush.zero_()
@@ -40,7 +40,7 @@ if os.environ.get("PROF_SET", "all") in ("b", "all"):  # the rest of the forward
   if os.environ.get("PROF_SET", "all") == "b":
     print("ok")
     sys.exit(0)
-for _ in range(3):
+for _ in range(int(os.environ.get("PROF_REPS", "3"))):
   flush.zero_()
   ops.conv_c32_tc(x2, wi2, g2, bias=b, scale=sc, shift=sh, residual=x2, lrelu=True, fmt="ws")
   flush.zero_()
