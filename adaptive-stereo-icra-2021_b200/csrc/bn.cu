@@ -44,6 +44,22 @@ bn_finalize_kernel(const float* __restrict__ stats, int ntiles, double count, co
   }
 }
 
+// Running-statistics update of ONE train-mode BatchNorm call, applied later than its bn_finalize (which was launched without the
+// running buffers): lets two passes through the same layers run on two streams (left / right image, adapt.py:72) and still
+// update running_mean / running_var / num_batches_tracked in the reference's order.  var = 1 / invstd^2 - eps.
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ invstd, double count, float eps,
+                                         float momentum, float* running_mean, float* running_var, long long* num_batches_tracked) {
+  pdl_launch(); pdl_wait();
+  const int ch = threadIdx.x;
+  const double is = (double)invstd[ch];
+  double var = 1.0 / (is * is) - (double)eps;
+  if (var < 0.0) var = 0.0;
+  const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+  running_mean[ch] = (float)((1.0 - momentum) * (double)running_mean[ch] + momentum * (double)mean[ch]);
+  running_var[ch] = (float)((1.0 - momentum) * (double)running_var[ch] + momentum * unbiased);
+  if (ch == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+}
+
 // Stage 1 of the two-stage statistics reduction: block b sums rows [b*chunk, (b+1)*chunk) of stats [ntiles][64] into
 // scratch[b][64] (fp64 accumulation, fixed order).  A single CTA walking ~1 MB of partials (one row per image row x column
 // block at full resolution) is bound by one SM's load bandwidth: 12-23 us per layer, 23 layers per adaptation step.
@@ -110,6 +126,15 @@ extern "C" int snb_bn_finalize_ws(const float* stats, int ntiles, long long coun
   snb_launch(bn_stats_prereduce_kernel, nblk, 256, 0, stream, stats, ntiles, chunk, scratch);
   SNB_LAUNCH_CHECK("bn_stats_prereduce_kernel");
   return bn_finalize_impl(scratch, nblk, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd, stream);
+}
+
+extern "C" int snb_bn_running_update(const float* mean, const float* invstd, long long count, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, float momentum, float eps, void* stream) {
+  SNB_REQUIRE(mean && invstd && running_mean && running_var && count > 0, "snb_bn_running_update: bad args");
+  snb_launch(bn_running_update_kernel, 1, 32, 0, stream, mean, invstd, (double)count, eps, momentum, running_mean, running_var,
+             num_batches_tracked);
+  SNB_LAUNCH_CHECK("bn_running_update_kernel");
+  return 0;
 }
 
 extern "C" int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,

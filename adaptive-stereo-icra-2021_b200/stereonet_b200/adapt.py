@@ -28,7 +28,7 @@ class AdaptStepper:
   (`replay=(left, right, gt)`) is captured too (static replay buffers, fused Khamis loss)."""
 
   def __init__(self, feature_net, stereo_net, optimizer, height=None, width=None, clip_grad_norm=True, er_loss_weight=0.05,
-               use_graph=False, batched_replay=False):
+               use_graph=False, batched_replay=False, two_streams=True):
     self.feature_net, self.stereo_net, self.optimizer = feature_net, stereo_net, optimizer
     self.clip, self.er_loss_weight = clip_grad_norm, er_loss_weight
     self.use_graph = use_graph              # (height / width are accepted for call-site compatibility with the reference's warper)
@@ -36,6 +36,7 @@ class AdaptStepper:
     # frame instead of a second full pass (adapt.py:339-349).  Off by default: train-mode BatchNorm then normalises with the
     # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
     self.batched_replay = batched_replay
+    self.two_streams, self._side = two_streams, None
     self._graphs = {}
     self._wprep = None                      # fused.WeightPrepBatch: all derived weight images in one launch per step
     self.launches_per_step = None
@@ -47,8 +48,32 @@ class AdaptStepper:
       raise RuntimeError("AdaptStepper(use_graph=True) needs make_optimizer(..., capturable=True) or fused=True")
 
   def predict(self, left, right):
-    fl, fr = self.feature_net(left), self.feature_net(right)                       # adapt.py:72
-    return self.stereo_net(left, fl, fr, "l", output_cost_volume=True)             # adapt.py:73
+    if not (self.two_streams and left.is_cuda and torch.is_grad_enabled()):
+      fl, fr = self.feature_net(left), self.feature_net(right)                     # adapt.py:72
+      return self.stereo_net(left, fl, fr, "l", output_cost_volume=True)           # adapt.py:73
+    # The two feature passes (and, through autograd, their backward passes) are independent chains of small, latency-bound
+    # kernels on a fraction of the SMs: the right-image pass runs on a second stream next to the left one.  Both passes update
+    # the same BatchNorm buffers, left first in the reference, so the right pass defers its running-statistics updates and
+    # they are applied on the main stream after the join.
+    from .autograd import fused
+    main = torch.cuda.current_stream(left.device)
+    if self._side is None:
+      self._side = torch.cuda.Stream(device=left.device)
+    side = self._side
+    side.wait_stream(main)
+    fl = self.feature_net(left)
+    pending = []
+    with torch.cuda.stream(side):
+      fused.DEFER_BN = pending
+      try:
+        fr = self.feature_net(right)
+      finally:
+        fused.DEFER_BN = None
+    main.wait_stream(side)
+    if not torch.cuda.is_current_stream_capturing():
+      fr.record_stream(main)
+    fused.flush_deferred_bn(pending)
+    return self.stereo_net(left, fl, fr, "l", output_cost_volume=True)
 
   def step(self, left, right, replay=None, sync_grads=None, dp_params=None, dp_group=None, dp_bucket=None):
     """One gradient update (adapt.py:313-314,328-337,381-394).  `replay` = (left, right, gt_disp) adds the

@@ -33,11 +33,29 @@ def state_epoch():
   return (EPOCH, BN_EPOCH)
 
 
+# While a list is installed here, train-mode BatchNorm calls do not touch the running statistics; they append
+# (bn, mean, invstd, count) instead and flush_deferred_bn() applies the updates later, in call order.  adapt.AdaptStepper uses
+# it for the feature pass it runs on a second stream (the left and right passes update the SAME buffers, in that order).
+DEFER_BN = None
+
+
 def bn_finalize(stats, count, bn):
   """Train-mode BatchNorm statistics (ops.bn_finalize) + invalidation of what was derived from the running statistics."""
+  if DEFER_BN is not None and bn.running_mean is not None:
+    out = ops.bn_finalize(stats, count, bn, update_running=False)
+    DEFER_BN.append((bn, out[2], out[3], count))
+    return out
   out = ops.bn_finalize(stats, count, bn)
   bump_bn_epoch()
   return out
+
+
+def flush_deferred_bn(pending):
+  for bn, mean, invstd, count in pending:
+    ops.bn_running_update(bn, mean, invstd, count)
+  if pending:
+    bump_bn_epoch()
+  del pending[:]
 
 
 # Fused optimizers (torch.optim.Adam(fused=True), torch._fused_adam_) update parameters in place WITHOUT bumping their

@@ -369,6 +369,13 @@ def bn_finalize(stats, count, bn, update_running=True):
   return out[0], out[1], out[2], out[3]
 
 
+def bn_running_update(bn, mean, invstd, count):
+  """The running-statistics update of a bn_finalize(..., update_running=False) call, applied later (stream-ordered)."""
+  check(_cabi.lib().snb_bn_running_update(_p(mean), _p(invstd), int(count), _p(bn.running_mean), _p(bn.running_var),
+                                          _p(bn.num_batches_tracked), BN_MOMENTUM, BN_EPS, _stream(mean)), "snb_bn_running_update")
+  _count()
+
+
 def bn_apply(z, scale, shift, residual=None, lrelu=True):
   y = torch.empty_like(z)
   check(_cabi.lib().snb_bn_apply(_p(z), _p(scale), _p(shift), _p(residual), _p(y), z.numel() // 32, 1 if lrelu else 0,

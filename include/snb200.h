@@ -204,6 +204,11 @@ SNB_API int snb_bn_finalize(const float* stats, int ntiles, long long count, con
 SNB_API int snb_bn_finalize_ws(const float* stats, int ntiles, long long count, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                        float* scale, float* shift, float* mean, float* invstd, float* scratch, void* stream);
+/* The running-statistics half of snb_bn_finalize[_ws] for a call that was made WITHOUT running buffers: running = (1 - m) running
+ * + m batch statistic (unbiased variance from invstd), num_batches_tracked += 1.  Lets the left / right feature passes of one
+ * adaptation step (adapt.py:72) run on two streams and still update nn.BatchNorm's buffers in the reference's order. */
+SNB_API int snb_bn_running_update(const float* mean, const float* invstd, long long count, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, float momentum, float eps, void* stream);
 /* y = [residual +] LeakyReLU(z*scale + shift) over n positions x 32 channels. */
 SNB_API int snb_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,
                  long long npos, int lrelu, void* stream);
