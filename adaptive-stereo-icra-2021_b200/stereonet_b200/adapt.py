@@ -36,7 +36,7 @@ class AdaptStepper:
     # frame instead of a second full pass (adapt.py:339-349).  Off by default: train-mode BatchNorm then normalises with the
     # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
     self.batched_replay = batched_replay
-    self.two_streams, self._side = two_streams, None
+    self.two_streams, self._side, self._wstream = two_streams, None, None
     self._graphs = {}
     self._wprep = None                      # fused.WeightPrepBatch: all derived weight images in one launch per step
     self.launches_per_step = None
@@ -105,11 +105,20 @@ class AdaptStepper:
     self._refresh_weights()
     if replay is not None and self.batched_replay:
       return self._fwd_bwd_batched(left, right, replay)
-    outputs = self.predict(left, right)
-    loss = monodepth_single_loss(left, right, outputs, s)                          # adapt.py:328-337 (snb_photo_loss)
-    if replay is not None:
-      out_er = self.predict(replay[0], replay[1])                                   # adapt.py:339-349: a second full pass
-      loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
+    from .autograd import fused
+    if self.two_streams and left.is_cuda:
+      if self._wstream is None:
+        self._wstream = torch.cuda.Stream(device=left.device)
+      fused.WGRAD_STREAM = self._wstream                                            # weight gradients next to the data path
+      fused.wgrad_token((1,), left.device)                                          # (creates the token buffer outside any capture)
+    try:
+      outputs = self.predict(left, right)
+      loss = monodepth_single_loss(left, right, outputs, s)                        # adapt.py:328-337 (snb_photo_loss)
+      if replay is not None:
+        out_er = self.predict(replay[0], replay[1])                                 # adapt.py:339-349: a second full pass
+        loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
+    finally:
+      fused.WGRAD_STREAM = None
     fcs = feature_contrast_mean(outputs["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
     self.optimizer.zero_grad()
     loss.backward()

@@ -40,8 +40,71 @@ class ConvBnLrelu(torch.autograd.Function):
     return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None
 
 
+def _on_this_stream(*tensors):
+  """Tensors allocated on another stream are about to be read by kernels of the current one: tell the caching allocator, or
+  their memory could be handed out again on the owning stream while these kernels still run."""
+  cur = torch.cuda.current_stream(tensors[0].device)
+  for t in tensors:
+    t.record_stream(cur)
+
+
+class WgradToken(torch.autograd.Function):
+  """Carries the weight of a conv into the graph on its OWN stream.  forward returns a zero-stride token shaped like the conv's
+  output (one float of storage, no kernel); ConvBnLreluSplit returns dz as the token's gradient, so THIS node's backward — which
+  autograd runs on the stream this forward ran on, with the proper event waits — computes the weight gradient next to the data
+  path instead of inside it: the tensor-bound wgrad kernel overlaps the HBM-bound BatchNorm backward of the next layer."""
+
+  @staticmethod
+  def forward(ctx, w, x, dil):
+    ctx.save_for_backward(x)
+    ctx.dil, ctx.wshape = dil, tuple(w.shape)
+    return fused.wgrad_token(x.shape, x.device)
+
+  @staticmethod
+  def backward(ctx, dz):
+    (x,) = ctx.saved_tensors
+    dz = _c(dz)
+    _on_this_stream(x, dz)
+    g = ops.geom(x.shape, 3, stride=1, dil=ctx.dil)
+    return fused.conv3x3_c32_wgrad(x, dz, g, ctx.wshape), None, None
+
+
+class ConvBnLreluSplit(torch.autograd.Function):
+  """ConvBnLrelu with the weight gradient split off into WgradToken (same kernels, same arithmetic)."""
+
+  @staticmethod
+  def forward(ctx, x, tok, b, gamma, beta, conv, bn, dil, residual, training):
+    g = ops.geom(x.shape, 3, stride=1, dil=dil)
+    z, stats = fused.conv3x3_c32(x, conv, g, bias=b.detach(), want_stats=training)
+    if training:
+      scale, shift, mean, invstd = fused.bn_finalize(stats, z.numel() // 32, bn)
+    else:
+      scale, shift = fused.bn_fold(bn)
+      mean, invstd = bn.running_mean, fused.bn_invstd(bn)
+    y = ops.bn_apply(z, scale, shift, residual=x if residual else None, lrelu=True)
+    ctx.save_for_backward(x, z, scale, shift, mean, invstd)
+    ctx.conv, ctx.dil, ctx.residual, ctx.training = conv, dil, residual, training
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, z, scale, shift, mean, invstd = ctx.saved_tensors
+    dy = _c(dy)
+    dz, dgamma, dbeta, dbias = ops.bn_lrelu_bwd(z, dy, scale, shift, mean, invstd, ctx.training, lrelu=True)
+    g = ops.geom(x.shape, 3, stride=1, dil=ctx.dil)
+    dx = None
+    if ctx.needs_input_grad[0]:
+      dx, _ = fused.conv3x3_c32_dgrad(dz, ctx.conv, g, residual=dy if ctx.residual else None)
+    return dx, dz, dbias, dgamma, dbeta, None, None, None, None, None
+
+
 def conv_bn_lrelu_autograd(x, conv, bn, dil, residual, training):
-  return ConvBnLrelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, conv, bn, dil, residual, training)
+  ws = fused.WGRAD_STREAM
+  if ws is None or not conv.weight.requires_grad:
+    return ConvBnLrelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, conv, bn, dil, residual, training)
+  with torch.cuda.stream(ws):
+    tok = WgradToken.apply(conv.weight, x.detach(), dil)
+  return ConvBnLreluSplit.apply(x, tok, conv.bias, bn.weight, bn.bias, conv, bn, dil, residual, training)
 
 
 class ConvC32(torch.autograd.Function):
@@ -79,6 +142,67 @@ class ConvC32(torch.autograd.Function):
     else:
       dw = ops.conv_c32_wgrad(x, dy, g, ctx.wshape)
     return dx, dw, ops.channel_sum(dy), None, None, None
+
+
+class WgradTokenC32(torch.autograd.Function):
+  """WgradToken for ConvC32 (bias-only 32->32 convs: 5x5 stride 2, 3x3): see WgradToken."""
+
+  @staticmethod
+  def forward(ctx, w, x, ksize, stride):
+    g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
+    ctx.save_for_backward(x)
+    ctx.ksize, ctx.stride, ctx.wshape = ksize, stride, tuple(w.shape)
+    oshape = tuple(ops.out_shape(g, False))
+    return fused.wgrad_token(oshape, x.device)
+
+  @staticmethod
+  def backward(ctx, dy):
+    (x,) = ctx.saved_tensors
+    dy = _c(dy)
+    _on_this_stream(x, dy)
+    g = ops.geom(x.shape, ctx.ksize, stride=ctx.stride, dil=1, pad=ctx.ksize // 2)
+    if ctx.ksize == 3 and ctx.stride == 1:
+      return fused.conv3x3_c32_wgrad(x, dy, g, ctx.wshape), None, None, None
+    return ops.conv_c32_wgrad(x, dy, g, ctx.wshape), None, None, None
+
+
+class ConvC32Split(torch.autograd.Function):
+  """ConvC32 with the weight gradient split off into WgradTokenC32."""
+
+  @staticmethod
+  def forward(ctx, x, tok, b, conv, ksize, stride):
+    g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
+    if ksize == 3 and stride == 1:
+      y, _ = fused.conv3x3_c32(x, conv, g, bias=b.detach())
+    elif ksize == 5 and stride == 2:
+      y = fused.conv5x5s2_c32(x, conv, b.detach())
+    else:
+      y, _ = ops.conv_c32(x, fused.wprep(conv), g, bias=b.detach())
+    ctx.conv, ctx.ksize, ctx.stride, ctx.xshape = conv, ksize, stride, tuple(x.shape)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    dy = _c(dy)
+    g = ops.geom(ctx.xshape, ctx.ksize, stride=ctx.stride, dil=1, pad=ctx.ksize // 2)
+    dx = None
+    if ctx.needs_input_grad[0]:
+      if ctx.ksize == 3 and ctx.stride == 1:
+        dx, _ = fused.conv3x3_c32_dgrad(dy, ctx.conv, g)
+      elif ctx.ksize == 5 and ctx.stride == 2:
+        dx = fused.conv5x5s2_c32_dgrad(dy, ctx.conv, ctx.xshape[1], ctx.xshape[2])
+      else:
+        dx, _ = ops.conv_c32(dy, fused.wprep(ctx.conv, 2), ops.geom_transposed(g))
+    return dx, dy, ops.channel_sum(dy), None, None, None
+
+
+def conv_c32_autograd(x, conv, ksize, stride):
+  ws = fused.WGRAD_STREAM
+  if ws is None or not conv.weight.requires_grad:
+    return ConvC32.apply(x, conv.weight, conv.bias, conv, ksize, stride)
+  with torch.cuda.stream(ws):
+    tok = WgradTokenC32.apply(conv.weight, x.detach(), ksize, stride)
+  return ConvC32Split.apply(x, tok, conv.bias, conv, ksize, stride)
 
 
 class Conv5x5s2First(torch.autograd.Function):

@@ -33,6 +33,20 @@ def state_epoch():
   return (EPOCH, BN_EPOCH)
 
 
+# A torch.cuda.Stream installed here (adapt.AdaptStepper does, around its forward) moves the weight gradients of the conv + BN +
+# LeakyReLU layers onto that stream: see functions.WgradToken.
+WGRAD_STREAM = None
+_TOKEN = {}
+
+
+def wgrad_token(shape, device):
+  """Zero-stride token of `shape` over one persistent float (never written): no allocation, so it can be handed out under a
+  stream that is not (yet) part of an ongoing graph capture.  AdaptStepper creates the buffer in its eager warm-up step."""
+  buf = _TOKEN.get(device)
+  if buf is None:
+    buf = _TOKEN[device] = torch.zeros((1,), device=device, dtype=torch.float32)
+  return buf.as_strided(tuple(shape), (0,) * len(shape))
+
 # While a list is installed here, train-mode BatchNorm calls do not touch the running statistics; they append
 # (bn, mean, invstd, count) instead and flush_deferred_bn() applies the updates later, in call order.  adapt.AdaptStepper uses
 # it for the feature pass it runs on a second stream (the left and right passes update the SAME buffers, in that order).
@@ -315,7 +329,7 @@ def conv_plain(x, conv, ksize, stride):
   g = ops.geom(x.shape, ksize, stride=stride, dil=1, pad=ksize // 2)
   if _needs_grad(x, conv):
     from . import functions
-    return functions.ConvC32.apply(x, conv.weight, conv.bias, conv, ksize, stride)
+    return functions.conv_c32_autograd(x, conv, ksize, stride)
   if ksize == 3 and stride == 1:
     y, _ = conv3x3_c32(x, conv, g, bias=conv.bias.detach())
   elif ksize == 5 and stride == 2:

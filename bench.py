@@ -343,7 +343,7 @@ def gpu_arm(args):
     fa.train(); sa.train()
     opt = make_optimizer(fa, sa, lr=5e-5, fused=True)
     bucket = parallel.DPBucket(opt, sa, fa) if world > 1 else None
-    stepper = AdaptStepper(fa, sa, opt, H, W, clip_grad_norm=True, use_graph=not args.no_graph)
+    stepper = AdaptStepper(fa, sa, opt, H, W, clip_grad_norm=True, use_graph=not args.no_graph, two_streams=not args.adapt_single_stream)
     frames = [tuple(t.to(dev) for t in synthetic_pair(1000 + 100 * rank + i, slope=60.0 - 2.0 * i)) for i in range(4)]   # a drifting ramp
     it = [0]
     if world > 1:
@@ -561,6 +561,7 @@ def main():
   ap.add_argument("--skip-cpu-adapt", action="store_true")
   ap.add_argument("--skip-sceneflow", action="store_true")
   ap.add_argument("--skip-timing-configs", action="store_true")
+  ap.add_argument("--adapt-single-stream", action="store_true", help="A/B: both feature passes of the adaptation step on one stream")
   args = ap.parse_args()
 
   rank = int(os.environ.get("RANK", "0"))
