@@ -298,8 +298,58 @@ class RefineHead(torch.autograd.Function):
     return dcoarse, None, dw, dbias, dgamma, dbeta, None, None
 
 
+class WgradTokenRefine(torch.autograd.Function):
+  """WgradToken for RefineHead's Conv2d(4 -> 32): see WgradToken."""
+
+  @staticmethod
+  def forward(ctx, w, coarse, rgb):
+    ctx.save_for_backward(coarse, rgb)
+    return fused.wgrad_token((rgb.shape[0], rgb.shape[2], rgb.shape[3], 32), rgb.device)
+
+  @staticmethod
+  def backward(ctx, dz):
+    coarse, rgb = ctx.saved_tensors
+    dz = _c(dz)
+    _on_this_stream(coarse, rgb, dz)
+    return ops.refine_in_wgrad(coarse, rgb, dz), None, None
+
+
+class RefineHeadSplit(torch.autograd.Function):
+  """RefineHead with the weight gradient split off into WgradTokenRefine."""
+
+  @staticmethod
+  def forward(ctx, coarse, rgb, tok, w, b, gamma, beta, bn, training):
+    up, z, stats = ops.refine_in_conv(coarse, rgb, w, b.detach(), want_stats=training)
+    if training:
+      scale, shift, mean, invstd = fused.bn_finalize(stats, z.numel() // 32, bn)
+    else:
+      scale, shift = fused.bn_fold(bn)
+      mean, invstd = bn.running_mean, fused.bn_invstd(bn)
+    y = ops.bn_apply(z, scale, shift, residual=None, lrelu=True)
+    ctx.save_for_backward(coarse, rgb, w, z, scale, shift, mean, invstd)
+    ctx.training = training
+    return up, y
+
+  @staticmethod
+  def backward(ctx, dup, dy):
+    coarse, rgb, w, z, scale, shift, mean, invstd = ctx.saved_tensors
+    dz, dgamma, dbeta, dbias = ops.bn_lrelu_bwd(z, _c(dy), scale, shift, mean, invstd, ctx.training, lrelu=True)
+    dcoarse = None
+    if ctx.needs_input_grad[0]:
+      wflip = torch.flip(w[:, 0].reshape(32, 9), dims=(1,)).reshape(1, 32, 3, 3).contiguous()
+      taps = ops.conv_c32_taps(dz, wflip, 9)
+      d_up = ops.tapsum_refine_out(taps, None, _c(dup), relu=False)
+      dcoarse = ops.upsample_bilinear_bwd(d_up, coarse.shape[-2], coarse.shape[-1], float(rgb.shape[-1]) / float(coarse.shape[-1]))
+    return dcoarse, None, dz, None, dbias, dgamma, dbeta, None, None
+
+
 def refine_head_autograd(coarse, rgb, conv, bn, training):
-  return RefineHead.apply(coarse, rgb, conv.weight, conv.bias, bn.weight, bn.bias, bn, training)
+  ws = fused.WGRAD_STREAM
+  if ws is None or not conv.weight.requires_grad:
+    return RefineHead.apply(coarse, rgb, conv.weight, conv.bias, bn.weight, bn.bias, bn, training)
+  with torch.cuda.stream(ws):
+    tok = WgradTokenRefine.apply(conv.weight, coarse.detach(), rgb)
+  return RefineHeadSplit.apply(coarse, rgb, tok, conv.weight.detach(), conv.bias, bn.weight, bn.bias, bn, training)
 
 
 class RefineTail(torch.autograd.Function):
