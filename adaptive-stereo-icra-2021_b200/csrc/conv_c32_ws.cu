@@ -175,9 +175,10 @@ __device__ __forceinline__ void issue_window(uint32_t d1, uint32_t d2, const uin
 
 // FOLD (the product setting): one N = 96 MMA over the three ring blocks per product (see above) instead of three N = 32 MMAs:
 // 37 / 40 / 44 us against 41 / 44 / 48 us per KITTI refinement block (dilation 1 / 4 / 8), 55 against 61 us per 3-D filter layer.
-template <int MODE, bool FOLD>
+template <int MODE, bool FOLD, bool RES2>      // RES2: a residual that is not the layer's input (p.res_mode == 2), added from a TMA-loaded tile
 __global__ void __launch_bounds__(NTHREADS_WS, 1)
-conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const Params p) {
+conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
+                   const __grid_constant__ CUtensorMap tmap_res, const Params p) {
   using C = Cfg<MODE>;
   constexpr int NA = C::NA, NRES = C::NRES, NWIN = C::NWIN;
   constexpr bool D3 = C::FLAT, TWO = C::TWO;
@@ -195,7 +196,8 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   uint64_t* tempty = tfull + RING;       // [RING]  epilogue -> MMA
   uint64_t* rsempty = tempty + RING;     // [NRES]  epilogue -> converters (residual slot drained)
   uint64_t* wbar = rsempty + NRES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  uint64_t* resfull = wbar + 1;          // [2 groups][2]  TMA (global residual tile) -> epilogue group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resfull + 4);
   float* sPar = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);    // [64] alpha | beta (16-B aligned)
   float* sRed = sPar + 96;                                  // [2 groups][4 warps][64]
 
@@ -210,6 +212,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
       for (int i = 0; i < RING; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }      // a tile is drained by ONE epilogue group
       for (int i = 0; i < NRES; ++i) mbar_init(&rsempty[i], 4);
+      for (int i = 0; i < 4; ++i) mbar_init(&resfull[i], 1);
       mbar_init(wbar, 1);
       mbar_fence_init();
     }
@@ -507,11 +510,13 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const bool has_stats = e.stats != nullptr;
     const float slope = e.lrelu ? SNB_LRELU_SLOPE : 1.f;
     float* red = sRed + egrp * 256;
-    // Output paths.  res_mode 0 / 1: the staged tile (SWIZZLE_128B image of 128 positions x 32 ch) leaves through ONE TMA tile
-    // store (positions past the row / slice are clipped by the tensor map) — no read-back pass.  res_mode 2 (a residual that is
-    // not the input): the coalesced pass below adds it from global memory and stores.  Train-mode statistics are a read-only
-    // column pass over the staged tile.
-    const bool tma_out = p.res_mode != 2;
+    // Output path: the staged tile (SWIZZLE_128B image of 128 positions x 32 ch) leaves through ONE TMA tile store (positions
+    // past the row / slice are clipped by the tensor map) — no read-back pass.  res_mode 2 (a residual that is not the input:
+    // data gradients of the residual blocks): its tile is TMA-LOADED into the staging buffer while the tile's MMAs still run, in
+    // the very layout the store uses, and every thread adds its own row in place (a coalesced read-add-store pass over global
+    // memory did this before and doubled the kernel: 88 against 45 us per full-resolution data gradient).  Train-mode statistics
+    // are a read-only column pass over the staged tile.
+    constexpr bool tma_out = true;
     uint32_t ntile_g = 0;                                     // tiles this group has staged so far
     const int bar_id = 4 + egrp;
     asm volatile("bar.sync 6, 256;\n" ::: "memory");          // sPar (written by the first epilogue warp) is visible
@@ -536,6 +541,12 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           }
           group_bar(bar_id);
         }
+        uint64_t* rbar = &resfull[egrp * 2 + (ntile_g % C::NSTG)];
+        const uint32_t rpar = (ntile_g / C::NSTG) & 1;
+        if (RES2 && et == 0) {                          // residual tile -> staging buffer (zero fill past the row / slice)
+          mbar_expect_tx(rbar, STG_BYTES);
+          tma_load_4d(stg, &tmap_res, rbar, 0, x0, z, s.b);
+        }
         ++ntile_g;
         WSWAIT(t_tfull, tc::mbar_wait(&tfull[slot], accphase));
         tc_fence_after();
@@ -556,6 +567,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           __syncwarp();
           if (lane == 0) { mbar_arrive(&tempty[slot]); if (!TWO && p.res_mode == 1) mbar_arrive(&rsempty[rslot]); }
           float* row = stg + m * 32;
+          if (RES2) tc::mbar_wait(rbar, rpar);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 a4 = *reinterpret_cast<const float4*>(sPar + 4 * c);
@@ -566,6 +578,10 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
             o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
             if (!TWO && p.res_mode == 1) { o.x += res[4 * c]; o.y += res[4 * c + 1]; o.z += res[4 * c + 2]; o.w += res[4 * c + 3]; }
+            if (RES2) {
+              const float4 rr = *reinterpret_cast<const float4*>(row + ((c ^ (m & 7)) << 2));
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
             *reinterpret_cast<float4*>(row + ((c ^ (m & 7)) << 2)) = o;
           }
         }
@@ -587,10 +603,6 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((chunk ^ (r & 7)) << 2));
           if (xx < lim) {
             const size_t off = (rowbase + xx) * 32 + chunk * 4;
-            if (p.res_mode == 2) {
-              const float4 rr = __ldcg(reinterpret_cast<const float4*>(e.residual + off));
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-            }
             if (has_stats) {
               s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
               s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
@@ -723,7 +735,7 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
   p.res_mode = e->residual == nullptr ? 0 : ((e->residual == x && !d3 && !p4) ? 1 : 2);
   snb_encode_tiled_fn enc = snb_get_encode_tiled();
   SNB_REQUIRE(enc != nullptr, "snb_conv_c32_ws: cuTensorMapEncodeTiled is not available from the driver");
-  CUtensorMap tmap, tmap_out;
+  CUtensorMap tmap, tmap_out, tmap_res;
   cuuint64_t dims[4], strides[3];
   if (d3) {
     const cuuint64_t HW = (cuuint64_t)g->H * g->W;
@@ -745,17 +757,26 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv_c32_ws: cuTensorMapEncodeTiled (output) failed (%d)", (int)cr);
+  tmap_res = tmap_out;
+  if (p.res_mode == 2) {
+    SNB_REQUIRE((reinterpret_cast<uintptr_t>(e->residual) & 15) == 0, "snb_conv_c32_ws: residual must be 16-byte aligned");
+    cr = enc(&tmap_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(e->residual), dims, strides, box_out, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv_c32_ws: cuTensorMapEncodeTiled (residual) failed (%d)", (int)cr);
+  }
   int dev = 0, sms = 148;
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nstrips < sms ? p.nstrips : sms;
   static const bool fold = []() { const char* s = getenv("SNB200_WS_FOLD"); return !(s != nullptr && s[0] == '0'); }();   // SNB200_WS_FOLD=0: N = 32 MMAs (measurements)
-#define WS_GO(MODEV, FOLDV) do { \
-    SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<MODEV, FOLDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<MODEV>::SMEM_BYTES)); \
-    snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, p); } while (0)
-  if (p4) WS_GO(wsk::MODE_P4, true);
-  else if (d3) { if (fold) WS_GO(wsk::MODE_3D, true); else WS_GO(wsk::MODE_3D, false); }
-  else    { if (fold) WS_GO(wsk::MODE_2D, true); else WS_GO(wsk::MODE_2D, false); }
+#define WS_GO(MODEV, FOLDV, RESV) do { \
+    SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<MODEV>::SMEM_BYTES)); \
+    snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, tmap_res, p); } while (0)
+  const bool res2 = p.res_mode == 2;
+  if (p4) { if (res2) WS_GO(wsk::MODE_P4, true, true); else WS_GO(wsk::MODE_P4, true, false); }
+  else if (d3) { if (res2) WS_GO(wsk::MODE_3D, true, true); else if (fold) WS_GO(wsk::MODE_3D, true, false); else WS_GO(wsk::MODE_3D, false, false); }
+  else    { if (res2) WS_GO(wsk::MODE_2D, true, true); else if (fold) WS_GO(wsk::MODE_2D, true, false); else WS_GO(wsk::MODE_2D, false, false); }
 #undef WS_GO
   SNB_LAUNCH_CHECK("conv_c32_ws_kernel");
   return 0;
