@@ -254,16 +254,21 @@ class Timer:
     torch.cuda.synchronize()
     probe_ms = self._max(a.elapsed_time(b) / 5)
     steps = int(min(max_steps, max(min_steps, self.min_seconds * 1e3 / max(probe_ms, 1e-3) + 1)))
-    self.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(self.stream)
-    for _ in range(steps):
-      step()
-    if finish:
-      finish()
-    b.record(self.stream)
-    self.barrier()
-    return steps, self._max(a.elapsed_time(b))
+    for attempt in range(3):
+      self.barrier()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record(self.stream)
+      for _ in range(steps):
+        step()
+      if finish:
+        finish()
+      b.record(self.stream)
+      self.barrier()
+      ms = self._max(a.elapsed_time(b))               # the same number on every rank, so every rank takes the same decision
+      if ms >= self.min_seconds * 1e3 or steps >= max_steps:
+        break
+      steps = int(min(max_steps, steps * self.min_seconds * 1e3 / max(ms, 1e-3) * 1.03 + 1))      # the probe over-estimated a step
+    return steps, ms
 
 
 def gpu_arm(args):
