@@ -178,7 +178,10 @@ __device__ __forceinline__ void issue_window(uint32_t d1, uint32_t d2, const uin
 template <int MODE, bool FOLD, bool RES2>      // RES2: a residual that is not the layer's input (p.res_mode == 2), added from a TMA-loaded tile
 __global__ void __launch_bounds__(NTHREADS_WS, 1)
 conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
-                   const __grid_constant__ CUtensorMap tmap_res, const Params p) {
+                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_p1,
+                   const __grid_constant__ CUtensorMap tmap_p2, const __grid_constant__ CUtensorMap tmap_p3, const Params p) {
+  // tmap_p1..3 (MODE_P4 only): the polyphase images 1..3 of the input (tmap = image 0) — four sub-tensors of a split input, or
+  // four STRIDED views (element strides 2 in x and y) of the un-split input, which needs no split pass at all.
   using C = Cfg<MODE>;
   constexpr int NA = C::NA, NRES = C::NRES, NWIN = C::NWIN;
   constexpr bool D3 = C::FLAT, TWO = C::TWO;
@@ -262,7 +265,8 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             WSWAIT(w_r, tc::mbar_wait(&rempty[sa], ((ac / NR) & 1) ^ 1));
             mbar_expect_tx(&rfull[sa], bytes);
             if (D3) tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - 1 + (win - 1) * p.W, s.z0 + u - 1, s.b);
-            else if (MODE == MODE_P4) tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - 1, s.z0 + u - 1, win * p.B + s.b);
+            else if (MODE == MODE_P4) tma_load_4d(base + sa * C::RAW_BYTES, win == 0 ? &tmap : (win == 1 ? &tmap_p1 : (win == 2 ? &tmap_p2 : &tmap_p3)),
+                                                  &rfull[sa], 0, s.cb * 128 - 1, s.z0 + u - 1, s.b);
             else    tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - p.dil, s.z0 + (u - 1) * p.dil, s.b);
             ++ac;
           }
@@ -721,8 +725,10 @@ extern "C" int snb_conv_weights_ws_floats(int kd) {      // kd = 5: the ten-imag
   return kd == 5 ? 10 * (tc::B_BYTES / 4) + 4 : (kd == 3 ? 9 * (tc::B_BYTES / 4) + 4 : 3 * tc::WIMG_FLOATS_PER_WINDOW);
 }
 
+// p4: 0 = plain conv; 1 = MODE_P4 over a split input x = phases [4][B][OH][OW][32]; 2 = MODE_P4 over the un-split input
+// x [B][in_h][in_w][32] through strided tensor maps (phase (a,b) = x[2i+a][2j+b], zero fill past the odd edge).
 static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
-                     long long* dbg, void* stream, bool p4 = false) {
+                     long long* dbg, void* stream, int p4 = 0, int in_h = 0, int in_w = 0) {
   wsk::Params p;
   if (int rc = ws_setup(g, p, "snb_conv_c32_ws")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv_c32_ws: null pointer");
@@ -745,14 +751,29 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
     dims[0] = 32; dims[1] = (cuuint64_t)g->W; dims[2] = (cuuint64_t)g->H; dims[3] = (cuuint64_t)g->B;
     strides[0] = 128; strides[1] = (cuuint64_t)g->W * 128; strides[2] = (cuuint64_t)g->W * g->H * 128;
   }
-  cuuint64_t dims_in[4] = {dims[0], dims[1], dims[2], p4 ? 4 * dims[3] : dims[3]};      // P4: [phase][image] along the outer axis
   const cuuint32_t box[4] = {32, (cuuint32_t)(128 + 2 * g->dil), 1, 1};
   const cuuint32_t box_out[4] = {32, 128, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims_in, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUtensorMap tmap_ph[4];
+  CUresult cr = CUDA_SUCCESS;
+  for (int k = 0; k < (p4 ? 4 : 1) && cr == CUDA_SUCCESS; ++k) {
+    const float* base_k = x;
+    cuuint64_t dk[4] = {dims[0], dims[1], dims[2], dims[3]}, sk[3] = {strides[0], strides[1], strides[2]};
+    if (p4 == 1) {
+      base_k = x + (size_t)k * g->B * g->H * g->W * 32;
+    } else if (p4 == 2) {
+      const int a = k >> 1, b = k & 1;
+      base_k = x + ((size_t)a * in_w + b) * 32;
+      dk[1] = (cuuint64_t)((in_w - b + 1) / 2); dk[2] = (cuuint64_t)((in_h - a + 1) / 2);
+      sk[0] = 2 * 128; sk[1] = (cuuint64_t)in_w * 2 * 128; sk[2] = (cuuint64_t)in_w * in_h * 128;
+    }
+    cr = enc(&tmap_ph[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base_k), dk, sk, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv_c32_ws: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  if (!p4) tmap_ph[1] = tmap_ph[2] = tmap_ph[3] = tmap_ph[0];
+  tmap = tmap_ph[0];
   cr = enc(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box_out, estr,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -772,7 +793,7 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
   static const bool fold = []() { const char* s = getenv("SNB200_WS_FOLD"); return !(s != nullptr && s[0] == '0'); }();   // SNB200_WS_FOLD=0: N = 32 MMAs (measurements)
 #define WS_GO(MODEV, FOLDV, RESV) do { \
     SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<MODEV>::SMEM_BYTES)); \
-    snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, tmap_res, p); } while (0)
+    snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, tmap_res, tmap_ph[1], tmap_ph[2], tmap_ph[3], p); } while (0)
   const bool res2 = p.res_mode == 2;
   if (p4) { if (res2) WS_GO(wsk::MODE_P4, true, true); else WS_GO(wsk::MODE_P4, true, false); }
   else if (d3) { if (res2) WS_GO(wsk::MODE_3D, true, true); else if (fold) WS_GO(wsk::MODE_3D, true, false); else WS_GO(wsk::MODE_3D, false, false); }
@@ -801,5 +822,18 @@ extern "C" int snb_conv5x5s2_c32_ws(const float* phases, const float* wimg, floa
   g.B = B; g.D = 1; g.H = OH; g.W = OW; g.OD = 1; g.OH = OH; g.OW = OW; g.KD = 1; g.KH = 3; g.KW = 3;
   g.stride = 1; g.dil = 1; g.pd = 0; g.ph = 1; g.pw = 1; g.transposed = 0;
   SNB_REQUIRE(e && !e->residual, "snb_conv5x5s2_c32_ws: no residual input");
-  return ws_launch(phases, wimg, y, &g, e, nullptr, stream, true);
+  return ws_launch(phases, wimg, y, &g, e, nullptr, stream, 1);
+}
+
+// The same layer straight from the un-split input x [B][H][W][32] (H, W >= 2): the four polyphase images are strided TMA views of x,
+// y [B][ceil(H/2)][ceil(W/2)][32].
+extern "C" int snb_conv5x5s2_c32_ws_x(const float* x, const float* wimg, float* y, int B, int H, int W,
+                                      const snb_conv_epilogue* e, void* stream) {
+  SNB_REQUIRE(H >= 2 && W >= 2, "snb_conv5x5s2_c32_ws_x: needs H, W >= 2");
+  snb_conv_geom g;
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  g.B = B; g.D = 1; g.H = OH; g.W = OW; g.OD = 1; g.OH = OH; g.OW = OW; g.KD = 1; g.KH = 3; g.KW = 3;
+  g.stride = 1; g.dil = 1; g.pd = 0; g.ph = 1; g.pw = 1; g.transposed = 0;
+  SNB_REQUIRE(e && !e->residual, "snb_conv5x5s2_c32_ws_x: no residual input");
+  return ws_launch(x, wimg, y, &g, e, nullptr, stream, 2, H, W);
 }

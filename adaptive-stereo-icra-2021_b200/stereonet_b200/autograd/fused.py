@@ -290,6 +290,8 @@ def conv5x5s2_c32(x, conv, bias, phases=None):
     g = ops.geom(x.shape, 5, stride=2, dil=1, pad=2)
     y, _ = ops.conv_c32(x, wprep(conv), g, bias=bias)
     return y
+  if CONV_BACKEND == "ws" and phases is None and x.shape[1] >= 2 and x.shape[2] >= 2:
+    return ops.conv5x5s2_c32_ws_x(x, wprep_p4(conv), bias=bias)          # polyphase images = strided TMA views of x: no split pass
   ph = phases if phases is not None else ops.phase_split(x)
   if CONV_BACKEND == "ws":
     return ops.conv5x5s2_c32_ws(ph, wprep_p4(conv), bias=bias)

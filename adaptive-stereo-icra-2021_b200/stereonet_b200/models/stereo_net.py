@@ -102,11 +102,16 @@ class EdgeAwareRefinement(nn.Module):
 
   def forward(self, coarse_disparity, guidance_rgb):
     """coarse_disparity [B,h,w], guidance_rgb [B,3,H,W] -> [B,1,H,W]."""
+    return self.forward_with_up(coarse_disparity, guidance_rgb)[0]
+
+  def forward_with_up(self, coarse_disparity, guidance_rgb):
+    """-> (refined [B,1,H,W], up [B,H,W]): `up` is the bilinearly upsampled coarse disparity times W / w (stereo_net.py:105-111),
+    which the first kernel of the refinement computes anyway."""
     conv, bn = self.conv2d_feature[0][0], self.conv2d_feature[0][1]
     up, x = fused.refine_head(coarse_disparity.contiguous(), guidance_rgb.contiguous(), conv, bn, self.training)
     for block in self.residual_astrous_blocks:
       x = block.forward_cl(x)
-    return fused.refine_tail(x, self.conv2d_out, up).unsqueeze(1)
+    return fused.refine_tail(x, self.conv2d_out, up).unsqueeze(1), up
 
 
 class DisparityRegression(nn.Module):
@@ -158,6 +163,13 @@ class StereoNet(nn.Module):
 
     if output_cost_volume:
       outputs["cost_volume_{}/{}".format(side, coarse_scale)] = cost_out            # :197-198
+    if not torch.is_grad_enabled() and W == pred.shape[-1] * (2 ** self.k):
+      # the refinement's first kernel upsamples the coarse disparity with the factor W / w (= 2^k here) for its own input:
+      # that IS the coarse output of :201-202, so the separate upsampling launch is dropped on the inference path
+      refined, up = self.edge_aware_refinements[0].forward_with_up(pred, left_img)
+      outputs["pred_disp_{}/{}".format(side, coarse_scale)] = up.unsqueeze(1)
+      outputs["pred_disp_{}/{}".format(side, self.input_scale)] = refined
+      return outputs
     outputs["pred_disp_{}/{}".format(side, coarse_scale)] = \
         fused.upsample(pred, H, W, float(2 ** self.k)).unsqueeze(1)                # :201-202
     outputs["pred_disp_{}/{}".format(side, self.input_scale)] = \

@@ -176,6 +176,17 @@ def conv5x5s2_c32_ws(phases, wimg, bias=None, lrelu=False):
   return y
 
 
+def conv5x5s2_c32_ws_x(x, wimg, bias=None, lrelu=False):
+  """5x5 stride-2 pad-2 32->32 conv straight from the un-split input [B,H,W,32] (strided TMA views; H, W >= 2)."""
+  _req(x, "x", 4); _req(wimg, "wimg")
+  B, H, W, _ = x.shape
+  y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, 32), device=x.device, dtype=torch.float32)
+  e = ConvEpilogue(_p(bias), None, None, None, None, 1 if lrelu else 0)
+  check(_cabi.lib().snb_conv5x5s2_c32_ws_x(_p(x), _p(wimg), _p(y), B, H, W, C.byref(e), _stream(x)), "snb_conv5x5s2_c32_ws_x")
+  _count()
+  return y
+
+
 def prep_conv_weights_tc_batch(table, n):
   """One launch for n weight images; `table` is an int64 device tensor [n,4] (see snb_prep_conv_weights_tc_batch)."""
   check(_cabi.lib().snb_prep_conv_weights_tc_batch(_p(table), n, _stream(table)), "snb_prep_conv_weights_tc_batch")

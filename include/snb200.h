@@ -125,6 +125,10 @@ SNB_API int snb_conv_weights_ws_floats(int kd);      /* kd = 1, 3; 5: the image 
  * walk step feeding one accumulator ring.  wimg from snb_prep_conv5x5s2_weights_ws (or batch kind 2).  No residual input. */
 SNB_API int snb_conv5x5s2_c32_ws(const float* phases, const float* wimg, float* y, int B, int OH, int OW,
                          const snb_conv_epilogue* e, void* stream);
+/* The same layer straight from the un-split input x [B][H][W][32] (H, W >= 2): the polyphase images are four STRIDED TMA views
+ * of x (element strides 2 in x and y, zero fill past an odd edge), so no split pass exists; y [B][ceil(H/2)][ceil(W/2)][32]. */
+SNB_API int snb_conv5x5s2_c32_ws_x(const float* x, const float* wimg, float* y, int B, int H, int W,
+                           const snb_conv_epilogue* e, void* stream);
 SNB_API int snb_prep_conv5x5s2_weights_ws(const float* w, float* out, void* stream);
 /* Diagnostics: same launch plus per-CTA cycle counters [grid][16]. */
 SNB_API int snb_conv_c32_ws_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,

@@ -144,12 +144,16 @@ def test_conv_tc_dgrad_weights(fmt):
   close(uncl(dx), x.grad, 1e-5, "tc dgrad 3d")
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 20, 44), (2, 47, 157), (1, 188, 624), (2, 9, 260), (1, 2, 2), (1, 95, 313)])
+@pytest.mark.parametrize("B,H,W", [(1, 20, 44), (2, 47, 157), (1, 188, 624), (2, 9, 260), (1, 2, 2), (1, 95, 313), (1, 1, 5), (1, 3, 2)])
 def test_conv5x5s2_one_launch(B, H, W):
   """downsample[1:] (nn.Conv2d(32, 32, 5, 2, 2), stereo_net.py:64-70) as ONE launch of the walk kernel over the four polyphase
   images of its input (snb_conv5x5s2_c32_ws), odd and even sizes, against fp32 torch on the CPU."""
   x, w, b = rnd(B, 32, H, W, seed=4), rnd(32, 32, 5, 5, seed=5, scale=0.05), rnd(32, seed=6)
   ref = F.conv2d(x, w, b, stride=2, padding=2)
   ph = ops.phase_split(cl(x))
-  y = ops.conv5x5s2_c32_ws(ph, ops.prep_conv5x5s2_weights_ws(w.to(DEV)), bias=b.to(DEV))
+  wimg5 = ops.prep_conv5x5s2_weights_ws(w.to(DEV))
+  y = ops.conv5x5s2_c32_ws(ph, wimg5, bias=b.to(DEV))
   close(uncl(y), ref, 1e-5, "5x5 stride-2 one-launch")
+  if H >= 2 and W >= 2:                              # the same layer from the un-split input (strided TMA views): identical arithmetic
+    y2 = ops.conv5x5s2_c32_ws_x(cl(x), wimg5, bias=b.to(DEV))
+    assert torch.equal(y2, y)
