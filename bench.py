@@ -460,6 +460,10 @@ def gpu_arm(args):
       r2_flops = 2 * 9 * 32 * 32 * H * W
       hd_ms, _ = time_kernel(lambda: ops.conv3d_out_softargmin(x3, snet.conv3d_alone.weight, snet.conv3d_alone.bias, True, True), 20, flush, stream)
       hd_bytes = 4 * hc * wc * (32 * D + 1 + D + 1)
+      tp_ms, _ = time_kernel(lambda: ops.conv_c32_taps(x3, snet.conv3d_alone.weight, 27), 20, flush, stream)
+      taps27 = ops.conv_c32_taps(x3, snet.conv3d_alone.weight, 27)
+      ts_ms, _ = time_kernel(lambda: ops.tapsum_softargmin(taps27, snet.conv3d_alone.bias, True), 20, flush, stream)
+      tp_bytes, ts_bytes = 4 * hc * wc * D * (32 + 27), 4 * hc * wc * (27 * D + D + 1)
       img2 = torch.rand(2, 3, H, W, device=dev)
       c0 = fnet.downsample[0]
       fc_ms, _ = time_kernel(lambda: ops.conv5x5s2_c3(img2, c0.weight, c0.bias), 20, flush, stream)
@@ -483,7 +487,9 @@ def gpu_arm(args):
       "cost_volume_batch8": hbm(cv8_ms, 8 * cv_bytes),
       "filter_conv3d_32x32": tens(f3_ms, f3_flops),
       "refine_conv2d_32x32_dil4": tens(r2_ms, r2_flops),
-      "head_conv3d_alone_softargmin_fcs": dict(hbm(hd_ms, hd_bytes), note="ONE kernel: conv3d_alone + softmax + expectation + cost + FCS"),
+      "head_taps27_tensor_core": dict(hbm(tp_ms, tp_bytes), note="inference head, kernel 1 of 2: conv3d_alone as a 32 -> 27-tap contraction on the tensor cores"),
+      "head_tapsum_softargmin": dict(hbm(ts_ms, ts_bytes), note="inference head, kernel 2 of 2: 27-tap gather + softmax + expectation + cost volume"),
+      "head_fused_one_kernel": dict(hbm(hd_ms, hd_bytes), note="training path: conv3d_alone + softmax + expectation + cost + FCS in ONE CUDA-core kernel"),
       "first_conv5x5s2_2images": tens(fc_ms, fc_flops),
       "refine_in_conv": hbm(ri_ms, ri_bytes),
     }
