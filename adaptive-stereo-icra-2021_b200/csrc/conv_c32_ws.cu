@@ -29,7 +29,7 @@
 //                beta = scale bias + shift) -> LeakyReLU -> + residual -> swizzled 16 KB tile in smem -> ONE TMA tile store.
 //   residual     BasicBlock's `x + ...` (stereo_net.py:50) adds the layer's own input: the converter of the tile's centre row
 //                holds x[m] in registers and parks it in TMEM next to the accumulator (2-D).  A residual that is not the input
-//                (data gradients, polyphase chains) is added from global memory in a coalesced pass instead of the TMA store.
+//                (data gradients of the residual blocks) is TMA-loaded into the staging buffer and added in place (RES2).
 // What bounds it now: shared-memory wavefronts (B-operand fetch + TMA write + converter reads + epilogue staging ~ 1300 per
 // 2-D tile) about level with the tensor pipe (~950 cycles per 2-D tile).
 // Warps: 0 producer, 1 MMA issuer (+ resident weights), 2-9 converters (two groups of four, alternating windows),
@@ -790,14 +790,13 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
   SNB_CUDA(cudaGetDevice(&dev));
   SNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.nstrips < sms ? p.nstrips : sms;
-  static const bool fold = []() { const char* s = getenv("SNB200_WS_FOLD"); return !(s != nullptr && s[0] == '0'); }();   // SNB200_WS_FOLD=0: N = 32 MMAs (measurements)
 #define WS_GO(MODEV, FOLDV, RESV) do { \
     SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<MODEV>::SMEM_BYTES)); \
     snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, tmap_res, tmap_ph[1], tmap_ph[2], tmap_ph[3], p); } while (0)
   const bool res2 = p.res_mode == 2;
   if (p4) { if (res2) WS_GO(wsk::MODE_P4, true, true); else WS_GO(wsk::MODE_P4, true, false); }
-  else if (d3) { if (res2) WS_GO(wsk::MODE_3D, true, true); else if (fold) WS_GO(wsk::MODE_3D, true, false); else WS_GO(wsk::MODE_3D, false, false); }
-  else    { if (res2) WS_GO(wsk::MODE_2D, true, true); else if (fold) WS_GO(wsk::MODE_2D, true, false); else WS_GO(wsk::MODE_2D, false, false); }
+  else if (d3) { if (res2) WS_GO(wsk::MODE_3D, true, true); else WS_GO(wsk::MODE_3D, true, false); }
+  else    { if (res2) WS_GO(wsk::MODE_2D, true, true); else WS_GO(wsk::MODE_2D, true, false); }
 #undef WS_GO
   SNB_LAUNCH_CHECK("conv_c32_ws_kernel");
   return 0;
