@@ -393,3 +393,57 @@ def test_adapt_step_fused_loss_matches_oracle_loss():
   ua, ub = torch.cat(ua).double(), torch.cat(ub).double()
   cos = float(ua @ ub / (ua.norm() * ub.norm() + 1e-30))
   assert cos > 0.97, cos
+
+
+@pytest.mark.parametrize("replay", [False, True])
+def test_adapt_step_streams_match_single_stream(replay):
+  """AdaptStepper(two_streams=True) — right-image feature pass on a second stream with deferred BatchNorm running-statistics
+  updates, weight gradients on their own stream through the WgradToken nodes — leaves the weights, BN buffers and losses the
+  single-stream step leaves (same kernels, same arithmetic; only the order of independent work changes)."""
+  from stereonet_b200.adapt import AdaptStepper, make_optimizer
+  k, Hh, Ww = 3, 96, 256
+  fsd, ssd = O.make_feature_state(k, 11), O.make_stereo_state(22, sharpen=10.0)
+  frames = [O.make_stereo_pair(1, Hh, Ww, seed=1000 + i, max_disp_px=40.0) for i in range(3)]
+  res = []
+  for two in (False, True):
+    f = S.FeatureExtractorNetwork(k).to(DEV); s = S.StereoNet(k, 1, 0).to(DEV)
+    f.load_state_dict(fsd); s.load_state_dict(ssd)
+    st = AdaptStepper(f, s, make_optimizer(f, s, lr=5e-5, fused=True), Hh, Ww, two_streams=two)
+    losses = []
+    for i in range(2):
+      l, r, _ = frames[i]
+      rep = tuple(t.to(DEV) for t in frames[2]) if replay else None
+      losses.append(st.step(l.to(DEV), r.to(DEV), replay=rep)[0].item())
+    torch.cuda.synchronize()
+    res.append((losses, {n: v.detach().cpu().clone() for n, v in list(s.state_dict().items()) + list(f.state_dict().items())}))
+  (la, wa), (lb, wb) = res
+  assert la == lb, (la, lb)
+  for n in wa:
+    if "num_batches_tracked" in n:
+      assert torch.equal(wa[n], wb[n]), n
+    elif "running_var" in n or "running_mean" in n:
+      # the deferred update rebuilds the batch variance from invstd (1 / invstd^2 - eps): a few ulps of the statistic
+      assert (wa[n] - wb[n]).abs().max().item() <= 2e-6 * wa[n].abs().max().item() + 1e-9, n
+    else:
+      assert torch.equal(wa[n], wb[n]), n
+
+
+def test_bn_running_update_matches_in_kernel_update():
+  """snb_bn_running_update (the deferred half of bn_finalize) against bn_finalize's own in-kernel update of the running buffers."""
+  from stereonet_b200 import ops
+  torch.manual_seed(0)
+  stats = torch.rand(300, 2, 32, device=DEV) * 5.0
+  stats[:, 1] += stats[:, 0] ** 2 * 3.0                       # sum z^2 >= (sum z)^2 / n with room to spare
+  count = 300 * 128
+  a, b = torch.nn.BatchNorm2d(32).to(DEV), torch.nn.BatchNorm2d(32).to(DEV)
+  for bn in (a, b):
+    with torch.no_grad():
+      bn.running_mean.uniform_(-1, 1); bn.running_var.uniform_(0.5, 2.0)
+  b.load_state_dict(a.state_dict())
+  ops.bn_finalize(stats, count, a)                            # in-kernel update
+  _, _, mean, invstd = ops.bn_finalize(stats, count, b, update_running=False)
+  ops.bn_running_update(b, mean, invstd, count)
+  torch.cuda.synchronize()
+  assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
+  assert (a.running_mean - b.running_mean).abs().max().item() <= 1e-6 * a.running_mean.abs().max().item()
+  assert (a.running_var - b.running_var).abs().max().item() <= 2e-6 * a.running_var.abs().max().item()
