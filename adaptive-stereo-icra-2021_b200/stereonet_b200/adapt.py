@@ -36,7 +36,7 @@ class AdaptStepper:
     # frame instead of a second full pass (adapt.py:339-349).  Off by default: train-mode BatchNorm then normalises with the
     # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
     self.batched_replay = batched_replay
-    self.two_streams, self._side, self._wstream = two_streams, None, None
+    self.two_streams, self._side, self._wstream, self._acc_stream, self._acc_nodes = two_streams, None, None, None, None
     self._graphs = {}
     self._wprep = None                      # fused.WeightPrepBatch: all derived weight images in one launch per step
     self.launches_per_step = None
@@ -109,6 +109,14 @@ class AdaptStepper:
     if self.two_streams and left.is_cuda:
       if self._wstream is None:
         self._wstream = torch.cuda.Stream(device=left.device)
+        # Gradient accumulation gets a stream of its own.  autograd runs a parameter's AccumulateGrad node on the stream that was
+        # current when the node was created and makes THAT stream wait for the producer of every incoming gradient: with the
+        # nodes on the main stream, each weight gradient finishing on the side streams would stall the main chain.  The nodes
+        # are created here, under the accumulation stream, and kept alive (autograd holds them weakly).
+        self._acc_stream = torch.cuda.Stream(device=left.device)
+        with torch.cuda.stream(self._acc_stream):
+          self._acc_nodes = [p.view_as(p).grad_fn.next_functions[0][0]
+                             for net in (self.stereo_net, self.feature_net) for p in net.parameters() if p.requires_grad]
       fused.WGRAD_STREAM = self._wstream                                            # weight gradients next to the data path
       fused.wgrad_token((1,), left.device)                                          # (creates the token buffer outside any capture)
     try:
