@@ -54,15 +54,19 @@ constexpr int STG_BYTES = 128 * 128;                     // one output tile, fp3
 // input (x[2i+a][2j+b] -> phase a*2+b, output-sized): out = sum over phases of a 3x3 'same' conv with the sub-kernel
 // w[2kz+a][2kw+b] — the four phase rows of one walk step are four raw windows feeding ONE accumulator ring, so the whole layer is
 // one launch instead of four chained ones that re-read and re-write the output (round 2, first half: 80 us per KITTI layer).
-constexpr int MODE_2D = 0, MODE_3D = 1, MODE_P4 = 2;
+// MODE 3: 3x3 conv of a FOUR-channel channels-last image (the refinement's input layer: [disparity, r, g, b] -> 32,
+// stereo_net.py:105-117).  A raw row is 16 B per pixel, so the three kw taps of a pixel are 48 contiguous bytes: they go into ONE
+// K = 16 slice (k = kw*4 + ch, 12 used), and a walk step costs 3 MMAs instead of 18 — the layer becomes a store-bound kernel.
+constexpr int MODE_2D = 0, MODE_3D = 1, MODE_P4 = 2, MODE_C4 = 3;
 template <int MODE> struct Cfg {
-  static constexpr bool TWO = MODE != MODE_2D;           // two accumulator rings D1 / D2 and [wh | wl''] images
+  static constexpr bool TWO = MODE == MODE_3D || MODE == MODE_P4;      // two accumulator rings D1 / D2 and [wh | wl''] images
   static constexpr bool FLAT = MODE == MODE_3D;          // positions = un-padded flat index of a (b,d) slice, walk along d
-  static constexpr bool ONCE = MODE != MODE_2D;          // converters: split every raw row ONCE, in place, then read it three times
+  static constexpr bool ONCE = TWO;                      // converters: split every raw row ONCE, in place, then read it three times
   static constexpr int NWIN = MODE == MODE_3D ? 3 : (MODE == MODE_P4 ? 4 : 1);     // raw windows per walk step (3-D: kh; P4: phase)
-  static constexpr int NIMG = MODE == MODE_3D ? 9 : (MODE == MODE_P4 ? 10 : 3);    // resident weight images
+  static constexpr int NIMG = MODE == MODE_3D ? 9 : (MODE == MODE_P4 ? 10 : (MODE == MODE_C4 ? 1 : 3));    // resident weight images
+  static constexpr int NKS = MODE == MODE_C4 ? 1 : 2;    // K = 16 slices per (window, kw)
   static constexpr int IMG_BYTES = TWO ? B_BYTES : 2 * B_BYTES;     // TWO: [wh | wl''] 12 KB; 2-D: P [wh | wl] + Q [2^-11 wh | -] 24 KB
-  static constexpr int RAW_BYTES = TWO ? 17 * 1024 : 20 * 1024;     // 130 / up to 160 position rows of 128 B
+  static constexpr int RAW_BYTES = MODE == MODE_C4 ? 3 * 1024 : (TWO ? 17 * 1024 : 20 * 1024);     // 130 / up to 160 position rows of 128 B (C4: 16 B)
   static constexpr int NSTG = TWO ? 1 : 2;               // staging tiles per epilogue group
   static constexpr int NA = TWO ? 2 : 3;                 // A slots of 96 columns = 3 kw x (xh 16 | xl' 16)
   static constexpr int NRES = 3;                         // 2-D: residual slots of 32 columns
@@ -70,7 +74,7 @@ template <int MODE> struct Cfg {
   static constexpr int SMEM_BYTES = NR * RAW_BYTES + 2 * NSTG * STG_BYTES + NIMG * IMG_BYTES + 4096 + 1024;
   // first weight image of a window and its number of kw taps (P4: odd-column phases have taps kw' = 0, 1 only: x5 = 2 kw' + 1 < 5)
   __host__ __device__ static constexpr int img_base(int win) { return MODE == MODE_P4 ? (win == 0 ? 0 : win == 1 ? 3 : win == 2 ? 5 : 8) : win * 3; }
-  __host__ __device__ static constexpr int nkw(int win) { return (MODE == MODE_P4 && (win & 1)) ? 2 : 3; }
+  __host__ __device__ static constexpr int nkw(int win) { return MODE == MODE_C4 ? 1 : ((MODE == MODE_P4 && (win & 1)) ? 2 : 3); }
   static_assert(A_BASE + NA * 96 <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
@@ -156,7 +160,7 @@ __device__ __forceinline__ void issue_window(uint32_t d1, uint32_t d2, const uin
 #pragma unroll
   for (int kw = 0; kw < NKW; ++kw) {
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
+    for (int ks = 0; ks < C::NKS; ++ks) {
       const uint32_t a = ta + kw * 32 + ks * 8;
       constexpr int Q_OFF = D3 ? 0 : B_BYTES;                 // second product's B: 3-D wh again, 2-D the 2^-11 wh image
       const uint64_t o1 = (uint64_t)((kw * C::IMG_BYTES + ks * 32) >> 4);
@@ -254,7 +258,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (lane == 0) {
       uint32_t ac = 0;
       long long w_r = 0; const long long t0 = clock64();
-      const uint32_t bytes = (uint32_t)RW * 128u;
+      const uint32_t bytes = (uint32_t)RW * (MODE == MODE_C4 ? 16u : 128u);
       WS_FOR_STRIPS(sid) {
         const Strip s = decode_strip<D3>(p, sid);
         if (s.ntiles == 0) continue;
@@ -267,7 +271,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             if (D3) tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - 1 + (win - 1) * p.W, s.z0 + u - 1, s.b);
             else if (MODE == MODE_P4) tma_load_4d(base + sa * C::RAW_BYTES, win == 0 ? &tmap : (win == 1 ? &tmap_p1 : (win == 2 ? &tmap_p2 : &tmap_p3)),
                                                   &rfull[sa], 0, s.cb * 128 - 1, s.z0 + u - 1, s.b);
-            else    tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - p.dil, s.z0 + (u - 1) * p.dil, s.b);
+            else    tma_load_4d(base + sa * C::RAW_BYTES, &tmap, &rfull[sa], 0, s.cb * 128 - p.dil, s.z0 + (u - 1) * p.dil, s.b);   // (C4: dil = 1, 16-B rows)
             ++ac;
           }
         }
@@ -343,9 +347,14 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (go_i[1]) mma_f16_i(d2 + go_d[1], ta + 16, make_desc(img0 + go_b[1]), go_i[1], 1);
                 mma_f16_i(d2 + new_d, ta + 16, make_desc(img0 + 2 * 4096), idesc_n(1), 0);      // D2 = xl' . wh
               }
-              if (ng == 1) issue_window<MODE, 1, true, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
-              else if (ng == 2) issue_window<MODE, 2, true, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
-              else issue_window<MODE, 3, true, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
+              constexpr int NKW0 = C::nkw(0);                   // (window 0 has three kw taps; C4: one)
+              if (ng == 1) issue_window<MODE, 1, true, NKW0>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else if (ng == 2) issue_window<MODE, 2, true, NKW0>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else issue_window<MODE, 3, true, NKW0>(d1, d2, g_d, ta, img0, g_b, g_i);
+            } else if (MODE == MODE_C4) {
+              if (ng == 1) issue_window<MODE, 1, false, 1>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else if (ng == 2) issue_window<MODE, 2, false, 1>(d1, d2, g_d, ta, img0, g_b, g_i);
+              else issue_window<MODE, 3, false, 1>(d1, d2, g_d, ta, img0, g_b, g_i);
             } else if (nkw == 3) {
               if (ng == 1) issue_window<MODE, 1, false, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
               else if (ng == 2) issue_window<MODE, 2, false, 3>(d1, d2, g_d, ta, img0, g_b, g_i);
@@ -394,7 +403,32 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           const int nkw = C::nkw(win);
           const long long tcount = tile_base + (u - 1);
           bool a_free = false;
-          if (C::ONCE) {
+          if (MODE == MODE_C4) {
+            // four-channel rows: pixels m, m+1, m+2 are 48 contiguous bytes = the 12 used K values (k = kw*4 + ch) of ONE K = 16 slice
+            const unsigned char* rp = rawp + m * 16;
+            const float4 q0 = *reinterpret_cast<const float4*>(rp), q1 = *reinterpret_cast<const float4*>(rp + 16),
+                         q2 = *reinterpret_cast<const float4*>(rp + 32);
+            const float xv[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            uint32_t hl[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hl[i] = 0u;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const uint32_t h = pack_f16x2(xv[2 * j], xv[2 * j + 1]);
+              const float2 f = unpack_f16x2(h);
+              hl[j] = h;
+              hl[16 + j] = pack_f16x2((xv[2 * j] - f.x) * 2048.f, (xv[2 * j + 1] - f.y) * 2048.f);
+            }
+            {
+              const uint32_t dep = hl[0] ^ hl[2] ^ hl[4];                  // one word of each of the three loads
+              __syncwarp();
+              if (lane == 0) mbar_arrive_after(&rempty[sr], dep);
+            }
+            WSWAIT(w_ae, tc::mbar_wait(&aempty[aslot], ((cnt / NA) & 1) ^ 1));
+            tc_fence_after();
+            tmem_st32(ta, hl);
+            a_free = true;
+          } else if (C::ONCE) {
             // 3-D: nine (kh,kw) operand copies per walk step made the converters — not the tensor pipe — the bound of this kernel
             // (all converters idled: 59 -> 35 us per KITTI layer; the MMA warp waited for operands a third of the time).  So every
             // raw row is split once, IN PLACE (the 128-B fp32 row becomes the 128-B [xh | xl'] row, same swizzle), and the three
@@ -728,7 +762,7 @@ extern "C" int snb_conv_weights_ws_floats(int kd) {      // kd = 5: the ten-imag
 // p4: 0 = plain conv; 1 = MODE_P4 over a split input x = phases [4][B][OH][OW][32]; 2 = MODE_P4 over the un-split input
 // x [B][in_h][in_w][32] through strided tensor maps (phase (a,b) = x[2i+a][2j+b], zero fill past the odd edge).
 static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv_geom* g, const snb_conv_epilogue* e,
-                     long long* dbg, void* stream, int p4 = 0, int in_h = 0, int in_w = 0) {
+                     long long* dbg, void* stream, int p4 = 0, int in_h = 0, int in_w = 0, bool c4 = false) {
   wsk::Params p;
   if (int rc = ws_setup(g, p, "snb_conv_c32_ws")) return rc;
   SNB_REQUIRE(x && wimg && y && e, "snb_conv_c32_ws: null pointer");
@@ -737,6 +771,7 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
   SNB_REQUIRE(!e->stats || (!e->scale && !e->lrelu && !e->residual), "snb_conv_c32_ws: statistics are taken of the plain conv + bias output");
   const bool d3 = g->KD == 3;
   SNB_REQUIRE(!p4 || (!d3 && g->dil == 1), "snb_conv5x5s2_c32_ws: bad geometry");
+  SNB_REQUIRE(!c4 || (!d3 && !p4 && g->dil == 1 && !e->residual), "snb_conv_c4_ws: bad geometry");
   p.wimg = wimg; p.y = y; p.e = *e; p.dbg = dbg;
   p.res_mode = e->residual == nullptr ? 0 : ((e->residual == x && !d3 && !p4) ? 1 : 2);
   snb_encode_tiled_fn enc = snb_get_encode_tiled();
@@ -767,8 +802,14 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
       dk[1] = (cuuint64_t)((in_w - b + 1) / 2); dk[2] = (cuuint64_t)((in_h - a + 1) / 2);
       sk[0] = 2 * 128; sk[1] = (cuuint64_t)in_w * 2 * 128; sk[2] = (cuuint64_t)in_w * in_h * 128;
     }
-    cr = enc(&tmap_ph[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base_k), dk, sk, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    cuuint32_t box_k[4] = {box[0], box[1], box[2], box[3]};
+    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+    if (c4) {                       // [B][H][W][4] fp32: a position row is 16 B, rows contiguous in smem, no swizzle
+      dk[0] = 4; sk[0] = 16; sk[1] = (cuuint64_t)g->W * 16; sk[2] = (cuuint64_t)g->W * g->H * 16;
+      box_k[0] = 4; swz = CU_TENSOR_MAP_SWIZZLE_NONE;
+    }
+    cr = enc(&tmap_ph[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base_k), dk, sk, box_k, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   SNB_REQUIRE(cr == CUDA_SUCCESS, "snb_conv_c32_ws: cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -794,7 +835,8 @@ static int ws_launch(const float* x, const float* wimg, float* y, const snb_conv
     SNB_CUDA(cudaFuncSetAttribute(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsk::Cfg<MODEV>::SMEM_BYTES)); \
     snb_launch(wsk::conv_c32_ws_kernel<MODEV, FOLDV, RESV>, grid, wsk::NTHREADS_WS, wsk::Cfg<MODEV>::SMEM_BYTES, stream, tmap, tmap_out, tmap_res, tmap_ph[1], tmap_ph[2], tmap_ph[3], p); } while (0)
   const bool res2 = p.res_mode == 2;
-  if (p4) { if (res2) WS_GO(wsk::MODE_P4, true, true); else WS_GO(wsk::MODE_P4, true, false); }
+  if (c4) WS_GO(wsk::MODE_C4, true, false);
+  else if (p4) { if (res2) WS_GO(wsk::MODE_P4, true, true); else WS_GO(wsk::MODE_P4, true, false); }
   else if (d3) { if (res2) WS_GO(wsk::MODE_3D, true, true); else WS_GO(wsk::MODE_3D, true, false); }
   else    { if (res2) WS_GO(wsk::MODE_2D, true, true); else WS_GO(wsk::MODE_2D, true, false); }
 #undef WS_GO
@@ -835,4 +877,17 @@ extern "C" int snb_conv5x5s2_c32_ws_x(const float* x, const float* wimg, float* 
   g.stride = 1; g.dil = 1; g.pd = 0; g.ph = 1; g.pw = 1; g.transposed = 0;
   SNB_REQUIRE(e && !e->residual, "snb_conv5x5s2_c32_ws_x: no residual input");
   return ws_launch(x, wimg, y, &g, e, nullptr, stream, 2, H, W);
+}
+
+// 3x3 'same' conv of a four-channel channels-last image x4 [B][H][W][4] -> y [B][H][W][32] (the refinement's input layer, the
+// image packed by snb_refine_pack_input).  wimg: snb_prep_conv_weights_tc(kd = 1, SNB_CONV_WS) of the [32][32][3][3] tensor
+// W'[co][kw*4 + ch][kh][0] = w[co][ch][kh][kw] (zero elsewhere); only its first image is read.  Epilogue as snb_conv_c32_ws
+// (bias, folded BN, LeakyReLU, train-mode statistics); no residual.
+extern "C" int snb_conv_c4_ws(const float* x4, const float* wimg, float* y, int B, int H, int W,
+                              const snb_conv_epilogue* e, void* stream) {
+  snb_conv_geom g;
+  g.B = B; g.D = 1; g.H = H; g.W = W; g.OD = 1; g.OH = H; g.OW = W; g.KD = 1; g.KH = 3; g.KW = 3;
+  g.stride = 1; g.dil = 1; g.pd = 0; g.ph = 1; g.pw = 1; g.transposed = 0;
+  SNB_REQUIRE(e != nullptr, "snb_conv_c4_ws: null epilogue");
+  return ws_launch(x4, wimg, y, &g, e, nullptr, stream, 0, 0, 0, true);
 }

@@ -293,6 +293,22 @@ upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, 
   out[((size_t)b * H + y) * W + x] = mul * v;
 }
 
+// Input image of the refinement's first layer, packed for snb_conv_c4_ws: x4[b][y][x] = (mul * bilinear(coarse), r, g, b)
+// (stereo_net.py:105-113: upsample, scale by W / w, concat with the guidance image), plus the upsampled plane itself.
+__global__ void __launch_bounds__(256)
+refine_pack_input_kernel(const float* __restrict__ coarse, const float* __restrict__ rgb, float4* __restrict__ x4,
+                         float* __restrict__ up, int h, int w, int H, int W, float mul) {
+  pdl_launch(); pdl_wait();
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const float v = mul * bilinear_sample(coarse + (size_t)b * h * w, h, w, y, x, (float)h / (float)H, (float)w / (float)W);
+  const size_t plane = (size_t)H * W, o = (size_t)y * W + x;
+  const float* img = rgb + (size_t)b * 3 * plane;
+  x4[(size_t)b * plane + o] = make_float4(v, __ldg(img + o), __ldg(img + plane + o), __ldg(img + 2 * plane + o));
+  up[(size_t)b * plane + o] = v;
+}
+
 // Deterministic gather form of the adjoint: each coarse pixel visits the fine pixels whose 2x2 footprint contains it.
 __global__ void __launch_bounds__(128)
 upsample_bilinear_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int h, int w, int H, int W, float mul) {
@@ -409,6 +425,16 @@ extern "C" int snb_upsample_bilinear(const float* in, float* out, int B, int h, 
   SNB_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "snb_upsample_bilinear: bad args");
   snb_launch(upsample_bilinear_kernel, dim3(snb_ceil_div(W, 256), H, B), 256, 0, stream, in, out, h, w, H, W, mul);
   SNB_LAUNCH_CHECK("upsample_bilinear_kernel");
+  return 0;
+}
+
+extern "C" int snb_refine_pack_input(const float* coarse, const float* rgb, float* x4, float* up, int B, int h, int w, int H, int W,
+                                     float mul, void* stream) {
+  SNB_REQUIRE(coarse && rgb && x4 && up && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "snb_refine_pack_input: bad args");
+  SNB_REQUIRE((reinterpret_cast<uintptr_t>(x4) & 15) == 0, "snb_refine_pack_input: x4 must be 16-byte aligned");
+  snb_launch(refine_pack_input_kernel, dim3(snb_ceil_div(W, 256), H, B), 256, 0, stream, coarse, rgb, reinterpret_cast<float4*>(x4), up,
+             h, w, H, W, mul);
+  SNB_LAUNCH_CHECK("refine_pack_input_kernel");
   return 0;
 }
 

@@ -83,6 +83,8 @@ SIGNATURES = {
   "snb_adam_clip_workspace_bytes": (_I, []),
   "snb_conv5x5s2_c32_ws": (_I, [_P, _P, _P, _I, _I, _I, _EP, _P]),
   "snb_conv5x5s2_c32_ws_x": (_I, [_P, _P, _P, _I, _I, _I, _EP, _P]),
+  "snb_refine_pack_input": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+  "snb_conv_c4_ws": (_I, [_P, _P, _P, _I, _I, _I, _EP, _P]),
   "snb_bn_running_update": (_I, [_P, _P, _LL, _P, _P, _P, _F, _F, _P]),
   "snb_prep_conv5x5s2_weights_ws": (_I, [_P, _P, _P]),
 }

@@ -301,6 +301,38 @@ def refine_in_conv(coarse, rgb, w, bias, scale=None, shift=None, lrelu=False, wa
   return up, z, stats
 
 
+def refine_in_weights_ws(w):
+  """[32,4,3,3] weight of the refinement's input conv -> the walk kernel's image: the [32,32,3,3] tensor
+  W'[co, kw*4 + ch, kh, 0] = w[co, ch, kh, kw] in the "ws" format (layout ops + snb_prep_conv_weights_tc)."""
+  _req(w, "weight", 4)
+  if tuple(w.shape) != (32, 4, 3, 3):
+    raise RuntimeError(f"stereonet_b200: expected a [32,4,3,3] weight, got {tuple(w.shape)}")
+  wp = torch.zeros((32, 32, 3, 3), device=w.device, dtype=torch.float32)
+  wp[:, :12, :, 0] = w.detach().permute(0, 3, 1, 2).reshape(32, 12, 3)          # [co, kw, ch, kh] -> [co, kw*4+ch, kh]
+  return prep_conv_weights_tc(wp, 0, fmt="ws")
+
+
+def refine_in_conv_ws(coarse, rgb, wimg, bias, scale=None, shift=None, lrelu=False, want_stats=False):
+  """Fused upsample + scale + concat, then Conv2d(4->32) on the walk kernel.  Returns (up [B,H,W], z [B,H,W,32], stats)."""
+  _req(coarse, "coarse_disparity", 3); _req(rgb, "guidance_rgb", 4); _req(wimg, "wimg")
+  B, h, w_ = coarse.shape
+  H, W = rgb.shape[-2:]
+  lib = _cabi.lib()
+  up = torch.empty((B, H, W), device=rgb.device, dtype=torch.float32)
+  x4 = torch.empty((B, H, W, 4), device=rgb.device, dtype=torch.float32)
+  check(lib.snb_refine_pack_input(_p(coarse), _p(rgb), _p(x4), _p(up), B, h, w_, H, W, float(W) / float(w_), _stream(rgb)),
+        "snb_refine_pack_input")
+  z = torch.empty((B, H, W, 32), device=rgb.device, dtype=torch.float32)
+  stats = None
+  if want_stats:
+    g = geom((B, H, W, 32), 3)
+    stats = torch.empty((lib.snb_conv_c32_ws_num_tiles(C.byref(g)), 2, 32), device=rgb.device, dtype=torch.float32)
+  e = ConvEpilogue(_p(bias), _p(scale), _p(shift), None, _p(stats), 1 if lrelu else 0)
+  check(lib.snb_conv_c4_ws(_p(x4), _p(wimg), _p(z), B, H, W, C.byref(e), _stream(rgb)), "snb_conv_c4_ws")
+  _count(2)
+  return up, z, stats
+
+
 def conv_c32_taps(x, w, ntaps):
   """Channel contraction of a 32->1 conv: x [B,(D),H,W,32] -> taps [B,(D),ntaps,H,W]."""
   _req(x, "x")

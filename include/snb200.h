@@ -130,6 +130,14 @@ SNB_API int snb_conv5x5s2_c32_ws(const float* phases, const float* wimg, float* 
 SNB_API int snb_conv5x5s2_c32_ws_x(const float* x, const float* wimg, float* y, int B, int H, int W,
                            const snb_conv_epilogue* e, void* stream);
 SNB_API int snb_prep_conv5x5s2_weights_ws(const float* w, float* out, void* stream);
+/* The refinement's input layer (upsample + scale + concat + Conv2d(4 -> 32) [+ BN + LeakyReLU], stereo_net.py:105-117) on the walk
+ * kernel: snb_refine_pack_input writes x4 [B][H][W][4] = (mul * bilinear(coarse), r, g, b) and the upsampled plane up [B][H][W];
+ * snb_conv_c4_ws convolves it — the three kw taps of a pixel are 48 contiguous bytes = ONE K = 16 slice, 3 MMAs per walk step.
+ * wimg: snb_prep_conv_weights_tc(kd = 1, mode = SNB_CONV_WS) of W'[co][kw*4 + ch][kh][0] = w[co][ch][kh][kw] (a [32][32][3][3]
+ * tensor, zero elsewhere).  Epilogue as snb_conv_c32_ws (stats rows: snb_conv_c32_ws_num_tiles of the 3x3 geometry); no residual. */
+SNB_API int snb_refine_pack_input(const float* coarse, const float* rgb, float* x4, float* up, int B, int h, int w, int H, int W,
+                          float mul, void* stream);
+SNB_API int snb_conv_c4_ws(const float* x4, const float* wimg, float* y, int B, int H, int W, const snb_conv_epilogue* e, void* stream);
 /* Diagnostics: same launch plus per-CTA cycle counters [grid][16]. */
 SNB_API int snb_conv_c32_ws_profile(const float* x, const float* wimg, float* y, const snb_conv_geom* g,
                             const snb_conv_epilogue* e, long long* counters, void* stream);

@@ -129,6 +129,26 @@ def test_refine_in_conv(B, h, w, H, W):
   close(uncl(y), F.leaky_relu(z_ref * scale.view(1, 32, 1, 1) + shift.view(1, 32, 1, 1), 0.2), 3e-6, "refine_in eval")
 
 
+@pytest.mark.parametrize("B,h,w,H,W", [(1, 5, 9, 40, 72), (2, 4, 17, 27, 130), (1, 12, 40, 96, 320), (1, 1, 1, 3, 5), (1, 3, 33, 20, 259)])
+def test_refine_in_conv_ws(B, h, w, H, W):
+  """The same layer on the walk kernel (snb_refine_pack_input + snb_conv_c4_ws: four-channel rows, one K = 16 slice per row)."""
+  coarse = torch.rand(B, h, w, generator=torch.Generator().manual_seed(1)) * 20
+  rgb = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(2))
+  wt, b = rnd(32, 4, 3, 3, seed=3, scale=0.2), rnd(32, seed=4)
+  up_ref = F.interpolate(coarse.unsqueeze(1), size=(H, W), mode="bilinear", align_corners=False) * (W / w)
+  z_ref = F.conv2d(torch.cat([up_ref, rgb], 1), wt, b, padding=1)
+  wimg = ops.refine_in_weights_ws(wt.to(DEV))
+  up, z, stats = ops.refine_in_conv_ws(coarse.to(DEV), rgb.to(DEV), wimg, b.to(DEV), want_stats=True)
+  close(up.cpu(), up_ref.squeeze(1), 2e-6, "upsampled disparity")
+  close(uncl(z), z_ref, 1e-5, "refine_in conv (ws)")
+  s = stats.double().sum(0).cpu()
+  close(s[0], z_ref.double().sum((0, 2, 3)), 1e-5, "sum")
+  close(s[1], (z_ref.double() ** 2).sum((0, 2, 3)), 1e-5, "sumsq")
+  scale, shift = rnd(32, seed=5).abs() + 0.5, rnd(32, seed=6)
+  _, y, _ = ops.refine_in_conv_ws(coarse.to(DEV), rgb.to(DEV), wimg, b.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV), lrelu=True)
+  close(uncl(y), F.leaky_relu(z_ref * scale.view(1, 32, 1, 1) + shift.view(1, 32, 1, 1), 0.2), 1e-5, "refine_in eval (ws)")
+
+
 @pytest.mark.parametrize("B,D,H,W,sharp", [(1, 24, 9, 20, 1.0), (2, 12, 7, 33, 30.0), (1, 6, 5, 70, 30.0), (1, 24, 47, 156, 10.0)])
 def test_conv3d_out_softargmin(B, D, H, W, sharp):
   x, w, b = rnd(B, 32, D, H, W, seed=1), rnd(1, 32, 3, 3, 3, seed=2, scale=0.05 * sharp), rnd(1, seed=3)
