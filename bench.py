@@ -471,7 +471,9 @@ def gpu_arm(args):
       ref = snet.edge_aware_refinements[0]
       cz = torch.rand(1, hc, wc, device=dev) * 20
       rconv = ref.conv2d_feature[0][0]
-      ri_ms, _ = time_kernel(lambda: ops.refine_in_conv(cz, img2[:1], rconv.weight, rconv.bias.detach(), lrelu=True), 20, flush, stream)
+      ri_old_ms, _ = time_kernel(lambda: ops.refine_in_conv(cz, img2[:1], rconv.weight, rconv.bias.detach(), lrelu=True), 20, flush, stream)
+      rwimg = ops.refine_in_weights_ws(rconv.weight)
+      ri_ms, _ = time_kernel(lambda: ops.refine_in_conv_ws(cz, img2[:1], rwimg, rconv.bias.detach(), lrelu=True), 20, flush, stream)
       ri_bytes = 4 * H * W * (32 + 3 + 1)
 
     def hbm(ms, nbytes):
@@ -491,7 +493,8 @@ def gpu_arm(args):
       "head_tapsum_softargmin": dict(hbm(ts_ms, ts_bytes), note="inference head, kernel 2 of 2: 27-tap gather + softmax + expectation + cost volume"),
       "head_fused_one_kernel": dict(hbm(hd_ms, hd_bytes), note="training path: conv3d_alone + softmax + expectation + cost + FCS in ONE CUDA-core kernel"),
       "first_conv5x5s2_2images": tens(fc_ms, fc_flops),
-      "refine_in_conv": hbm(ri_ms, ri_bytes),
+      "refine_in_conv": dict(hbm(ri_ms, ri_bytes), note="inference: snb_refine_pack_input + snb_conv_c4_ws (two launches)"),
+      "refine_in_conv_im2col_training_path": hbm(ri_old_ms, ri_bytes),
     }
     # dominant kernel of the step = the 32->32 convolution (4 x 3-D filter + 6 x refinement launches per pair)
     dom_name = "filter_conv3d_32x32" if 4 * f3_ms >= 6 * r2_ms else "refine_conv2d_32x32_dil4"
