@@ -8,11 +8,13 @@ idx = {h: i for i, h in enumerate(hdr)}
 NAMES = [  # (key, substring of the demangled kernel name, occurrence selector among the launches in capture order)
   ("conv2d_ws_dil1", "conv_c32_ws_kernel<0", "big0"), ("conv2d_ws_dil4", "conv_c32_ws_kernel<0", "big1"),
   ("conv2d_ws_feature_block", "conv_c32_ws_kernel<0", "small"),
-  ("conv3d_ws", "conv_c32_ws_kernel<1", "last"), ("conv5x5s2_p4_ws", "conv_c32_ws_kernel<2", "last"),
+  ("conv3d_ws", "conv_c32_ws_kernel<1", "last"), ("conv5x5s2_p4_ws_big", "conv_c32_ws_kernel<2", "first"), ("conv5x5s2_p4_ws_strided", "conv_c32_ws_kernel<2", "last"),
   ("conv3d_tma_h_crosscheck", "conv3d_c32_tma_kernel", "last"),
   ("head_fused", "conv3d_out_softargmin_kernel", "last"),
   ("cost_volume_b1_direct", "cost_volume_fwd_direct_kernel", "last"), ("cost_volume_b8_staged", "cost_volume_fwd_kernel", "last"),
-  ("first_conv5x5s2", "conv_small_tc_kernel<3", "last"), ("refine_in_conv", "conv_small_tc_kernel<4", "last"),
+  ("first_conv5x5s2", "conv_small_tc_kernel<3", "last"), ("refine_in_conv_im2col", "conv_small_tc_kernel<4", "last"),
+  ("refine_in_pack", "refine_pack_input_kernel", "last"), ("refine_in_conv_c4_ws", "conv_c32_ws_kernel<3", "last"),
+  ("head_taps27", "conv_c32_taps_tc_kernel<27", "last"), ("head_tapsum_softargmin", "tapsum_softargmin_kernel", "last"),
   ("refine_out_taps9", "conv_c32_taps_tc_kernel", "last"), ("refine_out_tapsum", "tapsum_refine_out_kernel", "last"),
   ("upsample", "upsample_bilinear_kernel", "last"), ("wgrad_tc", "conv_c32_wgrad_tc_kernel", "wg"),
 ]
@@ -37,6 +39,8 @@ for key, sub, sel in NAMES:
   dur = lambda r: f(r, "gpu__time_duration.sum")
   if sel == "last":
     picks = [ls[-1]]
+  elif sel == "first":
+    picks = [ls[0]]
   elif sel == "small":
     picks = [min(ls, key=dur)]
   elif sel in ("big0", "big1"):
