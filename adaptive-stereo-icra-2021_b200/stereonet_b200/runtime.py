@@ -18,8 +18,10 @@ class StereoEngine:
     self.output_cost_volume = output_cost_volume
     self.use_graph = use_graph
     self._graphs = {}
+    self._pipes = {}
 
   def invalidate(self):
+    self.synchronize()
     self._graphs.clear()
 
   def _forward(self, pair):
@@ -36,8 +38,11 @@ class StereoEngine:
       fl, fr = feats[:B], feats[B:]
     return self.stereo_net(left, fl, fr, "l", output_cost_volume=self.output_cost_volume)
 
-  def _entry(self, shape, device):
-    key = (tuple(shape), str(device), self.feature_net.training)
+  def _entry(self, shape, device, slot=0):
+    """The captured forward for this input shape.  `slot` selects one of several independent captures (own static input and
+    output buffers): the streaming API alternates between two so that the copies of one frame never touch the buffers the
+    forward of its neighbour is using."""
+    key = (tuple(shape), str(device), self.feature_net.training, slot)
     e = self._graphs.get(key)
     if e is not None:
       if e["epoch"] == fused.state_epoch():
@@ -66,9 +71,9 @@ class StereoEngine:
     return e
 
   @torch.no_grad()
-  def run_static(self, shape, device):
+  def run_static(self, shape, device, slot=0):
     """Replay on whatever currently sits in the static input buffers. Returns (outputs dict, launches per step)."""
-    e = self._entry(shape, device)
+    e = self._entry(shape, device, slot)
     if e["graph"] is not None:
       e["graph"].replay()
       if self.feature_net.training:            # the replay updated BN running statistics behind Python's back: whatever was folded
@@ -100,49 +105,45 @@ class StereoEngine:
     return out_host
 
   # ------------------------------------------------------------------------------------------------ streaming API
-  def _pipe(self, e, dev):
-    p = e.get("pipe")
+  def _pipe(self, shape, dev):
+    p = self._pipes.get((tuple(shape), str(dev)))
     if p is None:
-      B2 = e["pair"].shape[0]
       key = "pred_disp_l/{}".format(self.stereo_net.input_scale)
       p = dict(i=0, key=key, s_in=torch.cuda.Stream(device=dev), s_out=torch.cuda.Stream(device=dev),
-               stage_in=[torch.empty_like(e["pair"]) for _ in range(2)],
-               stage_out=[torch.empty_like(e["out"][key]) for _ in range(2)],
                ev_in=[torch.cuda.Event() for _ in range(2)], ev_free=[torch.cuda.Event() for _ in range(2)],
                ev_out=[torch.cuda.Event() for _ in range(2)], ev_outfree=[torch.cuda.Event() for _ in range(2)])
       cur = torch.cuda.current_stream(dev)
       for k in range(2):
         p["ev_free"][k].record(cur); p["ev_outfree"][k].record(cur)
-      e["pipe"] = p
+      self._pipes[(tuple(shape), str(dev))] = p
     return p
 
   @torch.no_grad()
   def infer_host_async(self, left_host, right_host, out_host):
     """Streaming variant of infer_host for frame sequences: the H2D copy of frame i+1 (copy-in stream), the forward of
-    frame i (current stream, CUDA graph) and the D2H copy of frame i-1 (copy-out stream) overlap through double-buffered
-    device staging.  `out_host` is valid after `synchronize()`; the caller must not overwrite `left_host`/`right_host`
-    of a frame before the next-but-one call returns (or before `synchronize()`)."""
+    frame i (current stream, CUDA graph) and the D2H copy of frame i-1 (copy-out stream) overlap.  Two captures of the forward
+    alternate (slots 0 / 1): the host images land directly in a capture's static input and the disparity leaves directly from its
+    static output, so no device-to-device staging copy sits on the compute stream.  `out_host` is valid after `synchronize()`;
+    the caller must not overwrite `left_host`/`right_host` of a frame before the next-but-one call returns (or before
+    `synchronize()`)."""
     dev = next(self.stereo_net.parameters()).device
-    e = self._entry(left_host.shape, dev)
-    p = self._pipe(e, dev)
+    p = self._pipe(left_host.shape, dev)
     k = p["i"] & 1
-    B = left_host.shape[0]
+    e = self._entry(left_host.shape, dev, slot=k)
     cur = torch.cuda.current_stream(dev)
-    p["s_in"].wait_event(p["ev_free"][k])                 # staging k was consumed by the forward two frames ago
+    p["s_in"].wait_event(p["ev_free"][k])                 # capture k consumed its input two frames ago
     with torch.cuda.stream(p["s_in"]):
-      p["stage_in"][k][:B].copy_(left_host, non_blocking=True)
-      p["stage_in"][k][B:].copy_(right_host, non_blocking=True)
+      e["left"].copy_(left_host, non_blocking=True)
+      e["right"].copy_(right_host, non_blocking=True)
       p["ev_in"][k].record(p["s_in"])
     cur.wait_event(p["ev_in"][k])
-    e["pair"].copy_(p["stage_in"][k], non_blocking=True)  # device-to-device into the graph's static input
+    cur.wait_event(p["ev_outfree"][k])                    # the D2H of two frames ago has drained capture k's output
+    out, _ = self.run_static(left_host.shape, dev, slot=k)
     p["ev_free"][k].record(cur)
-    out, _ = self.run_static(left_host.shape, dev)
-    cur.wait_event(p["ev_outfree"][k])                    # the D2H of two frames ago has drained staging k
-    p["stage_out"][k].copy_(out[p["key"]], non_blocking=True)
     p["ev_out"][k].record(cur)
     p["s_out"].wait_event(p["ev_out"][k])
     with torch.cuda.stream(p["s_out"]):
-      out_host.copy_(p["stage_out"][k], non_blocking=True)
+      out_host.copy_(out[p["key"]], non_blocking=True)
       p["ev_outfree"][k].record(p["s_out"])
     p["i"] += 1
     return out_host
@@ -150,10 +151,8 @@ class StereoEngine:
   def synchronize(self):
     """Block the host until every copy issued by infer_host_async has completed: afterwards the `out_host` buffers are valid
     and the pinned input buffers may be overwritten.  (The current stream is also made to wait for the copy streams.)"""
-    for e in self._graphs.values():
-      p = e.get("pipe")
-      if p is not None:
-        dev = e["pair"].device
-        cur = torch.cuda.current_stream(dev)
-        cur.wait_stream(p["s_in"]); cur.wait_stream(p["s_out"])
-        p["s_in"].synchronize(); p["s_out"].synchronize()
+    for (_, devs), p in self._pipes.items():
+      dev = torch.device(devs)
+      cur = torch.cuda.current_stream(dev)
+      cur.wait_stream(p["s_in"]); cur.wait_stream(p["s_out"])
+      p["s_in"].synchronize(); p["s_out"].synchronize()
