@@ -286,7 +286,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[8] = t_w0 - t_entry; dd[9] = clock64() - t_w0; }
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sb_u32 = __shfl_sync(0xffffffffu, base_u32, 0) + NR * C::RAW_BYTES + 2 * C::NSTG * STG_BYTES;
-    long long tile_base = 0;
+    uint32_t tile_base = 0;                                        // (32-bit on purpose: these feed % and / on every tile)
     uint32_t win_count = 0;
     long long t_full = 0, t_tempty = 0; const long long t_mbegin = clock64();
     WS_FOR_STRIPS(sid) {
@@ -300,7 +300,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // MMA groups of this walk step, computed once: a group = (ring block of its first tile, weight row block, instruction
         // descriptor for N = 32 x #tiles).  FOLD: contiguous ring blocks form one group (two where the ring wraps); else one group
         // per tile.  `old` groups exclude the new tile u (first product of a new tile, see issue_fresh).
-        const int pos_lo = (int)((tile_base + jlo) % RING);
+        const int pos_lo = (int)((tile_base + (uint32_t)jlo) % RING);
         const int n_all = jhi - jlo + 1, n_old = has_new ? n_all - 1 : n_all;
         uint32_t g_d[3], g_b[3], g_i[3]; int ng;
         uint32_t go_d[2], go_b[2], go_i[2];
@@ -320,9 +320,9 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           go_d[0] = g_d[0]; go_b[0] = g_b[0]; go_i[0] = n_old > 0 ? idesc_n(1) : 0u;
           go_d[1] = g_d[1]; go_b[1] = g_b[1]; go_i[1] = n_old > 1 ? idesc_n(1) : 0u;
         }
-        const uint32_t new_d = (uint32_t)((tile_base + u) % RING) * 32;         // ring block of the new tile (weight row block 2: kz = 0)
+        const uint32_t new_d = ((tile_base + (uint32_t)u) % RING) * 32;         // ring block of the new tile (weight row block 2: kz = 0)
         if (has_new) {        // the epilogue must have drained the ring block of the new tile
-          const long long tc_new = tile_base + u;
+          const uint32_t tc_new = tile_base + (uint32_t)u;
           WSWAIT(t_tempty, mbar_wait_warp(&tempty[tc_new % RING], (uint32_t)(((tc_new / RING) & 1) ^ 1)));
           tc_fence_after();
         }
@@ -364,13 +364,13 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               else if (ng == 2) issue_window<MODE, 2, false, 2>(d1, d2, g_d, ta, img0, g_b, g_i);
               else issue_window<MODE, 3, false, 2>(d1, d2, g_d, ta, img0, g_b, g_i);
             }
-            if (win == NWIN - 1 && u >= 2) mma_commit_raw(&tfull[(tile_base + u - 2) % RING]);   // tile u-2 has all its kz taps
+            if (win == NWIN - 1 && u >= 2) mma_commit_raw(&tfull[(tile_base + (uint32_t)(u - 2)) % RING]);   // tile u-2 has all its kz taps
             mma_commit_raw(&aempty[aslot]);
           }
           __syncwarp();
         }
       }
-      tile_base += s.ntiles;
+      tile_base += (uint32_t)s.ntiles;
     }
     if (p.dbg && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[2] = t_full; dd[3] = t_tempty; dd[4] = clock64() - t_mbegin; }
     __syncwarp();
@@ -384,7 +384,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     long long w_rf = 0, w_ae = 0, w_rs = 0; const long long t0 = clock64();
     uint32_t cnt = 0;                                              // windows so far (all strips)
-    long long tile_base = 0;
+    uint32_t tile_base = 0;                                        // (32-bit on purpose: these feed % and / on every tile)
     WS_FOR_STRIPS(sid) {
       const Strip s = decode_strip<D3>(p, sid);
       if (s.ntiles == 0) continue;
@@ -401,7 +401,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           // 2-D: this window is the centre row (kz = 1) of tile j = u - 1: its un-shifted pixels are that tile's residual
           const bool centre = MODE == MODE_2D && p.res_mode == 1 && u >= 1 && u <= s.ntiles;
           const int nkw = C::nkw(win);
-          const long long tcount = tile_base + (u - 1);
+          const uint32_t tcount = tile_base + (uint32_t)(u - 1);   // (only used for 1 <= u <= ntiles)
           bool a_free = false;
           if (MODE == MODE_C4) {
             // four-channel rows: pixels m, m+1, m+2 are 48 contiguous bytes = the 12 used K values (k = kw*4 + ch) of ONE K = 16 slice
@@ -531,7 +531,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           if (lane == 0) mbar_arrive(&afull[aslot]);
         }
       }
-      tile_base += s.ntiles;
+      tile_base += (uint32_t)s.ntiles;
     }
     if (p.dbg && warp == CONV_WARP0 && lane == 0) { long long* dd = p.dbg + blockIdx.x * 16; dd[11] = w_rf; dd[12] = w_ae; dd[13] = clock64() - t0; dd[14] = w_rs; }
   } else {
@@ -558,7 +558,7 @@ conv_c32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint32_t ntile_g = 0;                                     // tiles this group has staged so far
     const int bar_id = 4 + egrp;
     asm volatile("bar.sync 6, 256;\n" ::: "memory");          // sPar (written by the first epilogue warp) is visible
-    long long tcount = 0;
+    uint32_t tcount = 0;
     long long t_tfull = 0, t_px = 0, t_out = 0, t_bar = 0, t_ld = 0, t_bar2 = 0; const long long t_ebegin = clock64();
     WS_FOR_STRIPS(sid) {
       const Strip s = decode_strip<D3>(p, sid);
