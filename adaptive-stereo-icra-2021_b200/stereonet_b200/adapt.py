@@ -37,6 +37,7 @@ class AdaptStepper:
     # statistics of both samples together, which is NOT what the reference's two batch-1 passes compute.
     self.batched_replay = batched_replay
     self.two_streams, self._side, self._wstream, self._acc_stream, self._acc_nodes = two_streams, None, None, None, None
+    self._rstream, self._rside = None, None
     self._graphs = {}
     self._wprep = None                      # fused.WeightPrepBatch: all derived weight images in one launch per step
     self.launches_per_step = None
@@ -62,17 +63,19 @@ class AdaptStepper:
     side = self._side
     side.wait_stream(main)
     fl = self.feature_net(left)
-    pending = []
+    outer = fused.DEFER_BN                     # not None when this whole pass already defers (the replay pass, below)
+    pending = outer if outer is not None else []
     with torch.cuda.stream(side):
       fused.DEFER_BN = pending
       try:
         fr = self.feature_net(right)
       finally:
-        fused.DEFER_BN = None
+        fused.DEFER_BN = outer
     main.wait_stream(side)
     if not torch.cuda.is_current_stream_capturing():
       fr.record_stream(main)
-    fused.flush_deferred_bn(pending)
+    if outer is None:
+      fused.flush_deferred_bn(pending)
     return self.stereo_net(left, fl, fr, "l", output_cost_volume=True)
 
   def step(self, left, right, replay=None, sync_grads=None, dp_params=None, dp_group=None, dp_bucket=None):
@@ -120,11 +123,38 @@ class AdaptStepper:
       fused.WGRAD_STREAM = self._wstream                                            # weight gradients next to the data path
       fused.wgrad_token((1,), left.device)                                          # (creates the token buffer outside any capture)
     try:
-      outputs = self.predict(left, right)
-      loss = monodepth_single_loss(left, right, outputs, s)                        # adapt.py:328-337 (snb_photo_loss)
-      if replay is not None:
-        out_er = self.predict(replay[0], replay[1])                                 # adapt.py:339-349: a second full pass
-        loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
+      if replay is not None and self.two_streams and left.is_cuda:
+        # The replay pass (adapt.py:339-349) is independent of the stream pass until the two losses are added: it runs on its own
+        # stream (its feature passes side by side on two more), with ALL its BatchNorm running-statistics updates deferred and
+        # applied after the stream pass's — the reference's order.
+        main = torch.cuda.current_stream(left.device)
+        if self._rstream is None:
+          self._rstream = torch.cuda.Stream(device=left.device)
+          self._rside = torch.cuda.Stream(device=left.device)
+        self._rstream.wait_stream(main)
+        outputs = self.predict(left, right)
+        loss = monodepth_single_loss(left, right, outputs, s)                      # adapt.py:328-337 (snb_photo_loss)
+        pend_r = []
+        side_main, self._side = self._side, self._rside
+        with torch.cuda.stream(self._rstream):
+          fused.DEFER_BN = pend_r
+          try:
+            out_er = self.predict(replay[0], replay[1])
+            loss_er = khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
+          finally:
+            fused.DEFER_BN = None
+            self._side = side_main
+        main.wait_stream(self._rstream)
+        if not torch.cuda.is_current_stream_capturing():
+          loss_er.record_stream(main)
+        fused.flush_deferred_bn(pend_r)
+        loss = loss + self.er_loss_weight * loss_er
+      else:
+        outputs = self.predict(left, right)
+        loss = monodepth_single_loss(left, right, outputs, s)                      # adapt.py:328-337 (snb_photo_loss)
+        if replay is not None:
+          out_er = self.predict(replay[0], replay[1])                               # adapt.py:339-349: a second full pass
+          loss = loss + self.er_loss_weight * khamis_robust_loss(out_er["pred_disp_l/{}".format(s)], replay[2])
     finally:
       fused.WGRAD_STREAM = None
     fcs = feature_contrast_mean(outputs["cost_volume_l/{}".format(s + self.stereo_net.k)]).mean()
